@@ -1,0 +1,190 @@
+/*
+ * mhentropy_b200 — C ABI of the B200-native multi-hypothesis hot path of GloryyrolG/MHEntropy.
+ *
+ * The reference (pure Python/PyTorch) has no FFI; its boundary for this path is the nn.Module API
+ * of RealNVP (hand/flows.py:125-362), ManoLayer (hand/ManoLayer.py:10-165,
+ * hand/manopth/manolayer.py:13-274) and the MHEnt loss glue (hand/network.py:455-831).  This
+ * header is what a binding for that boundary binds: every entry point names the reference code
+ * it replaces.  The Python drop-in (mhentropy_b200/*.py) calls exactly these symbols through
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 (unless noted) owned by the caller; the library
+ *     never allocates, never synchronises and keeps no global state besides the last-error text;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - return value 0 = ok, otherwise an mhe_status; mhe_last_error_string() has the detail;
+ *   - rows are hypothesis-major: row r = n*B + b  (reference network.py:734,747,793);
+ *   - "accumulate" outputs are added to (+=), everything else is overwritten.
+ */
+#ifndef MHENTROPY_B200_H
+#define MHENTROPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mhe_status {
+    MHE_OK = 0,
+    MHE_ERR_INVALID_ARG = 1,
+    MHE_ERR_WORKSPACE = 2,
+    MHE_ERR_CUDA = 3,
+    MHE_ERR_UNSUPPORTED = 4
+} mhe_status;
+
+const char* mhe_last_error_string(void);
+/* library version, and the compute capability the kernels were built for (100 = sm_100a) */
+int mhe_version(void);
+int mhe_built_for_sm(void);
+/* number of kernel launches enqueued by this process so far (bench.py's gpu_launches) */
+long long mhe_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Conditional RealNVP flow — reference hand/flows.py.
+ *
+ * Shape: dim D (45), hidden H (512, both hidden layers), cond C (512), layers L (12 = 2*num_steps).
+ * Parameters live in ONE flat fp32 buffer ("flat layout"), every segment aligned to 64 floats:
+ *   for layer i in [0,L), net n in {0 = s, 1 = t}:   block (i*2+n) at offset (i*2+n)*BLK
+ *        W0 [H][D]  (l.0.weight)   b0 [H]   W1 [H][H] (l.1.weight)   b1 [H]   W2 [D][H] (l.2.weight)   b2 [D]
+ *   then for idx = (i*2+n)*2+j, j in {0,1}:          Cw[idx] [H][C]  (c.j.weight)
+ *   then for the same idx:                           Cb[idx] [H]     (c.j.bias)
+ * (nn.Linear layouts, reference flows.py:83-93).  Gradients use the same layout.
+ * mhe_flow_param_offset() returns the float offset of a tensor; which = 0..5 for W0,b0,W1,b1,W2,b2
+ * and 6,7 / 8,9 for c.0.weight,c.0.bias / c.1.weight,c.1.bias.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mhe_flow_shape {
+    int dim;
+    int hidden;
+    int cond;
+    int layers;
+} mhe_flow_shape;
+
+size_t mhe_flow_param_floats(mhe_flow_shape s);
+size_t mhe_flow_param_offset(mhe_flow_shape s, int layer, int net, int which);
+/* floats per image of the hoisted conditioning projections: L*4*H */
+size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s);
+/* bytes of scratch needed by the flow passes over R rows (forward and backward) */
+size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R);
+
+/* Hoisted conditioning projections (reference flows.py:107-109 "Can be pre-processed"):
+ *   cp[b][idx][h] = sum_c feat[b][c]*Cw[idx][h][c] + Cb[idx][h] + b_j[h]      (b_j = l.j.bias folded in)
+ * feat [B][C] -> cp [B][L*4][H].                                                               */
+int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const float* feat, int B, float* cp, void* stream);
+/* dcp [B][L*4][H] -> dparams (accumulate: Cw, Cb, b0, b1 slots), dfeat [B][C] (overwritten; may be NULL) */
+int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const float* feat, const float* dcp, int B,
+                      float* dparams, float* dfeat, void* stream);
+
+/* One pass through the L coupling layers.
+ *   direction 0: z -> x, layers 0..L-1,  x' = m x + (1-m)(x e^s + t),  logdet += sum s   (flows.py:210-217)
+ *   direction 1: x -> z, layers L-1..0,  z' = (1-m)(z - t) e^-s + m z,  logdet -= sum s   (flows.py:219-227)
+ * in [R][D] -> out [R][D], logdet [R] (may be NULL).  Row r uses cp of image r % B.
+ * saved: NULL, or [(L+1)][R][D] receiving each layer's input (processing order) and the output —
+ * the only activations the backward needs (hidden activations are recomputed).                   */
+int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
+                      const float* in, int R, int B, int direction,
+                      float* out, float* logdet, float* saved,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* dout [R][D], dlogdet [R] (NULL = 0) -> din [R][D]; dparams (accumulate; W0,W1,W2,b2 slots),
+ * dcp [B][L*4][H] (accumulate).                                                                 */
+int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
+                      const float* saved, int R, int B, int direction,
+                      const float* dout, const float* dlogdet,
+                      float* din, float* dparams, float* dcp,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* log N(z; 0, I) + logdet per row (flows.py:320) and its gradient seeds:
+ *   fwd: logp[r] = -0.5|z_r|^2 - 0.5 D ln(2 pi) + logdet[r]   (logdet may be NULL)
+ *   bwd: dz[r][:] = -z[r][:] * dlogp[r]                                                          */
+int mhe_std_normal_logp_fwd(const float* z, const float* logdet, int R, int D, float* logp, void* stream);
+int mhe_std_normal_logp_bwd(const float* z, const float* dlogp, int R, int D, float* dz, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MANO layer — reference hand/manopth/manolayer.py:110-274 (use_pca, ncomps=45, axis-angle root,
+ * right hand, center_idx=9) and the wrapper's second joint set hand/ManoLayer.py:141-148.
+ * Constants (device, fp32), packed by the caller once:
+ *   comps [45][45] (th_selected_comps), hands_mean [45], v_template [778][3], shapedirs [778][3][10],
+ *   posedirs_t [135][2334] (th_posedirs transposed: k-major), jreg [16][778], weights [778][16],
+ *   jt [16][3] = jreg*v_template, js [16][3][10] = jreg*shapedirs.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mhe_mano_consts {
+    const float* comps;
+    const float* hands_mean;
+    const float* v_template;
+    const float* shapedirs;
+    const float* posedirs_t;
+    const float* jreg;
+    const float* weights;
+    const float* jt;
+    const float* js;
+} mhe_mano_consts;
+
+#define MHE_MANO_VERTS 778
+#define MHE_MANO_JOINTS 21
+/* joint_order: 0 = manopth order (manolayer.py:260); 1 = RHD order (ManoLayer.py:54-56, utils.py:15).
+ * mesh_grad != 0 sizes the scratch for a backward that receives dverts / djoints2.                 */
+size_t mhe_mano_workspace_bytes(int R, int mesh_grad);
+
+/* theta [R][ld_theta>=48], beta [R][ld_beta>=10] -> verts [R][778][3] mm (NULL = skip the mesh, only the
+ * 5 tip vertices are skinned), jtr [R][21][3] mm, joints2 [R][21][3] mm (wrapper's regressed set; NULL = skip;
+ * needs verts).  Nothing is saved for the backward: it recomputes from theta / beta.               */
+int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, const float* beta, int ld_beta,
+                 int R, int joint_order, float* verts, float* jtr, float* joints2,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* dverts / djtr / djoints2 (any may be NULL = 0) -> dtheta [R][ld_dtheta] (48 written), dbeta [R][ld_dbeta]
+ * (10 written).  accumulate != 0 adds into dtheta/dbeta instead of overwriting.                  */
+int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, const float* beta, int ld_beta,
+                 int R, int joint_order,
+                 const float* dverts, const float* djtr, const float* djoints2,
+                 float* dtheta, int ld_dtheta, float* dbeta, int ld_dbeta, int accumulate,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Reprojection + loss reductions — reference hand/network.py:466-514 (root 12 / bone 11 normalise,
+ * orthographic projection), :233-258 (Laplace, b const), :155-165 (box / ball priors),
+ * :612-667, :760-831 (N-means, entropy) and criteria.py:55,173 (mean_B of -log_p).
+ * z [R][61] = th3 | th45 | bt | logs | t (network.py:703-717); joints in RHD order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct mhe_loss_cfg {
+    float laplace_b;      /* 0.03  ho3d.yaml:44 */
+    float th45_box;       /* 2     network.py:427 */
+    float th45_alpha;     /* 50    ho3d.yaml:41 */
+    float th3_radius;     /* pi    network.py:431 */
+    float th3_alpha;      /* 5 */
+    float bt_box;         /* 0.03  network.py:433 */
+    float bt_alpha;       /* 50 */
+    int root_idx;         /* 12    network.py:478 */
+    int norm_idx;         /* 11    network.py:479 */
+} mhe_loss_cfg;
+
+/* z = combine(x_flow [R][45], z_det [B][16] = th3|bt|logs|t)  (network.py:703-717, 747) */
+int mhe_combine_z_fwd(const float* x_flow, const float* z_det, int R, int B, float* z, void* stream);
+/* dz [R][61] -> dx_flow [R][45] (overwritten), dz_det [B][16] (overwritten: sum over the hypotheses) */
+int mhe_combine_z_bwd(const float* dz, int R, int B, float* dx_flow, float* dz_det, void* stream);
+
+/* joints [R][21][3] (RHD order, mm), z [R][61], crop_uv [B][42], vis [B][21], log_q [R] ->
+ *   uv [R][42] (may be NULL), row_log_p [R] (Laplace + priors, network.py:662), and per image
+ *   log_p [B] = mean_n(-log_q) + mean_n(row_log_p), h [B], q_log_p [B] (any may be NULL),
+ *   loss [1] = mean_b(-log_p) (may be NULL).                                                    */
+int mhe_reproj_loss_fwd(const mhe_loss_cfg* cfg, const float* joints, const float* z, const float* crop_uv,
+                        const float* vis, const float* log_q, int R, int B,
+                        float* uv, float* row_log_p, float* log_p, float* h, float* q_log_p, float* loss,
+                        void* stream);
+/* dlog_p [B] (NULL: use dloss), dloss [1] device scalar (NULL = 1.0) ->
+ *   djoints [R][21][3], dz [R][61] (priors + camera terms; overwritten), dlog_q [R].               */
+int mhe_reproj_loss_bwd(const mhe_loss_cfg* cfg, const float* joints, const float* z, const float* crop_uv,
+                        const float* vis, int R, int B, const float* dlog_p, const float* dloss,
+                        float* djoints, float* dz, float* dlog_q, void* stream);
+
+/* xyz / verts normalisation and projection for MHEnt.sample (network.py:466-483, 497-514, 876-877):
+ * joints [R][21][3], verts [R][778][3] (NULL ok), logs_t = z[:, 58:61] with row stride ld_z ->
+ * xyz [R][21][3], verts_n [R][778][3], uv [R][21][2] (pixels when inv_norm != 0).                 */
+int mhe_normalize_project(const mhe_loss_cfg* cfg, const float* joints, const float* verts, const float* z,
+                          int ld_z, int R, int inv_norm, int image_size,
+                          float* xyz, float* verts_n, float* uv, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHENTROPY_B200_H */

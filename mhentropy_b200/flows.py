@@ -1,0 +1,357 @@
+"""Drop-in ``RealNVP`` — the reference's conditional flow (``hand/flows.py:125-362``) on the B200 kernels.
+
+Same constructor, methods, attributes and state-dict keys as the reference class, so
+``MHEnt`` (``hand/network.py:341,692,733``) and released checkpoints (``ent_ho3d.pth``) keep working:
+``t.{i}.l.{j}.*``, ``t.{i}.c.{j}.*``, ``s.…``, ``mask``.  The parameters are views into one flat fp32
+buffer (layout in ``include/mhentropy_b200.h``) that the CUDA kernels read directly; gradients come
+back in the same flat layout.
+
+The kernel path covers the configuration the reference ships (int ``tsfm_on`` = conditional flow,
+no ``kemb`` / partitioner, equal hidden widths, ``weights=None``).  Other constructor options keep
+their reference semantics through stock PyTorch ops (API coverage, not a fallback of the measured
+path).  CUDA tensors always take the kernel path and fail loudly if the library is missing.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import distributions
+
+from . import _lib
+from ._lib import FlowShape, check, lib, ptr, stream_ptr
+
+LEAKY_SLOPE = 0.01
+
+
+class _nets(nn.Module):
+    """Coupling MLP container (reference ``flows.py:75-122``): holds ``l.{0,1,2}`` and ``c.{0,1}``.
+
+    ``forward`` is the stock-PyTorch evaluation used only off the kernel path (CPU tensors or
+    unsupported configurations).
+    """
+
+    def __init__(self, dim, cond_dim=0, h_dims=(64, 64), s=True):
+        super().__init__()
+        self.cond_dim = cond_dim
+        self.s = s
+        self.l = nn.ModuleList([nn.Linear(dim, h_dims[0]), nn.Linear(h_dims[0], h_dims[1]), nn.Linear(h_dims[1], dim)])
+        if cond_dim:
+            self.c = nn.ModuleList([nn.Linear(cond_dim, h) for h in h_dims])
+
+    def forward(self, x, cond=None):
+        h = self.l[0](x)
+        for i in range(2):
+            if self.cond_dim > 0:
+                h = h + self.c[i](cond)
+            h = self.l[i + 1](F.leaky_relu(h, LEAKY_SLOPE))
+        return torch.tanh(h) if self.s else h
+
+
+_WHICH = {('l', 0, 'weight'): 0, ('l', 0, 'bias'): 1, ('l', 1, 'weight'): 2, ('l', 1, 'bias'): 3,
+          ('l', 2, 'weight'): 4, ('l', 2, 'bias'): 5, ('c', 0, 'weight'): 6, ('c', 0, 'bias'): 7,
+          ('c', 1, 'weight'): 8, ('c', 1, 'bias'): 9}
+
+
+class _GatherFlat(torch.autograd.Function):
+    """Autograd bridge: the 240 reference-named parameters <-> the flat buffer the kernels read."""
+
+    @staticmethod
+    def forward(ctx, flow, *params):
+        ctx.flow = flow
+        return flow._flat.detach()
+
+    @staticmethod
+    def backward(ctx, gflat):
+        return (None, *ctx.flow._split_flat(gflat))
+
+
+class _CondFn(torch.autograd.Function):
+    """cp = hoisted conditioning projections of every layer (``flows.py:107-109``)."""
+
+    @staticmethod
+    def forward(ctx, feat, flat, shape):
+        feat = feat.contiguous()
+        _lib.require_cuda_f32(feat, flat)
+        B = feat.shape[0]
+        cp = torch.empty(B, lib().mhe_flow_cp_floats_per_image(shape), device=feat.device, dtype=torch.float32)
+        check(lib().mhe_flow_cond_fwd(shape, ptr(flat), ptr(feat), B, ptr(cp), stream_ptr(feat.device)), 'mhe_flow_cond_fwd')
+        ctx.save_for_backward(feat, flat)
+        ctx.shape = shape
+        return cp
+
+    @staticmethod
+    def backward(ctx, dcp):
+        feat, flat = ctx.saved_tensors
+        dcp = dcp.contiguous()
+        dflat = torch.zeros_like(flat)
+        dfeat = torch.empty_like(feat) if ctx.needs_input_grad[0] else None
+        check(lib().mhe_flow_cond_bwd(ctx.shape, ptr(flat), ptr(feat), ptr(dcp), feat.shape[0], ptr(dflat), ptr(dfeat),
+                                      stream_ptr(feat.device)), 'mhe_flow_cond_bwd')
+        return dfeat, dflat, None
+
+
+class _FlowPassFn(torch.autograd.Function):
+    """One pass through the coupling layers; returns (out, logdet)."""
+
+    @staticmethod
+    def forward(ctx, inp, cp, flat, mask, shape, direction, B):
+        inp = inp.contiguous()
+        _lib.require_cuda_f32(inp, cp, flat, mask)
+        R, D = inp.shape
+        dev = inp.device
+        out = torch.empty_like(inp)
+        logdet = torch.empty(R, device=dev, dtype=torch.float32)
+        need_grad = any(ctx.needs_input_grad[:3])
+        saved = torch.empty((shape.layers + 1), R, D, device=dev, dtype=torch.float32) if need_grad else None
+        wsb = lib().mhe_flow_workspace_bytes(shape, R)
+        ws = _lib.WORKSPACE.get(wsb, dev)
+        check(lib().mhe_flow_pass_fwd(shape, ptr(flat), ptr(mask), ptr(cp), ptr(inp), R, B, direction, ptr(out), ptr(logdet),
+                                      ptr(saved), ptr(ws), wsb, stream_ptr(dev)), 'mhe_flow_pass_fwd')
+        if need_grad:
+            ctx.save_for_backward(cp, flat, mask, saved)
+        ctx.shape, ctx.direction, ctx.B = shape, direction, B
+        return out, logdet
+
+    @staticmethod
+    def backward(ctx, dout, dlogdet):
+        cp, flat, mask, saved = ctx.saved_tensors
+        shape = ctx.shape
+        R, D = saved.shape[1], saved.shape[2]
+        dev = saved.device
+        dout = torch.zeros(R, D, device=dev) if dout is None else dout.contiguous()
+        dlogdet = None if dlogdet is None else dlogdet.contiguous()
+        din = torch.empty(R, D, device=dev, dtype=torch.float32)
+        dflat = torch.zeros_like(flat)
+        dcp = torch.zeros_like(cp)
+        wsb = lib().mhe_flow_workspace_bytes(shape, R)
+        ws = _lib.WORKSPACE.get(wsb, dev)
+        check(lib().mhe_flow_pass_bwd(shape, ptr(flat), ptr(mask), ptr(cp), ptr(saved), R, ctx.B, ctx.direction, ptr(dout),
+                                      ptr(dlogdet), ptr(din), ptr(dflat), ptr(dcp), ptr(ws), wsb, stream_ptr(dev)),
+              'mhe_flow_pass_bwd')
+        return din, dcp, dflat, None, None, None, None
+
+
+class _StdNormalLogpFn(torch.autograd.Function):
+    """log N(z; 0, I) + logdet (``flows.py:320``)."""
+
+    @staticmethod
+    def forward(ctx, z, logdet):
+        z = z.contiguous()
+        logdet = logdet.contiguous()
+        _lib.require_cuda_f32(z, logdet)
+        R, D = z.shape
+        logp = torch.empty(R, device=z.device, dtype=torch.float32)
+        check(lib().mhe_std_normal_logp_fwd(ptr(z), ptr(logdet), R, D, ptr(logp), stream_ptr(z.device)), 'mhe_std_normal_logp_fwd')
+        ctx.save_for_backward(z)
+        return logp
+
+    @staticmethod
+    def backward(ctx, dlogp):
+        (z,) = ctx.saved_tensors
+        dlogp = dlogp.contiguous()
+        dz = torch.empty_like(z)
+        check(lib().mhe_std_normal_logp_bwd(ptr(z), ptr(dlogp), z.shape[0], z.shape[1], ptr(dz), stream_ptr(z.device)),
+              'mhe_std_normal_logp_bwd')
+        return dz, dlogp
+
+
+class RealNVP(nn.Module):
+    """Conditional RealNVP, API-compatible with reference ``flows.RealNVP`` (``flows.py:125-362``)."""
+
+    def __init__(self, nets=_nets, nett=_nets, mask=None, prior=None, dim=63, tsfm_on=None, kemb=False, jointN=21,
+                 h_dims=(64, 64), num_steps=3, cond_mapping_dims=None):
+        super().__init__()
+        if dim == 1:
+            raise ValueError
+        if kemb:
+            raise NotImplementedError('kemb (joint-independent embeddings) is outside the accelerated path')
+        self.dim = dim
+        self.jointN = jointN
+        if mask is None:
+            a = [0] * (dim // 2) + [1] * (dim - dim // 2)
+            b = [1 - v for v in a]
+            mask = torch.from_numpy(np.array([a, b] * num_steps).astype(np.float32))   # flows.py:152-155
+        if prior is None:
+            prior = distributions.MultivariateNormal(torch.zeros(dim), torch.eye(dim))   # flows.py:156-157
+        self.tsfm_on = tsfm_on
+        cond_dim = tsfm_on if type(tsfm_on) == int else 0
+        partitioner = nn.ModuleList()
+        for in_f, out_f in (cond_mapping_dims or []):
+            assert out_f % jointN == 0
+            partitioner.append(nn.Linear(in_f, out_f))
+        self.joint_feat_partitioner = partitioner
+        self.prior = prior
+        self.register_buffer('mask', mask)
+        h_dims = list(h_dims)
+        self.t = nn.ModuleList([nett(dim, cond_dim=cond_dim, h_dims=h_dims, s=False) for _ in range(len(mask))])
+        self.s = nn.ModuleList([nets(dim, cond_dim=cond_dim, h_dims=h_dims) for _ in range(len(mask))])
+        self.scale = 1.
+        self.h_dims = h_dims
+        self.cond_dim = cond_dim
+        self._kernel_ok = (cond_dim > 0 and len(h_dims) == 2 and h_dims[0] == h_dims[1] and 2 <= dim <= 64
+                           and len(partitioner) == 0 and nets is _nets and nett is _nets)
+        self._shape = FlowShape(dim, h_dims[0], cond_dim, len(mask)) if self._kernel_ok else None
+        self._flat = None
+        self._slots = None
+
+    # ------------------------------------------------------------------ flat parameter storage
+    def _named_flow_params(self):
+        for net_id, name in ((0, 's'), (1, 't')):
+            for i, net in enumerate(getattr(self, name)):
+                for kind in ('l', 'c'):
+                    for j, lin in enumerate(getattr(net, kind)):
+                        for pname in ('weight', 'bias'):
+                            yield (i, net_id, _WHICH[(kind, j, pname)]), getattr(lin, pname)
+
+    def _adopt(self, device):
+        """Move every parameter into one flat buffer on ``device``; parameters become views of it."""
+        shape = self._shape
+        total = lib().mhe_flow_param_floats(shape)
+        flat = torch.zeros(total, device=device, dtype=torch.float32)
+        slots = []
+        for (i, n, which), p in self._named_flow_params():
+            off = lib().mhe_flow_param_offset(shape, i, n, which)
+            view = flat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            slots.append((p, off, p.numel(), tuple(p.shape)))
+        self._flat, self._slots = flat, slots
+
+    def _flat_is_current(self, device) -> bool:
+        if self._flat is None or self._flat.device != device:
+            return False
+        base = self._flat.data_ptr()
+        for p, off, _, _ in (self._slots[0], self._slots[len(self._slots) // 2], self._slots[-1]):
+            if p.data_ptr() != base + 4 * off:
+                return False
+        return True
+
+    def flat_parameters(self, device=None) -> torch.Tensor:
+        """The flat fp32 parameter buffer the kernels read (adopting the parameters if needed)."""
+        device = torch.device(device) if device is not None else self.mask.device
+        if not self._flat_is_current(device):
+            self._adopt(device)
+        return self._flat
+
+    def _split_flat(self, gflat):
+        return [gflat[off:off + n].view(shape) for _, off, n, shape in self._slots]
+
+    def _flat_for_autograd(self, device):
+        flat = self.flat_parameters(device)
+        params = [p for p, _, _, _ in self._slots]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _GatherFlat.apply(self, *params)
+        return flat
+
+    def _use_kernels(self, x) -> bool:
+        if x.is_cuda:
+            if not self._kernel_ok:
+                raise _lib.MheError('this RealNVP configuration is outside the accelerated path; run it on CPU tensors '
+                                    'through the stock implementation or use the shipped configuration')
+            return True
+        return False
+
+    # ------------------------------------------------------------------ reference API
+    def cond_projections(self, cond):
+        """Hoisted ``c.{0,1}(cond)`` of all layers, (B, L*4*H); kernel path only."""
+        flat = self._flat_for_autograd(cond.device)
+        return _CondFn.apply(cond.float(), flat, self._shape)
+
+    def _pass(self, inp, cond, direction, cp=None, images=None):
+        flat = self._flat_for_autograd(inp.device)
+        if cp is None:
+            cp = _CondFn.apply(cond.float(), flat, self._shape)
+            images = cond.shape[0]
+        return _FlowPassFn.apply(inp.float(), cp, flat, self.mask, self._shape, direction, images)
+
+    def forward_p(self, z, cond=None):
+        """z -> x (``flows.py:210-217``)."""
+        if self._use_kernels(z):
+            return self._pass(z, cond, 0)[0]
+        x = z
+        for i in range(len(self.t)):
+            x_ = x * self.mask[i]
+            s = self.s[i](x_, cond=cond) * (1 - self.mask[i])
+            t = self.t[i](x_, cond=cond) * (1 - self.mask[i])
+            x = x_ + (1 - self.mask[i]) * (x * torch.exp(s) + t)
+        return x
+
+    def backward_p(self, x, cond=None):
+        """x -> (z, log|det|) (``flows.py:219-227``)."""
+        if self._use_kernels(x):
+            return self._pass(x, cond, 1)
+        log_det, z = x.new_zeros(x.shape[0]), x
+        for i in reversed(range(len(self.t))):
+            z_ = self.mask[i] * z
+            s = self.s[i](z_, cond=cond) * (1 - self.mask[i])
+            t = self.t[i](z_, cond=cond) * (1 - self.mask[i])
+            z = (1 - self.mask[i]) * (z - t) * torch.exp(-s) + z_
+            log_det = log_det - s.sum(dim=1)
+        return z, log_det
+
+    def make_cond(self, feat):
+        """``flows.py:229-269`` for the supported case (no kemb, no partitioner): a reshape."""
+        bs = feat.shape[0]
+        bs1 = bs * self.jointN if self.dim in [2, 3] else bs
+        if self.dim <= 3 and len(self.joint_feat_partitioner):
+            raise NotImplementedError('joint feature partitioner is outside the accelerated path')
+        return feat.reshape(bs1, -1)
+
+    def log_prob(self, x, mu=None, logvar=None, return_dict=False, weights=None, return_z=False):
+        """``flows.py:271-331``.  ``logvar`` carries the features when ``tsfm_on`` is an int.
+
+        Extension: ``logvar`` may hold one feature row per image, (B, F), while ``x`` holds R = S*B
+        hypothesis-major rows (row r belongs to image r % B); the conditioning is then projected once
+        per image instead of once per row.  With R rows of features (the reference's
+        ``feat.repeat(N, 1)``) the behaviour is the reference's.
+        """
+        if type(self.tsfm_on) != int:
+            raise NotImplementedError("tsfm_on in {'x','z',None} is outside the accelerated path")
+        if weights is not None and bool((1 - weights.float()).count_nonzero()):
+            raise NotImplementedError       # flows.py:284-285
+        bs = x.shape[0]
+        x = x.reshape(-1, self.dim) / self.scale
+        cond = self.make_cond(logvar)
+        if self._use_kernels(x):
+            z, logdet = self._pass(x, cond, 1)
+            loss = _StdNormalLogpFn.apply(z, logdet).view(bs, -1).sum(1)
+        else:
+            z, logdet = self.backward_p(x, cond=cond)
+            loss = (-0.5 * (z * z).sum(-1) - 0.5 * self.dim * math.log(2 * math.pi) + logdet).view(bs, -1).sum(1)
+        if return_z:
+            return z, loss
+        if return_dict:
+            return {'loss': loss}
+        return loss
+
+    def sample(self, batchSize, temp=0.7, mu=None, logvar=None, return_z=False, z0=None):
+        """``flows.py:333-359``.  ``z0`` (extension) supplies the prior draw instead of sampling it here."""
+        if type(self.tsfm_on) != int:
+            raise NotImplementedError("tsfm_on in {'x','z',None} is outside the accelerated path")
+        if z0 is None:
+            z0 = self.prior.sample((batchSize,)).to(logvar.device) * temp     # flows.py:339
+        z = z0
+        cond = self.make_cond(logvar)
+        x = self.forward_p(z, cond=cond) * self.scale
+        bs = logvar.shape[0] if self.dim in [2, 3] else z0.shape[0]
+        if return_z:
+            return x.view(bs, -1), z0.view(bs, -1)
+        return x.view(bs, -1)
+
+    def sample_with_log_prob(self, feat, z0, S):
+        """Fused extension: x = flow(z0 | feat) and log q(x | feat) from ONE pass (SURVEY.md §4 identity).
+
+        feat (B, F) one row per image; z0 (S*B, dim) hypothesis-major.  Returns x (S*B, dim), log_q (S*B,).
+        """
+        flat = self._flat_for_autograd(z0.device)
+        cp = _CondFn.apply(feat.float(), flat, self._shape)
+        x, logdet = _FlowPassFn.apply(z0.float(), cp, flat, self.mask, self._shape, 0, feat.shape[0])
+        log_q = _StdNormalLogpFn.apply(z0.float(), -logdet)
+        return x * self.scale, log_q
+
+    def forward(self, x):
+        return self.log_prob(x)
