@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the MHEntropy multi-hypothesis hot path on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one fused training step from the image feature on, for B images x S hypotheses:
+hoisted conditioning, flow sample + log q (entropy), z assembly, MANO, visible-2D reprojection + priors,
+N-means, loss, and the full backward (flow weights, feature, det-head outputs).  N = 1 runs BASELINE.json
+configs[1] (B=64, S=10); N > 1 keeps 64 images per GPU (weak scaling) and all-reduces the flat gradient and
+the loss over NCCL inside the timed region.  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the reference's CPU PyTorch algorithm for the same step (the oracle port in
+oracle/, two flow passes + autograd exactly as hand/network.py does) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'hypotheses/sec (flow+MANO fwd+bwd)'
+UNIT = 'hypotheses/s'
+
+# algorithmic FLOP per hypothesis (SURVEY.md §8d / BASELINE.md §4)
+FLOW_PASS_FLOP = 14_794_752
+COND_FLOP_PER_IMAGE = 25_165_824
+MANO_FWD_FLOP = 1_255_950
+
+
+def train_step_flop_per_hyp(S: int) -> float:
+    return 3 * (FLOW_PASS_FLOP + MANO_FWD_FLOP) + 3 * COND_FLOP_PER_IMAGE / S
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'bf16_tflops_sustained': d['bf16_tflops_sustained'],
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['nvml unavailable']}
+        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(B: int, S: int, steps: int, warmup: int, budget_s: float):
+    """The reference's algorithm for the step on the host cores (oracle port, torch CPU, all threads)."""
+    from mhentropy_b200.mano_assets import synthetic_mano
+    from mhentropy_b200.synthetic import synthetic_batch
+    from oracle import flow_oracle as fo, loss_oracle as lo, mano_oracle as mo
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = fo.init_state_dict(seed=0)
+    sdg = {k: v.clone().requires_grad_(k != 'mask') for k, v in sd.items()}
+    c = mo.mano_constants(synthetic_mano(0))
+    batch = synthetic_batch(B, S, seed=0)
+
+    def step():
+        for v in sdg.values():
+            v.grad = None
+        feat = batch['feat'].clone().requires_grad_(True)
+        zd = batch['z_det'].clone().requires_grad_(True)
+        out = lo.reverse_kld(sdg, c, feat, zd, batch['z0'], batch['crop_uv'], batch['vis'], S)
+        loss = lo.mhent_loss(out['log_p'])
+        loss.backward()
+        return float(loss)
+
+    t_start = time.perf_counter()
+    for _ in range(max(warmup, 1)):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 3:
+            break
+    total = sum(times)
+    return {'value': B * S * len(times) / total, 'steps': len(times), 'ms_per_step': 1e3 * total / len(times), 'cores': cores}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    B, S = args.batch, args.hyp
+    r = cpu_reference_run(B, S, args.steps, args.warmup, budget_s=150.0)
+    sample = f'{r["steps"]} full steps of B={B} x S={S} (fwd+bwd), torch CPU fp32, {r["cores"]} threads'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': r['steps'],
+        'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'training step B={B} x S={S} hypotheses (BASELINE configs[1]): flow sample+log_prob, MANO, '
+                               'visible-2D + entropy loss fwd+bwd', 'images_per_gpu': B, 'hypotheses': S},
+        'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': sample},
+        'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from mhentropy_b200 import MHEntHead, _lib
+    from mhentropy_b200.engine import TrainStep
+    from mhentropy_b200.mano_assets import synthetic_mano
+    from mhentropy_b200.synthetic import synthetic_batch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the product path has no CPU fallback); '
+                         'use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B, S = args.batch, args.hyp
+    R = B * S
+    L = _lib.lib()
+
+    torch.manual_seed(0)
+    head = MHEntHead(mano_data=synthetic_mano(0)).to(dev)       # random-init flow weights (seed 0), synthetic MANO
+    for p in head.parameters():
+        p.requires_grad_(True)
+    # every rank draws its own images; inputs start in pinned host memory for the e2e leg
+    batch = synthetic_batch(B, S, seed=1000 + rank)
+    host = {k: v.pin_memory() for k, v in batch.items()}
+    devb = {k: v.to(dev) for k, v in batch.items()}
+    h2d_bytes = sum(v.numel() * 4 for v in batch.values())
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def allreduce(engine):
+        if world > 1:
+            dist.all_reduce(engine.dflat)
+            dist.all_reduce(engine.loss)
+
+    # ---------------- value: inputs resident in HBM, fused engine (CUDA graph) ----------------
+    eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=not args.no_graph)
+    eng.load(**devb)
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        eng.run()
+        allreduce(eng)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = L.mhe_kernel_launch_count()
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        for a, b in ev:
+            flush.zero_()                    # evict weights/activations from L2 between timed steps
+            a.record()
+            eng.run()
+            allreduce(eng)
+            b.record()
+        torch.cuda.synchronize()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms)
+    launches_per_step = eng.launches_per_step
+    value = world * R * args.steps / (total_ms * 1e-3)
+
+    # ---------------- e2e: public API (MHEntHead.get_loss + autograd), host buffers in the timed region --------
+    def e2e_step():
+        feat = host['feat'].to(dev, non_blocking=True).requires_grad_(True)
+        z_det = host['z_det'].to(dev, non_blocking=True).requires_grad_(True)
+        z0 = host['z0'].to(dev, non_blocking=True)
+        y = {'crop_uv': host['crop_uv'].to(dev, non_blocking=True), 'vis': host['vis'].to(dev, non_blocking=True)}
+        head.zero_grad(set_to_none=True)
+        out = head.get_loss(feat, y, z0=z0, z_det=z_det, N=S, want_verts=True)
+        loss = (-out['log_p']).mean()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(head.q_z_giv_i._last_flat_grad)
+        return loss.item()                   # device -> host read of the step's result
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = args.steps
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * e2e_steps / (float(e2e_ms) * 1e-3)
+
+    # ---------------- roofline of the dominant kernel: the 512x512 coupling GEMMs, timed live with events -------
+    peaks = measured_peaks()
+    roof = None
+    if rank == 0:
+        probe_eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=False)
+        probe_eng.load(**devb)
+        tags = [b'flow G1', b'dgrad G1', b'wgrad W1']
+        tot_ms, tot_n = 0.0, 0
+        import ctypes
+        for tag in tags:
+            _lib.check(L.mhe_probe_configure(tag, 4096), 'probe')
+            for _ in range(3):
+                flush.zero_()
+                probe_eng.run()
+            torch.cuda.synchronize()
+            L.mhe_probe_reset()
+            for _ in range(5):
+                flush.zero_()
+                probe_eng.run()
+            ms, n = ctypes.c_float(), ctypes.c_int()
+            _lib.check(L.mhe_probe_read(ctypes.byref(ms), ctypes.byref(n)), 'probe read')
+            tot_ms += ms.value
+            tot_n += n.value
+        L.mhe_probe_configure(None, 0)
+        H = 512
+        flop_per_launch = 2.0 * R * H * H * 2           # both nets of one layer, one 512x512 contraction over R rows
+        avg_ms = tot_ms / max(tot_n, 1)
+        achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'kernel': 'sgemm_kernel (512x512 coupling-layer contractions: fwd, dgrad, wgrad)',
+                'achieved': achieved, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'peak_source': f'{peaks["source"]} bf16 dense sustained', 'launches_timed': tot_n, 'avg_launch_us': avg_ms * 1e3,
+                'share_of_step': (tot_ms / 5) / (total_ms / args.steps),
+                'note': 'fp32 CUDA-core path (parity mode); judged against the bf16 tensor peak with the 1x algorithmic FLOP count'}
+        flop_step = train_step_flop_per_hyp(S) * R
+        weight_bytes = 20_030_520 * 4
+        roof_step = {'algorithmic_gflop': flop_step / 1e9, 't_tensor_us': flop_step / (peaks['bf16_tflops_sustained'] * 1e12) * 1e6,
+                     't_hbm_us': (3 * weight_bytes + R * 9_336) / (peaks['hbm_gbs'] * 1e9) * 1e6,
+                     'measured_us': total_ms / args.steps * 1e3}
+        roof_step['frac_of_governing'] = max(roof_step['t_tensor_us'], roof_step['t_hbm_us']) / roof_step['measured_us']
+
+    # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(B, S, steps=10, warmup=2, budget_s=25.0)
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+               'sample': f'{r["steps"]} full steps of B={B} x S={S} fwd+bwd (oracle port of the reference algorithm, torch CPU fp32)'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'training step B={B} x S={S} hypotheses per GPU (BASELINE configs[1]): flow sample+log_prob, '
+                                   'MANO (778-vertex mesh fwd), visible-2D + entropy loss, fwd+bwd'
+                                   + (', NCCL allreduce of the flat gradient' if world > 1 else ''),
+                       'images_per_gpu': B, 'hypotheses': S, 'rows_per_gpu': R, 'l2': 'flushed (256 MiB write) before every timed step',
+                       'launch': 'CUDA graph' if not args.no_graph else 'stream', 'parallelism': f'dp{world}'},
+            'clocks': clocks.summary(),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4,
+                    'api': 'MHEntHead.get_loss + autograd backward, pinned host inputs, loss.item()'},
+            'gpu_launches': int(launches_per_step) * args.steps,
+            'gpu_launches_per_step': int(launches_per_step),
+            'roofline': roof, 'step_roofline': roof_step, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='images per GPU')
+    ap.add_argument('--hyp', type=int, default=10, help='hypotheses per image')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -40,6 +40,13 @@ int mhe_version(void);
 int mhe_built_for_sm(void);
 /* number of kernel launches enqueued by this process so far (bench.py's gpu_launches) */
 long long mhe_kernel_launch_count(void);
+/* Timing probe for measurement only: CUDA events are recorded on the launching stream around every
+ * GEMM launch whose label contains `tag` (e.g. "flow G1", "dgrad G1", "wgrad W1"), up to max_launches
+ * pairs; mhe_probe_read() synchronises on them and returns the summed duration and the launch count.
+ * mhe_probe_configure(NULL, 0) switches it off (the default).                                     */
+int mhe_probe_configure(const char* tag, int max_launches);
+int mhe_probe_reset(void);
+int mhe_probe_read(float* total_ms, int* launches);
 
 /* ------------------------------------------------------------------------------------------
  * Conditional RealNVP flow — reference hand/flows.py.
@@ -86,18 +93,18 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, 
                       const float* in, int R, int B, int direction,
                       float* out, float* logdet, float* saved,
                       void* workspace, size_t workspace_bytes, void* stream);
-/* dout [R][D], dlogdet [R] (NULL = 0) -> din [R][D]; dparams (accumulate; W0,W1,W2,b2 slots),
- * dcp [B][L*4][H] (accumulate).                                                                 */
+/* dout [R][D], dlogdet [R] (NULL = 0; multiplied by dlogdet_scale, so -1 turns dL/dlog_q of the fused
+ * sampler into dL/dlogdet) -> din [R][D]; dparams (accumulate; W0,W1,W2,b2 slots), dcp [B][L*4][H] (accumulate). */
 int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
                       const float* saved, int R, int B, int direction,
-                      const float* dout, const float* dlogdet,
+                      const float* dout, const float* dlogdet, float dlogdet_scale,
                       float* din, float* dparams, float* dcp,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* log N(z; 0, I) + logdet per row (flows.py:320) and its gradient seeds:
- *   fwd: logp[r] = -0.5|z_r|^2 - 0.5 D ln(2 pi) + logdet[r]   (logdet may be NULL)
+ *   fwd: logp[r] = -0.5|z_r|^2 - 0.5 D ln(2 pi) + logdet_sign*logdet[r]   (logdet may be NULL)
  *   bwd: dz[r][:] = -z[r][:] * dlogp[r]                                                          */
-int mhe_std_normal_logp_fwd(const float* z, const float* logdet, int R, int D, float* logp, void* stream);
+int mhe_std_normal_logp_fwd(const float* z, const float* logdet, float logdet_sign, int R, int D, float* logp, void* stream);
 int mhe_std_normal_logp_bwd(const float* z, const float* dlogp, int R, int D, float* dz, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -38,6 +38,9 @@ _SIGNATURES = {
     'mhe_version': (c_int, []),
     'mhe_built_for_sm': (c_int, []),
     'mhe_kernel_launch_count': (c_longlong, []),
+    'mhe_probe_configure': (c_int, [c_char_p, c_int]),
+    'mhe_probe_reset': (c_int, []),
+    'mhe_probe_read': (c_int, [POINTER(c_float), POINTER(c_int)]),
     'mhe_flow_param_floats': (c_size_t, [FlowShape]),
     'mhe_flow_param_offset': (c_size_t, [FlowShape, c_int, c_int, c_int]),
     'mhe_flow_cp_floats_per_image': (c_size_t, [FlowShape]),
@@ -45,8 +48,8 @@ _SIGNATURES = {
     'mhe_flow_cond_fwd': (c_int, [FlowShape, _P, _P, c_int, _P, _P]),
     'mhe_flow_cond_bwd': (c_int, [FlowShape, _P, _P, _P, c_int, _P, _P, _P]),
     'mhe_flow_pass_fwd': (c_int, [FlowShape, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
-    'mhe_flow_pass_bwd': (c_int, [FlowShape, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
-    'mhe_std_normal_logp_fwd': (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    'mhe_flow_pass_bwd': (c_int, [FlowShape, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    'mhe_std_normal_logp_fwd': (c_int, [_P, _P, c_float, c_int, c_int, _P, _P]),
     'mhe_std_normal_logp_bwd': (c_int, [_P, _P, c_int, c_int, _P, _P]),
     'mhe_mano_workspace_bytes': (c_size_t, [c_int, c_int]),
     'mhe_mano_fwd': (c_int, [POINTER(ManoConsts), _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),

@@ -31,6 +31,15 @@ inline int check_launch(const char* what) {
     return MHE_OK;
 }
 
+// Optional timing probe (bench.py's roofline leg): CUDA events around every launch whose label contains
+// the configured substring, recorded on the launching stream.
+struct ProbeScope {
+    bool on;
+    cudaStream_t stream;
+    ProbeScope(const char* what, cudaStream_t s);
+    ~ProbeScope();
+};
+
 #define MHE_TRY(expr)                      \
     do {                                   \
         int _st = (expr);                  \

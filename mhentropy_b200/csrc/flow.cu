@@ -83,7 +83,7 @@ __global__ void coupling_fwd_kernel(const float* __restrict__ x, const float* __
 //   dpre[2][R][D]: gradient at the pre-activation of the output heads (s before tanh, t), zero on passive dims
 //   gx[R][D]: dL/dx without the path through the nets (added later by the dgrad of layer 0)
 __global__ void coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ mask,
-                                    const float* g, const float* __restrict__ gl, int R, int D, int direction,
+                                    const float* g, const float* __restrict__ gl, float gl_scale, int R, int D, int direction,
                                     float* __restrict__ dpre, float* gx) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)R * D) return;
@@ -97,7 +97,7 @@ __global__ void coupling_bwd_kernel(const float* __restrict__ x, const float* __
         return;
     }
     const float s = st[i], t = st[(long)R * D + i], xv = x[i];
-    const float glv = gl ? gl[r] : 0.f;
+    const float glv = gl ? gl_scale * gl[r] : 0.f;
     float ds, dt, dx;
     if (direction == 0) {
         const float e = expf(s);
@@ -140,14 +140,14 @@ __global__ void hyp_sum_kernel(const float* __restrict__ in, int R, int B, int N
     dcp[(long)b * cp_ld + off + (long)z * zstride + n] += acc;
 }
 
-__global__ void std_normal_logp_fwd_kernel(const float* __restrict__ z, const float* __restrict__ logdet, int R, int D, float* __restrict__ logp) {
+__global__ void std_normal_logp_fwd_kernel(const float* __restrict__ z, const float* __restrict__ logdet, float sign, int R, int D, float* __restrict__ logp) {
     const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (r >= R) return;
     float ss = 0.f;
     for (int d = lane; d < D; d += 32) { const float v = z[(long)r * D + d]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
-    if (lane == 0) logp[r] = -0.5f * ss - 0.5f * D * 1.8378770664093453f + (logdet ? logdet[r] : 0.f);
+    if (lane == 0) logp[r] = -0.5f * ss - 0.5f * D * 1.8378770664093453f + (logdet ? sign * logdet[r] : 0.f);
 }
 __global__ void std_normal_logp_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dlogp, int R, int D, float* __restrict__ dz) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,8 +300,9 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, 
                       float* out, float* logdet, float* saved,
                       void* workspace, size_t workspace_bytes, void* stream_) {
     MHE_REQUIRE(valid_shape(s), "pass_fwd: bad shape");
-    MHE_REQUIRE(params && mask && cp && in && out && workspace, "pass_fwd: null pointer");
     MHE_REQUIRE(R >= 0 && B > 0 && direction >= 0 && direction <= 1, "pass_fwd: bad R/B/direction");
+    if (R == 0) return MHE_OK;
+    MHE_REQUIRE(params && mask && cp && in && out && workspace, "pass_fwd: null pointer");
     if (workspace_bytes < mhe_flow_workspace_bytes(s, R)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
     FlowLayout L(s);
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -332,12 +333,13 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, 
 
 int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
                       const float* saved, int R, int B, int direction,
-                      const float* dout, const float* dlogdet,
+                      const float* dout, const float* dlogdet, float dlogdet_scale,
                       float* din, float* dparams, float* dcp,
                       void* workspace, size_t workspace_bytes, void* stream_) {
     MHE_REQUIRE(valid_shape(s), "pass_bwd: bad shape");
-    MHE_REQUIRE(params && mask && cp && saved && dout && din && dparams && dcp && workspace, "pass_bwd: null pointer");
     MHE_REQUIRE(R >= 0 && B > 0 && direction >= 0 && direction <= 1, "pass_bwd: bad R/B/direction");
+    if (R == 0) return MHE_OK;
+    MHE_REQUIRE(params && mask && cp && saved && dout && din && dparams && dcp && workspace, "pass_bwd: null pointer");
     if (workspace_bytes < mhe_flow_workspace_bytes(s, R)) { set_error("pass_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
     FlowLayout L(s);
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -355,7 +357,7 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, 
         MHE_TRY(layer_nets_fwd(L, params, mrow, cp, x, R, B, layer, ws, stream));  // recompute a0, a1, st
         // gradient wrt this layer's input is built in din when it is the final result, else in ws.gx
         float* gx = (step == 0) ? din : ws.gx;
-        coupling_bwd_kernel<<<cdiv((int)RD, 256), 256, 0, stream>>>(x, ws.st, mrow, g, dlogdet, R, L.D, direction, ws.dpre, gx);
+        coupling_bwd_kernel<<<cdiv((int)RD, 256), 256, 0, stream>>>(x, ws.st, mrow, g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dpre, gx);
         MHE_TRY(check_launch("coupling bwd"));
         {   // dgrad G2: dh1 = (dpre W2) * lrelu'(a1)
             GemmArgs a; a.A = ws.dpre; a.lda = L.D; a.strideA = RD;
@@ -418,14 +420,16 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, 
     return MHE_OK;
 }
 
-int mhe_std_normal_logp_fwd(const float* z, const float* logdet, int R, int D, float* logp, void* stream) {
+int mhe_std_normal_logp_fwd(const float* z, const float* logdet, float logdet_sign, int R, int D, float* logp, void* stream) {
+    if (R == 0) return MHE_OK;
     MHE_REQUIRE(z && logp && R >= 0 && D > 0, "std_normal_logp_fwd: bad args");
     if (R == 0) return MHE_OK;
-    std_normal_logp_fwd_kernel<<<cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(z, logdet, R, D, logp);
+    std_normal_logp_fwd_kernel<<<cdiv(R, 8), 256, 0, (cudaStream_t)stream>>>(z, logdet, logdet_sign, R, D, logp);
     return check_launch("std normal logp fwd");
 }
 
 int mhe_std_normal_logp_bwd(const float* z, const float* dlogp, int R, int D, float* dz, void* stream) {
+    if (R == 0) return MHE_OK;
     MHE_REQUIRE(z && dlogp && dz && R >= 0 && D > 0, "std_normal_logp_bwd: bad args");
     if (R == 0) return MHE_OK;
     std_normal_logp_bwd_kernel<<<cdiv((int)((long)R * D), 256), 256, 0, (cudaStream_t)stream>>>(z, dlogp, R, D, dz);

@@ -157,6 +157,7 @@ template <Major AM, Major BMaj, class Epi>
 inline int launch_sgemm(const GemmArgs& g, const Epi& epi, cudaStream_t stream, const char* what) {
     if (g.M <= 0 || g.N <= 0 || g.batches <= 0) return MHE_OK;
     const int z = g.batches * g.ksplit;
+    ProbeScope probe(what, stream);
     const long big_ctas = (long)cdiv(g.M, 128) * cdiv(g.N, 128) * z;
     if (big_ctas >= 2 * 148) {
         dim3 grid(cdiv(g.N, 128), cdiv(g.M, 128), z);

@@ -130,6 +130,7 @@ using namespace mhe;
 extern "C" {
 
 int mhe_combine_z_fwd(const float* x_flow, const float* z_det, int R, int B, float* z, void* stream) {
+    if (R == 0) return MHE_OK;
     MHE_REQUIRE(x_flow && z_det && z && R >= 0 && B > 0 && R % B == 0, "combine_z_fwd: bad args");
     if (R == 0) return MHE_OK;
     combine_z_fwd_kernel<<<cdiv((int)((long)R * kZ), 256), 256, 0, (cudaStream_t)stream>>>(x_flow, z_det, R, B, z);
@@ -137,6 +138,7 @@ int mhe_combine_z_fwd(const float* x_flow, const float* z_det, int R, int B, flo
 }
 
 int mhe_combine_z_bwd(const float* dz, int R, int B, float* dx_flow, float* dz_det, void* stream) {
+    if (R == 0) return MHE_OK;
     MHE_REQUIRE(dz && dx_flow && dz_det && R >= 0 && B > 0 && R % B == 0, "combine_z_bwd: bad args");
     if (R == 0) return MHE_OK;
     const long n = (long)R * 45 > (long)B * 16 ? (long)R * 45 : (long)B * 16;
@@ -179,6 +181,7 @@ int mhe_reproj_loss_bwd(const mhe_loss_cfg* cfg, const float* joints, const floa
 int mhe_normalize_project(const mhe_loss_cfg* cfg, const float* joints, const float* verts, const float* z,
                           int ld_z, int R, int inv_norm, int image_size,
                           float* xyz, float* verts_n, float* uv, void* stream) {
+    if (R == 0) return MHE_OK;
     MHE_REQUIRE(cfg && joints && z && R >= 0 && ld_z >= 61, "normalize_project: bad args");
     if (R == 0) return MHE_OK;
     normalize_project_kernel<<<R, 128, 0, (cudaStream_t)stream>>>(*cfg, joints, verts, z, ld_z, R, inv_norm, image_size, xyz, verts_n, uv);

@@ -356,6 +356,7 @@ size_t mhe_mano_workspace_bytes(int R, int mesh_grad) { return R < 0 ? 0 : ManoW
 int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, const float* beta, int ld_beta,
                  int R, int joint_order, float* verts, float* jtr, float* joints2,
                  void* workspace, size_t workspace_bytes, void* stream_) {
+    if (R == 0) return MHE_OK;
     MHE_REQUIRE(c && theta && beta && jtr && workspace, "mano_fwd: null pointer");
     MHE_REQUIRE(R >= 0 && ld_theta >= 48 && ld_beta >= 10 && joint_order >= 0 && joint_order <= 1, "mano_fwd: bad sizes");
     MHE_REQUIRE(!joints2 || verts, "mano_fwd: joints2 needs verts");
@@ -389,6 +390,7 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
                  int R, int joint_order, const float* dverts, const float* djtr, const float* djoints2,
                  float* dtheta, int ld_dtheta, float* dbeta, int ld_dbeta, int accumulate,
                  void* workspace, size_t workspace_bytes, void* stream_) {
+    if (R == 0) return MHE_OK;
     MHE_REQUIRE(c && theta && beta && dtheta && dbeta && workspace, "mano_bwd: null pointer");
     MHE_REQUIRE(R >= 0 && ld_theta >= 48 && ld_beta >= 10 && ld_dtheta >= 48 && ld_dbeta >= 10 && joint_order >= 0 && joint_order <= 1, "mano_bwd: bad sizes");
     const bool mesh = dverts || djoints2;

@@ -1,0 +1,121 @@
+"""Fused multi-hypothesis training / sampling steps driven straight through the C ABI.
+
+``TrainStep`` runs what ``MHEnt.get_loss`` + ``MHEntLoss`` + ``backward()`` run in the reference
+(``hand/network.py:760-831``, ``hand/criteria.py:55,173``; call stack SURVEY.md §3.1) from the image feature
+on: hoisted conditioning, ONE flow pass giving samples and log q (entropy), z assembly, MANO, visible-2D
+reprojection + priors, N-means, and the full backward into a flat gradient buffer — a fixed sequence of
+kernel launches on preallocated buffers, so it can be captured in a CUDA graph.  It computes exactly what
+``MHEntHead.get_loss(...)`` + autograd computes (tests/test_gpu_engine.py).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr
+from .losses import MHEntHead
+
+
+class TrainStep:
+    def __init__(self, head: MHEntHead, B: int, S: int, device, want_verts: bool = True, use_graph: bool = True):
+        self.head, self.B, self.S, self.R = head, B, S, B * S
+        self.dev = torch.device(device)
+        flow = head.q_z_giv_i
+        self.shape = flow._shape
+        self.flat = flow.flat_parameters(self.dev)
+        self.mask = flow.mask
+        self.consts = head.mano_dec.mano_layer._consts(self.dev)
+        self.cfg = head.loss_cfg
+        L = lib()
+        R, D, dev = self.R, flow.dim, self.dev
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        cpf = L.mhe_flow_cp_floats_per_image(self.shape)
+        # static inputs
+        self.feat, self.z_det, self.z0 = f(B, flow.cond_dim), f(B, 16), f(R, D)
+        self.crop_uv, self.vis = f(B, 42), f(B, 21)
+        # forward state
+        self.cp, self.x, self.logdet, self.log_q = f(B, cpf), f(R, D), f(R), f(R)
+        self.saved = f(self.shape.layers + 1, R, D)
+        self.z, self.jtr = f(R, 61), f(R, 21, 3)
+        self.verts = f(R, 778, 3) if want_verts else None
+        self.uv, self.row_lp = f(R, 42), f(R)
+        self.log_p, self.h, self.qlp, self.loss = f(B), f(B), f(B), f(1)
+        # gradients
+        self.dflat = torch.zeros_like(self.flat)
+        self.dcp = f(B, cpf)
+        self.djtr, self.dz, self.dlog_q = f(R, 21, 3), f(R, 61), f(R)
+        self.dx, self.dz_det, self.dz0, self.dfeat = f(R, D), f(B, 16), f(R, D), f(B, flow.cond_dim)
+        self.ws_bytes = max(L.mhe_flow_workspace_bytes(self.shape, R), L.mhe_mano_workspace_bytes(R, 0))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.graph = None
+        self.use_graph = use_graph
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------
+    def _enqueue(self):
+        L, s = lib(), _lib.stream_ptr(self.dev)
+        R, B, shape, ws, wsb = self.R, self.B, self.shape, ptr(self.ws), self.ws_bytes
+        z = self.z
+        theta, beta = z.data_ptr(), z.data_ptr() + 48 * 4
+        # ---- forward
+        check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), ptr(self.feat), B, ptr(self.cp), s), 'cond_fwd')
+        check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
+                                  ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
+        check(L.mhe_std_normal_logp_fwd(ptr(self.z0), ptr(self.logdet), -1.0, R, shape.dim, ptr(self.log_q), s), 'log_q')
+        check(L.mhe_combine_z_fwd(ptr(self.x), ptr(self.z_det), R, B, ptr(z), s), 'combine_z')
+        check(L.mhe_mano_fwd(self.consts, theta, 61, beta, 61, R, 1, ptr(self.verts), ptr(self.jtr), None, ws, wsb, s), 'mano_fwd')
+        check(L.mhe_reproj_loss_fwd(self.cfg, ptr(self.jtr), ptr(z), ptr(self.crop_uv), ptr(self.vis), ptr(self.log_q), R, B,
+                                    ptr(self.uv), ptr(self.row_lp), ptr(self.log_p), ptr(self.h), ptr(self.qlp), ptr(self.loss), s),
+              'reproj_loss_fwd')
+        # ---- backward (dloss = 1)
+        self.dflat.zero_()
+        self.dcp.zero_()
+        check(L.mhe_reproj_loss_bwd(self.cfg, ptr(self.jtr), ptr(z), ptr(self.crop_uv), ptr(self.vis), R, B, None, None,
+                                    ptr(self.djtr), ptr(self.dz), ptr(self.dlog_q), s), 'reproj_loss_bwd')
+        dz = self.dz.data_ptr()
+        check(L.mhe_mano_bwd(self.consts, theta, 61, beta, 61, R, 1, None, ptr(self.djtr), None, dz, 61, dz + 48 * 4, 61, 1,
+                             ws, wsb, s), 'mano_bwd')
+        check(L.mhe_combine_z_bwd(ptr(self.dz), R, B, ptr(self.dx), ptr(self.dz_det), s), 'combine_z_bwd')
+        # log_q = log N(z0) - logdet  ->  dL/dlogdet = -dL/dlog_q
+        check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
+                                  ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
+        check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat), s),
+              'cond_bwd')
+
+    def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
+        """Copy one batch (host or device tensors) into the static input buffers."""
+        self.feat.copy_(feat, non_blocking=non_blocking)
+        self.z_det.copy_(z_det, non_blocking=non_blocking)
+        self.z0.copy_(z0, non_blocking=non_blocking)
+        self.crop_uv.copy_(crop_uv, non_blocking=non_blocking)
+        self.vis.copy_(vis, non_blocking=non_blocking)
+
+    def run(self):
+        """One forward+backward on the loaded batch: ``loss`` (1,), ``dflat``, ``dfeat``, ``dz_det`` are updated."""
+        if not self.use_graph:
+            n0 = lib().mhe_kernel_launch_count()
+            self._enqueue()
+            self.launches_per_step = lib().mhe_kernel_launch_count() - n0
+            return self.loss
+        if self.graph is None:
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self._enqueue()                      # warm-up outside capture
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            n0 = lib().mhe_kernel_launch_count()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.launches_per_step = lib().mhe_kernel_launch_count() - n0
+            self.graph = g
+        self.graph.replay()
+        return self.loss
+
+    def flow_grads(self) -> dict:
+        """Gradients as reference-named tensors (views into the flat gradient buffer)."""
+        flow = self.head.q_z_giv_i
+        names = [n for n, _ in flow.named_parameters()]
+        by_param = {id(p): n for n, p in flow.named_parameters()}
+        return {by_param[id(p)]: self.dflat[off:off + n].view(shape) for p, off, n, shape in flow._slots}

@@ -66,6 +66,7 @@ class _GatherFlat(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gflat):
+        ctx.flow._last_flat_grad = gflat      # the parameters' .grad are views of this buffer (one NCCL all-reduce)
         return (None, *ctx.flow._split_flat(gflat))
 
 
@@ -130,7 +131,7 @@ class _FlowPassFn(torch.autograd.Function):
         wsb = lib().mhe_flow_workspace_bytes(shape, R)
         ws = _lib.WORKSPACE.get(wsb, dev)
         check(lib().mhe_flow_pass_bwd(shape, ptr(flat), ptr(mask), ptr(cp), ptr(saved), R, ctx.B, ctx.direction, ptr(dout),
-                                      ptr(dlogdet), ptr(din), ptr(dflat), ptr(dcp), ptr(ws), wsb, stream_ptr(dev)),
+                                      ptr(dlogdet), 1.0, ptr(din), ptr(dflat), ptr(dcp), ptr(ws), wsb, stream_ptr(dev)),
               'mhe_flow_pass_bwd')
         return din, dcp, dflat, None, None, None, None
 
@@ -145,7 +146,7 @@ class _StdNormalLogpFn(torch.autograd.Function):
         _lib.require_cuda_f32(z, logdet)
         R, D = z.shape
         logp = torch.empty(R, device=z.device, dtype=torch.float32)
-        check(lib().mhe_std_normal_logp_fwd(ptr(z), ptr(logdet), R, D, ptr(logp), stream_ptr(z.device)), 'mhe_std_normal_logp_fwd')
+        check(lib().mhe_std_normal_logp_fwd(ptr(z), ptr(logdet), 1.0, R, D, ptr(logp), stream_ptr(z.device)), 'mhe_std_normal_logp_fwd')
         ctx.save_for_backward(z)
         return logp
 
@@ -197,6 +198,7 @@ class RealNVP(nn.Module):
         self._shape = FlowShape(dim, h_dims[0], cond_dim, len(mask)) if self._kernel_ok else None
         self._flat = None
         self._slots = None
+        self._last_flat_grad = None
 
     # ------------------------------------------------------------------ flat parameter storage
     def _named_flow_params(self):

@@ -1,0 +1,44 @@
+"""Data parallelism over images: one process per GPU, weights replicated, rank g owns images
+[g*B/G, (g+1)*B/G) with all their S hypotheses, so the per-image N-means and the hoisted conditioning stay
+local.  The only exchange per training step is one all-reduce of the flat fp32 gradient and of the scalar loss.
+The reference has no distributed code; this is the B200 addition (NCCL over NVLink; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def image_range(B: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced image range of ``rank`` (first ``B % world`` ranks get one extra image)."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: dict, S: int, rank: int, world: int) -> dict:
+    """Slice a global batch by image.  ``z0`` is hypothesis-major (row r = n*B + b, reference network.py:734),
+    so its shard keeps every hypothesis n of the local images, again hypothesis-major."""
+    B = batch['feat'].shape[0]
+    lo, hi = image_range(B, rank, world)
+    out = {}
+    for k, v in batch.items():
+        if k == 'z0':
+            out[k] = v.reshape(S, B, -1)[:, lo:hi].reshape(S * (hi - lo), -1).contiguous()
+        else:
+            out[k] = v[lo:hi].contiguous()
+    return out
+
+
+def allreduce_step(flat_grad: torch.Tensor, loss: torch.Tensor, local_images: int, global_images: int, group=None):
+    """Turn per-rank (mean-over-local-images) loss and gradient into the global-batch mean, in place.
+
+    loss_global = sum_g (B_g / B) loss_g, likewise for the gradient: scale locally, then sum-all-reduce.
+    """
+    w = local_images / global_images
+    flat_grad.mul_(w)
+    loss.mul_(w)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, group=group)
+        dist.all_reduce(loss, group=group)
+    return flat_grad, loss

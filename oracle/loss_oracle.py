@@ -138,17 +138,4 @@ def mhent_sample(sd, mano_c, feat, z_det, z0, N):
     }
 
 
-def synthetic_batch(B, S, seed=0, dtype=torch.float32, temp=1.0, cond_dim=512, dim=45):
-    """The synthetic inputs of SURVEY.md §8d, drawn in the stated order from ``seed``."""
-    g = torch.Generator().manual_seed(seed)
-    feat = torch.randn(B, cond_dim, generator=g)
-    th3 = 0.5 * torch.randn(B, 3, generator=g)
-    beta = 0.02 * torch.randn(B, 10, generator=g)
-    logs = math.log(0.3) + 0.1 * torch.randn(B, 1, generator=g)
-    t = 0.1 * torch.randn(B, 2, generator=g)
-    z0 = torch.randn(B * S, dim, generator=g) * temp
-    crop_uv = torch.rand(B, 42, generator=g) * 2 - 1
-    vis = (torch.rand(B, 21, generator=g) < 0.7).float()
-    z_det = torch.cat([th3, beta, logs, t], dim=1)
-    return {'feat': feat.to(dtype), 'z_det': z_det.to(dtype), 'z0': z0.to(dtype),
-            'crop_uv': crop_uv.to(dtype), 'vis': vis.to(dtype)}
+from mhentropy_b200.synthetic import synthetic_batch  # noqa: E402,F401  (shared recipe)

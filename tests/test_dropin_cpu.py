@@ -1,0 +1,104 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every declared symbol, the flat
+parameter layout is consistent, and the drop-in classes keep the reference's API / state-dict keys."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mhentropy_b200 import MHEntHead, ManoLayer, RealNVP, _lib
+from mhentropy_b200.build import build
+from mhentropy_b200.mano_assets import synthetic_mano
+from oracle import flow_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _built():
+    build()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'mhentropy_b200.h')).read()
+    declared = set(re.findall(r'\b(mhe_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert _lib.lib().mhe_built_for_sm() == 100
+    assert _lib.lib().mhe_version() >= 100
+
+
+def test_flat_layout_matches_reference_parameter_count():
+    shape = _lib.FlowShape(45, 512, 512, 12)
+    total = _lib.lib().mhe_flow_param_floats(shape)
+    flow = RealNVP(dim=45, tsfm_on=512, h_dims=[512, 512], num_steps=6)
+    n_params = sum(p.numel() for p in flow.parameters())
+    assert n_params == 20_030_520
+    assert total >= n_params and total - n_params < 24 * 64 * 2
+    # slots are disjoint, aligned and inside the buffer
+    spans = []
+    for (i, n, which), p in flow._named_flow_params():
+        off = _lib.lib().mhe_flow_param_offset(shape, i, n, which)
+        assert off % 64 == 0 and off + p.numel() <= total
+        spans.append((off, off + p.numel()))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    assert _lib.lib().mhe_flow_cp_floats_per_image(shape) == 12 * 4 * 512
+
+
+def test_state_dict_keys_match_reference(golden_dir):
+    fx = np.load(os.path.join(golden_dir, 'flow_small.npz'))
+    ref_keys = {k[2:] for k in fx.files if k.startswith('w/')}
+    flow = RealNVP(dim=45, tsfm_on=32, kemb=False, jointN=21, h_dims=[64, 64], num_steps=2)
+    assert set(flow.state_dict().keys()) == ref_keys
+    flow.load_state_dict({k: torch.from_numpy(fx['w/' + k]) for k in ref_keys})
+    head = MHEntHead(q_z_giv_i_cfg=dict(h_dims=[64, 64], num_steps=2, tsfm_on=32), mano_data=synthetic_mano(0), feat_dim=32)
+    keys = set(head.state_dict().keys())
+    assert 'q_z_giv_i.t.0.l.0.weight' in keys and 'q_z_giv_i.mask' in keys
+    for b in ('th_shapedirs', 'th_posedirs', 'th_v_template', 'th_J_regressor', 'th_weights', 'th_faces', 'th_hands_mean',
+              'th_comps', 'th_selected_comps', 'th_betas'):
+        assert f'mano_dec.mano_layer.{b}' in keys
+    assert 'det_head.0.weight' in keys and 'det_head.2.bias' in keys
+
+
+def test_construction_order_reproduces_reference_weights():
+    torch.manual_seed(21)
+    flow = RealNVP(dim=45, tsfm_on=16, kemb=False, jointN=21, h_dims=[32, 32], num_steps=3)
+    sd = fo.init_state_dict(dim=45, cond_dim=16, h_dims=(32, 32), num_steps=3, seed=21)
+    for k, v in flow.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_cpu_tensors_use_stock_ops_and_match_oracle(golden_dir):
+    """API coverage off the kernel path: CPU tensors are evaluated with stock PyTorch ops."""
+    fx = np.load(os.path.join(golden_dir, 'flow_small.npz'))
+    flow = RealNVP(dim=45, tsfm_on=32, kemb=False, jointN=21, h_dims=[64, 64], num_steps=2)
+    flow.load_state_dict({k[2:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith('w/')})
+    x = flow.forward_p(torch.from_numpy(fx['z0']), cond=torch.from_numpy(fx['feat']))
+    assert np.abs(x.detach().numpy() - fx['x']).max() < 1e-6
+    lp = flow.log_prob(torch.from_numpy(fx['xin']), logvar=torch.from_numpy(fx['feat']))
+    assert np.abs(lp.detach().numpy() - fx['log_prob']).max() < 1e-4
+    with pytest.raises(NotImplementedError):
+        flow.log_prob(torch.from_numpy(fx['xin']), logvar=torch.from_numpy(fx['feat']), weights=torch.zeros(10, 45))
+
+
+def test_cuda_path_fails_loudly_without_gpu():
+    layer = ManoLayer(flat_hand_mean=False, ncomps=45, use_pca=True, skeidx='RHD', mano_data=synthetic_mano(0))
+    with pytest.raises(_lib.MheError):
+        layer(beta=torch.zeros(2, 10), theta=torch.zeros(2, 48))     # CPU tensors: no fallback for MANO
+    with pytest.raises(NotImplementedError):
+        ManoLayer(flat_hand_mean=True, ncomps=6, use_pca=True, mano_data=synthetic_mano(0))
+
+
+def test_invalid_arguments_return_error_codes():
+    L = _lib.lib()
+    shape = _lib.FlowShape(45, 512, 512, 12)
+    st = L.mhe_flow_cond_fwd(shape, None, None, 4, None, None)
+    assert st == 1 and b'null' in L.mhe_last_error_string()
+    assert L.mhe_flow_param_offset(_lib.FlowShape(1, 0, 0, 0), 0, 0, 0) == ctypes.c_size_t(-1).value
+    st = L.mhe_reproj_loss_fwd(ctypes.byref(_lib.LossCfg()), None, None, None, None, None, 7, 2, None, None, None, None, None, None, None)
+    assert st == 1

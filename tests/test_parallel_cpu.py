@@ -1,0 +1,84 @@
+"""N > 1 path on CPU (gloo, world_size 2): sharding by image + all-reduce reproduces the single-process step."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mhentropy_b200.mano_assets import synthetic_mano
+from mhentropy_b200.parallel import allreduce_step, image_range, shard_batch
+from mhentropy_b200.synthetic import synthetic_batch
+from oracle import flow_oracle as fo
+from oracle import loss_oracle as lo
+from oracle import mano_oracle as mo
+
+CFG = dict(dim=45, cond_dim=32, h_dims=(64, 64), num_steps=2)
+B, S = 5, 3     # odd image count: ragged shards
+
+
+def _step(batch, n_images_local):
+    sd = fo.init_state_dict(seed=4, **CFG)
+    sdg = {k: v.clone().requires_grad_(k != 'mask') for k, v in sd.items()}
+    c = mo.mano_constants(synthetic_mano(0))
+    out = lo.reverse_kld(sdg, c, batch['feat'], batch['z_det'], batch['z0'], batch['crop_uv'], batch['vis'], S)
+    loss = lo.mhent_loss(out['log_p'])
+    loss.backward()
+    flat = torch.cat([v.grad.flatten() for k, v in sdg.items() if k != 'mask'])
+    return loss.detach().reshape(1).clone(), flat
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    full = synthetic_batch(B, S, seed=9, cond_dim=32)
+    mine = shard_batch(full, S, rank, world)
+    lo_, hi_ = image_range(B, rank, world)
+    loss, flat = _step(mine, hi_ - lo_)
+    allreduce_step(flat, loss, hi_ - lo_, B)
+    if rank == 0:
+        q.put((loss.numpy(), flat.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_image_range_partitions():
+    for Bn in (1, 5, 64, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [image_range(Bn, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == Bn
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_shard_keeps_hypothesis_major_rows():
+    full = synthetic_batch(B, S, seed=9, cond_dim=32)
+    sh = shard_batch(full, S, 1, 2)
+    lo_, hi_ = image_range(B, 1, 2)
+    nb = hi_ - lo_
+    for n in range(S):
+        for j in range(nb):
+            assert torch.equal(sh['z0'][n * nb + j], full['z0'][n * B + lo_ + j])
+    assert torch.equal(sh['feat'], full['feat'][lo_:hi_])
+
+
+def test_two_rank_step_matches_single_process():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    loss2, flat2 = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = synthetic_batch(B, S, seed=9, cond_dim=32)
+    loss1, flat1 = _step(full, B)
+    assert abs(float(loss2[0]) - float(loss1)) < 1e-4 * abs(float(loss1))
+    err = float((torch.from_numpy(flat2) - flat1).norm() / flat1.norm())
+    assert err < 1e-4, err
