@@ -231,6 +231,11 @@ def run_ours(args):
     launches_per_step = eng.launches_per_step
     value = world * R * args.steps / (total_ms * 1e-3)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({'profile_only': True, 'ms_per_step': total_ms / args.steps, 'gpu_launches_per_step': int(launches_per_step)}))
+        return
+
     # ---------------- e2e: public API (MHEntHead.get_loss + autograd), host buffers in the timed region --------
     def e2e_step():
         feat = host['feat'].to(dev, non_blocking=True).requires_grad_(True)
@@ -343,6 +348,7 @@ def main():
     ap.add_argument('--hyp', type=int, default=10, help='hypotheses per image')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='value leg only (for ncu launch lists)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -191,6 +191,18 @@ int mhe_normalize_project(const mhe_loss_cfg* cfg, const float* joints, const fl
                           int ld_z, int R, int inv_norm, int image_size,
                           float* xyz, float* verts_n, float* uv, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core building blocks (tcgen05 + TMA), exposed for tests and tools.
+ * fp32 values travel as split-bf16 planes x = hi + lo: bf16 [batches][planes][rows_p][cols_p].
+ * ------------------------------------------------------------------------------------------ */
+/* src fp32 [batches][rows][cols] dense -> dst planes, zero padded to rows_p x cols_p (cols_p % 8 == 0). */
+int mhe_split_planes(const float* src, int rows, int cols, void* dst, int rows_p, int cols_p, int planes, int batches, void* stream);
+/* C [batches][M][N] fp32 = A * B from dense plane tensors.  a_mn / b_mn = 0: A is [M][K], B is [N][K] (K-major);
+ * = 1: A is [K][M], B is [K][N] (MN-major).  planes = 1: plain bf16; 2: bf16x3 (hi*hi + hi*lo + lo*hi).
+ * bn in {64, 128} is the N tile; ksplit > 1 splits K across CTAs with atomic accumulation.          */
+int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K, int batches, int planes, int a_mn, int b_mn, int bn,
+                    int ksplit, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,170 @@
+// Host side of the tensor-core GEMM: TMA tensor-map construction (driver entry point, no libcuda link),
+// a small tensor-map cache, the fp32 -> split-bf16 plane conversion and a raw GEMM entry point for tests.
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include "tc_gemm.cuh"
+
+namespace mhe {
+namespace tc {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int make_tensor_map(CUtensorMap* map, const PlaneTensor& t, int box_rows) {
+    auto encode = get_encode();
+    if (!encode) { set_error("cuTensorMapEncodeTiled entry point not available"); return MHE_ERR_CUDA; }
+    if (((uintptr_t)t.base & 15) || (t.row_pitch % 8) || (t.plane_stride % 8) || (t.batch_stride % 8)) {
+        set_error("tensor map: base/strides must be 16-byte aligned");
+        return MHE_ERR_INVALID_ARG;
+    }
+    const long plane_stride = t.plane_stride > 0 ? t.plane_stride : (long)t.rows * t.row_pitch;
+    const long batch_stride = t.batch_stride > 0 ? t.batch_stride : plane_stride * t.planes;
+    cuuint64_t gdim[4] = {(cuuint64_t)t.cols, (cuuint64_t)t.rows, (cuuint64_t)t.planes, (cuuint64_t)t.batches};
+    cuuint64_t gstr[3] = {(cuuint64_t)t.row_pitch * 2, (cuuint64_t)plane_stride * 2, (cuuint64_t)batch_stride * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)t.base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d planes=%d batches=%d pitch=%ld box_rows=%d", (int)r, t.cols, t.rows,
+                  t.planes, t.batches, t.row_pitch, box_rows);
+        return MHE_ERR_CUDA;
+    }
+    return MHE_OK;
+}
+
+struct MapKey {
+    const void* base; int cols, rows, planes, batches, box_rows; long row_pitch, plane_stride, batch_stride;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && cols == o.cols && rows == o.rows && planes == o.planes && batches == o.batches && box_rows == o.box_rows &&
+               row_pitch == o.row_pitch && plane_stride == o.plane_stride && batch_stride == o.batch_stride;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.base);
+        auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.cols); mix(k.rows); mix(k.planes); mix(k.batches); mix(k.box_rows); mix((size_t)k.row_pitch); mix((size_t)k.plane_stride); mix((size_t)k.batch_stride);
+        return h;
+    }
+};
+
+// Tensor maps depend only on (pointer, geometry); they are pure descriptors, so caching them is safe even
+// when a buffer is freed and a new one is later allocated at the same address with the same geometry.
+const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap*, MapKeyHash> cache;
+    MapKey key{t.base, t.cols, t.rows, t.planes, t.batches, box_rows, t.row_pitch, t.plane_stride, t.batch_stride};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *status = MHE_OK; return it->second; }
+    if (cache.size() > 65536) {   // unbounded pointer churn: start over
+        for (auto& kv : cache) free(kv.second);
+        cache.clear();
+    }
+    CUtensorMap* m = nullptr;
+    if (posix_memalign((void**)&m, 64, sizeof(CUtensorMap)) != 0) { set_error("tensor map alloc failed"); *status = MHE_ERR_CUDA; return nullptr; }
+    *status = make_tensor_map(m, t, box_rows);
+    if (*status != MHE_OK) { free(m); return nullptr; }
+    cache.emplace(key, m);
+    return m;
+}
+
+// fp32 [batches][rows][cols] (src_ld pitch) -> bf16 planes [batches][planes][rows_p][cols_p], zero padded,
+// optional per-column multiplier (the coupling mask).
+__global__ void split_planes_kernel(const float* __restrict__ src, long src_ld, long src_batch, int rows, int cols, const float* __restrict__ colscale,
+                                    __nv_bfloat16* __restrict__ dst, int rows_p, int cols_p, int planes) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per = (long)rows_p * cols_p;
+    if (idx >= per) return;
+    const int b = blockIdx.y;
+    const int r = (int)(idx / cols_p), c = (int)(idx % cols_p);
+    float v = 0.f;
+    if (r < rows && c < cols) {
+        v = src[(long)b * src_batch + (long)r * src_ld + c];
+        if (colscale) v *= colscale[c];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16* d = dst + (long)b * planes * per + idx;
+    d[0] = hi;
+    if (planes > 1) d[per] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+int split_planes(const float* src, long src_ld, long src_batch, int rows, int cols, const float* colscale, __nv_bfloat16* dst, int rows_p,
+                 int cols_p, int planes, int batches, cudaStream_t stream) {
+    if (rows_p <= 0 || cols_p <= 0 || batches <= 0) return MHE_OK;
+    dim3 grid(cdiv((int)((long)rows_p * cols_p), 256), batches);
+    split_planes_kernel<<<grid, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p, planes);
+    return check_launch("split planes");
+}
+
+struct EpiRawStore {   // C[batch][row][col] = acc  (+= when accumulate; atomic when K is split)
+    float* C; long ldc; long strideC; int accumulate; int atomic;
+    __device__ void operator()(int b, int, int row, int col0, const float* v, const GemmShape& g) const {
+        float* p = C + (long)b * strideC + (long)row * ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (col0 + j < g.N) {
+                if (atomic) atomicAdd(p + j, v[j]);
+                else if (accumulate) p[j] += v[j];
+                else p[j] = v[j];
+            }
+        }
+    }
+};
+
+}  // namespace tc
+}  // namespace mhe
+
+using namespace mhe;
+using namespace mhe::tc;
+
+extern "C" {
+
+int mhe_split_planes(const float* src, int rows, int cols, void* dst, int rows_p, int cols_p, int planes, int batches, void* stream) {
+    MHE_REQUIRE(src && dst && rows >= 0 && cols >= 0 && rows_p >= rows && cols_p >= cols && cols_p % 8 == 0 && (planes == 1 || planes == 2),
+                "split_planes: bad args");
+    return split_planes(src, cols, (long)rows * cols, rows, cols, nullptr, (__nv_bfloat16*)dst, rows_p, cols_p, planes, batches, (cudaStream_t)stream);
+}
+
+// Raw tensor-core GEMM for tests: A, B are plane tensors [batches][planes][rows][cols] (dense), C fp32 [batches][M][N].
+// a_mn / b_mn select MN-major operands (A stored [K][M], B stored [K][N]); otherwise A is [M][K], B is [N][K].
+int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K, int batches, int planes, int a_mn, int b_mn, int bn,
+                    int ksplit, void* stream_) {
+    MHE_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batches > 0 && (planes == 1 || planes == 2) && (bn == 64 || bn == 128) && ksplit >= 1,
+                "tc_gemm_raw: bad args");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PlaneTensor ta, tb;
+    ta.base = (const __nv_bfloat16*)A; ta.planes = planes; ta.batches = batches;
+    tb.base = (const __nv_bfloat16*)B; tb.planes = planes; tb.batches = batches;
+    if (a_mn) { ta.cols = M; ta.rows = K; } else { ta.cols = K; ta.rows = M; }
+    if (b_mn) { tb.cols = N; tb.rows = K; } else { tb.cols = K; tb.rows = N; }
+    ta.row_pitch = ta.cols; tb.row_pitch = tb.cols;
+    MHE_REQUIRE(ta.cols % 8 == 0 && tb.cols % 8 == 0, "tc_gemm_raw: contiguous extents must be multiples of 8");
+    GemmShape g{M, N, K, batches, ksplit};
+    EpiRawStore e{C, N, (long)M * N, 0, ksplit > 1};
+    if (ksplit > 1 && cudaMemsetAsync(C, 0, (size_t)batches * M * N * sizeof(float), stream) != cudaSuccess) return MHE_ERR_CUDA;
+#define MHE_RAW(BN_, AMN_, BMN_, NP_) return launch_tc_gemm<BN_, AMN_, BMN_, NP_>(ta, tb, g, e, stream, "tc raw")
+#define MHE_RAW_NP(BN_, AMN_, BMN_) do { if (planes == 1) MHE_RAW(BN_, AMN_, BMN_, 1); else MHE_RAW(BN_, AMN_, BMN_, 3); } while (0)
+#define MHE_RAW_MAJ(BN_) do { if (!a_mn && !b_mn) MHE_RAW_NP(BN_, false, false); else if (!a_mn && b_mn) MHE_RAW_NP(BN_, false, true); \
+                              else if (a_mn && !b_mn) MHE_RAW_NP(BN_, true, false); else MHE_RAW_NP(BN_, true, true); } while (0)
+    if (bn == 64) MHE_RAW_MAJ(64); else MHE_RAW_MAJ(128);
+#undef MHE_RAW
+#undef MHE_RAW_NP
+#undef MHE_RAW_MAJ
+    return MHE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+// Blackwell tensor-core GEMM for the coupling MLPs: tcgen05.mma (bf16 operands, fp32 accumulate in TMEM),
+// operands staged by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring, warp-specialised
+// (1 TMA warp, 1 MMA warp, 4 epilogue warps reading the accumulator back with tcgen05.ld).
+//
+// Precision: fp32 values are carried as SPLIT-bf16 PLANES  x = hi + lo  (hi = bf16(x), lo = bf16(x - hi)).
+// A product uses the three tensor-core passes hi*hi + hi*lo + lo*hi accumulated in fp32 ("bf16x3"), which
+// keeps ~16 mantissa bits per product — what the parity tolerances need — at the
+// bf16 MMA rate.  NPAIR = 1 runs plain bf16.
+//
+// Operand tensors are 4-D bf16 arrays  [batch][plane][rows][cols]  (cols contiguous) described by a TMA
+// tensor map.  An operand is K-major when cols index K (rows index M or N) and MN-major when cols index
+// M/N (rows index K); MN-major lets dgrad (dy * W) and wgrad (dy^T * x) read weights and activations in
+// their natural layouts, with no transposed copies.  Shared-memory tiles are the canonical UMMA SW128
+// layouts: K-major  [rows][64 cols] 128 B per row, 8-row groups 1024 B apart;
+//          MN-major boxes of [64 k-rows][64 cols], 8-k groups 1024 B apart, 64-col groups one box apart.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace mhe {
+namespace tc {
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+// ---- host: tensor maps ----------------------------------------------------------------------------
+struct PlaneTensor {          // [batches][planes][rows][cols] bf16, element strides
+    const __nv_bfloat16* base = nullptr;
+    int cols = 0, rows = 0, planes = 1, batches = 1;
+    long row_pitch = 0, plane_stride = 0, batch_stride = 0;
+};
+
+int make_tensor_map(CUtensorMap* map, const PlaneTensor& t, int box_rows);
+
+// ---- device primitives ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// parity wait with a watchdog: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128
+__host__ __device__ constexpr uint32_t instr_desc(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) /*c = f32*/ | (1u << 7) /*a = bf16*/ | (1u << 10) /*b = bf16*/ |
+           ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmShape {
+    int M, N, K;       // logical extents (rows of A, rows/cols of B, contraction)
+    int batches;       // grid.z = batches * ksplit
+    int ksplit;
+};
+
+template <int BN, int NPL>
+struct SmemPlan {
+    static constexpr int kABytes = BM * BK * 2;           // one plane of A per stage (16 KB)
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = NPL * (kABytes + kBBytes);
+    static constexpr int kStages = (200 * 1024) / kStageBytes >= 4 ? 4 : (200 * 1024) / kStageBytes;
+    static constexpr int kBytes = kStages * kStageBytes + 1024;   // + alignment slack
+};
+
+// C[batch] (M x N) = sum_pairs A_pa (M x K) * B_pb (K x N).  Epi::operator()(batch, split, row, col0, v[32], shape)
+// is called by every epilogue thread once per 32-column chunk with its accumulator row.
+template <int BN, bool A_MN, bool B_MN, int NPAIR, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi) {
+    constexpr int NPL = NPAIR == 1 ? 1 : 2;
+    using Plan = SmemPlan<BN, NPL>;
+    constexpr int NS = Plan::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_accum;
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int batch = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+    const int kb_total = (g.K + BK - 1) / BK;
+    const int kb_per = (kb_total + g.ksplit - 1) / g.ksplit;
+    const int kb_begin = split * kb_per;
+    const int kb_end = min(kb_total, kb_begin + kb_per);
+    const int nkb = max(kb_end - kb_begin, 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_accum), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    auto stage_a = [&](int s, int p) { return smem0 + s * Plan::kStageBytes + p * Plan::kABytes; };
+    auto stage_b = [&](int s, int p) { return smem0 + s * Plan::kStageBytes + NPL * Plan::kABytes + p * Plan::kBBytes; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % NS;
+                const uint32_t ph = (i / NS) & 1;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_expect_tx(full, Plan::kStageBytes);
+                const int k0 = (kb_begin + i) * BK;
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) {
+                    if (!A_MN) tma_load_4d(stage_a(s, p), &mapA, full, k0, m0, p, batch);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, &mapA, full, m0 + 64 * j, k0, p, batch);
+                    }
+                    if (!B_MN) tma_load_4d(stage_b(s, p), &mapB, full, k0, n0, p, batch);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, &mapB, full, n0 + 64 * j, k0, p, batch);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(BN, A_MN, B_MN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % NS;
+                const uint32_t ph = (i / NS) & 1;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int pr = 0; pr < NPAIR; ++pr) {
+                    const int pa = (pr == 2) ? 1 : 0;     // pairs: (hi,hi) (hi,lo) (lo,hi)
+                    const int pb = (pr == 1) ? 1 : 0;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint64_t da = A_MN ? smem_desc(stage_a(s, pa) + ks * 2048, 8192, 1024) : smem_desc(stage_a(s, pa) + ks * 32, 16, 1024);
+                        const uint64_t db = B_MN ? smem_desc(stage_b(s, pb) + ks * 2048, 8192, 1024) : smem_desc(stage_b(s, pb) + ks * 32, 16, 1024);
+                        umma_bf16(tmem_d, da, db, idesc, (i | pr | ks) != 0 ? 1u : 0u);
+                    }
+                }
+                tcgen05_commit(smem_u32(&bar_empty[s]));   // frees the stage once these MMAs have read it
+            }
+            tcgen05_commit(smem_u32(&bar_accum));          // accumulator complete
+        }
+    } else {
+        const int q = warp & 3;                            // TMEM lane quadrant this warp may access
+        const int row = m0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(smem_u32(&bar_accum), 0);
+            tcgen05_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            if (nkb > 0) tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (row < g.M && n0 + c0 < g.N) epi(batch, split, row, n0 + c0, v, g);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+    }
+}
+
+// launch helper: builds (cached) tensor maps and launches.  A: rows = M (K-major) or K (MN-major), etc.
+const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status);
+
+template <int BN, bool A_MN, bool B_MN, int NPAIR, class Epi>
+inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const GemmShape& g, const Epi& epi, cudaStream_t stream, const char* what) {
+    if (g.M <= 0 || g.N <= 0 || g.batches <= 0) return MHE_OK;
+    constexpr int NPL = NPAIR == 1 ? 1 : 2;
+    using Plan = SmemPlan<BN, NPL>;
+    int st = MHE_OK;
+    const CUtensorMap* ma = cached_map(A, A_MN ? 64 : BM, &st);
+    if (st != MHE_OK) return st;
+    const CUtensorMap* mb = cached_map(B, B_MN ? 64 : BN, &st);
+    if (st != MHE_OK) return st;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, NPAIR, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes) != cudaSuccess) {
+            set_error("%s: cannot raise dynamic shared memory to %d", what, Plan::kBytes);
+            return MHE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    ProbeScope probe(what, stream);
+    dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), g.batches * g.ksplit);
+    kern<<<grid, kThreads, Plan::kBytes, stream>>>(*ma, *mb, g, epi);
+    return check_launch(what);
+}
+
+}  // namespace tc
+}  // namespace mhe

@@ -220,7 +220,7 @@ def test_training_step_vs_fp64_oracle_config1():
     def run_oracle(dtype):
         sdg = {k: v.to(dtype).clone().requires_grad_(k != 'mask') for k, v in sd.items()}
         c = mo.mano_constants(mano, dtype)
-        feat = batch['feat'].to(dtype).requires_grad_(True)
+        feat = batch['feat'].to(dtype).clone().requires_grad_(True)
         out = lo.reverse_kld(sdg, c, feat, batch['z_det'].to(dtype), batch['z0'].to(dtype), batch['crop_uv'].to(dtype),
                              batch['vis'].to(dtype), S)
         lo.mhent_loss(out['log_p']).backward()
@@ -231,7 +231,7 @@ def test_training_step_vs_fp64_oracle_config1():
     head = MHEntHead(mano_data=mano)
     head.q_z_giv_i.load_state_dict(sd)
     head = head.to(DEV)
-    feat = batch['feat'].to(DEV).requires_grad_(True)
+    feat = batch['feat'].detach().clone().to(DEV).requires_grad_(True)
     y = {'crop_uv': batch['crop_uv'].to(DEV), 'vis': batch['vis'].to(DEV)}
     out = head.get_loss(feat, y, z0=batch['z0'].to(DEV), z_det=batch['z_det'].to(DEV), N=S)
     (-out['log_p']).mean().backward()
