@@ -72,16 +72,27 @@ size_t mhe_flow_param_floats(mhe_flow_shape s);
 size_t mhe_flow_param_offset(mhe_flow_shape s, int layer, int net, int which);
 /* floats per image of the hoisted conditioning projections: L*4*H */
 size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s);
-/* bytes of scratch needed by the flow passes over R rows (forward and backward) */
-size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R);
+/* Two arithmetic paths share every flow entry point:
+ *   packed == NULL : exact fp32 on the CUDA cores;
+ *   packed != NULL : tcgen05 tensor cores in bf16x3 split precision (hi*hi + hi*lo + lo*hi, fp32 accumulate);
+ *                    `packed` holds the weights as split-bf16 planes, refreshed by mhe_flow_pack_weights()
+ *                    whenever the parameters change.  Needs dim <= 64, hidden % 64 == 0, cond % 8 == 0
+ *                    (mhe_flow_packed_bytes() returns 0 otherwise).                                   */
+size_t mhe_flow_packed_bytes(mhe_flow_shape s);
+int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, void* stream);
+/* bytes of scratch needed by the flow passes over R rows (forward and backward) on the chosen path */
+size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core);
+/* bytes of scratch the tensor-core conditioning GEMMs need for B images (0 when that path is unsupported) */
+size_t mhe_flow_cond_workspace_bytes(mhe_flow_shape s, int B);
 
 /* Hoisted conditioning projections (reference flows.py:107-109 "Can be pre-processed"):
  *   cp[b][idx][h] = sum_c feat[b][c]*Cw[idx][h][c] + Cb[idx][h] + b_j[h]      (b_j = l.j.bias folded in)
  * feat [B][C] -> cp [B][L*4][H].                                                               */
-int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const float* feat, int B, float* cp, void* stream);
+int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* feat, int B, float* cp,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* dcp [B][L*4][H] -> dparams (accumulate: Cw, Cb, b0, b1 slots), dfeat [B][C] (overwritten; may be NULL) */
-int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const float* feat, const float* dcp, int B,
-                      float* dparams, float* dfeat, void* stream);
+int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* feat, const float* dcp, int B,
+                      float* dparams, float* dfeat, void* workspace, size_t workspace_bytes, void* stream);
 
 /* One pass through the L coupling layers.
  *   direction 0: z -> x, layers 0..L-1,  x' = m x + (1-m)(x e^s + t),  logdet += sum s   (flows.py:210-217)
@@ -89,13 +100,13 @@ int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const float* feat, 
  * in [R][D] -> out [R][D], logdet [R] (may be NULL).  Row r uses cp of image r % B.
  * saved: NULL, or [(L+1)][R][D] receiving each layer's input (processing order) and the output —
  * the only activations the backward needs (hidden activations are recomputed).                   */
-int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
+int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
                       const float* in, int R, int B, int direction,
                       float* out, float* logdet, float* saved,
                       void* workspace, size_t workspace_bytes, void* stream);
 /* dout [R][D], dlogdet [R] (NULL = 0; multiplied by dlogdet_scale, so -1 turns dL/dlog_q of the fused
  * sampler into dL/dlogdet) -> din [R][D]; dparams (accumulate; W0,W1,W2,b2 slots), dcp [B][L*4][H] (accumulate). */
-int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
+int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
                       const float* saved, int R, int B, int direction,
                       const float* dout, const float* dlogdet, float dlogdet_scale,
                       float* din, float* dparams, float* dcp,

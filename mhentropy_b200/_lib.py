@@ -44,11 +44,14 @@ _SIGNATURES = {
     'mhe_flow_param_floats': (c_size_t, [FlowShape]),
     'mhe_flow_param_offset': (c_size_t, [FlowShape, c_int, c_int, c_int]),
     'mhe_flow_cp_floats_per_image': (c_size_t, [FlowShape]),
-    'mhe_flow_workspace_bytes': (c_size_t, [FlowShape, c_int]),
-    'mhe_flow_cond_fwd': (c_int, [FlowShape, _P, _P, c_int, _P, _P]),
-    'mhe_flow_cond_bwd': (c_int, [FlowShape, _P, _P, _P, c_int, _P, _P, _P]),
-    'mhe_flow_pass_fwd': (c_int, [FlowShape, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
-    'mhe_flow_pass_bwd': (c_int, [FlowShape, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    'mhe_flow_workspace_bytes': (c_size_t, [FlowShape, c_int, c_int]),
+    'mhe_flow_cond_workspace_bytes': (c_size_t, [FlowShape, c_int]),
+    'mhe_flow_packed_bytes': (c_size_t, [FlowShape]),
+    'mhe_flow_pack_weights': (c_int, [FlowShape, _P, _P, _P]),
+    'mhe_flow_cond_fwd': (c_int, [FlowShape, _P, _P, _P, c_int, _P, _P, c_size_t, _P]),
+    'mhe_flow_cond_bwd': (c_int, [FlowShape, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    'mhe_flow_pass_fwd': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    'mhe_flow_pass_bwd': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
     'mhe_std_normal_logp_fwd': (c_int, [_P, _P, c_float, c_int, c_int, _P, _P]),
     'mhe_std_normal_logp_bwd': (c_int, [_P, _P, c_int, c_int, _P, _P]),
     'mhe_mano_workspace_bytes': (c_size_t, [c_int, c_int]),

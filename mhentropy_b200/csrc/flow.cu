@@ -5,6 +5,7 @@
 // projections hoisted to one GEMM per step (mhe_flow_cond_fwd) with the l.0/l.1 biases folded in.
 // The backward recomputes a0/a1 from the saved layer input instead of storing them.
 #include "gemm_simt.cuh"
+#include "flow_tc.cuh"
 
 namespace mhe {
 
@@ -249,17 +250,44 @@ size_t mhe_flow_param_offset(mhe_flow_shape s, int layer, int net, int which) {
 
 size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s) { return (size_t)s.layers * 4 * s.hidden; }
 
-size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R) {
+size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core) {
     if (!valid_shape(s) || R < 0) return 0;
-    return FlowWs::floats(FlowLayout(s), R) * sizeof(float);
+    FlowLayout L(s);
+    if (tensor_core) return tcflow::supported(L) ? tcflow::Ws::bytes(L, R) : 0;
+    return FlowWs::floats(L, R) * sizeof(float);
 }
 
-int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const float* feat, int B, float* cp, void* stream_) {
+size_t mhe_flow_cond_workspace_bytes(mhe_flow_shape s, int B) {
+    if (!valid_shape(s) || B < 0) return 0;
+    FlowLayout L(s);
+    return tcflow::supported(L) ? tcflow::cond_ws_bytes(L, B) : 0;
+}
+
+size_t mhe_flow_packed_bytes(mhe_flow_shape s) {
+    if (!valid_shape(s)) return 0;
+    FlowLayout L(s);
+    return tcflow::supported(L) ? tcflow::Packed::elems(L) * 2 : 0;
+}
+
+int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, void* stream) {
+    MHE_REQUIRE(valid_shape(s) && params && packed, "pack_weights: bad args");
+    FlowLayout L(s);
+    if (!tcflow::supported(L)) { set_error("pack_weights: shape outside the tensor-core path (dim <= 64, hidden %% 64 == 0, cond %% 8 == 0)"); return MHE_ERR_UNSUPPORTED; }
+    return tcflow::pack_weights(L, params, packed, (cudaStream_t)stream);
+}
+
+int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* feat, int B, float* cp,
+                      void* workspace, size_t workspace_bytes, void* stream_) {
     MHE_REQUIRE(valid_shape(s), "cond_fwd: bad shape");
     MHE_REQUIRE(params && feat && cp && B >= 0, "cond_fwd: null pointer or negative B");
     if (B == 0) return MHE_OK;
     FlowLayout L(s);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (packed) {
+        if (!tcflow::supported(L)) { set_error("cond_fwd: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
+        if (!workspace || workspace_bytes < tcflow::cond_ws_bytes(L, B)) { set_error("cond_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        return tcflow::cond_fwd(L, params, packed, feat, B, cp, workspace, stream);
+    }
     GemmArgs g; g.A = feat; g.lda = L.C; g.strideA = 0;
     g.B = params + L.cw_base; g.ldb = L.C; g.strideB = (long)L.cw_stride;
     g.M = B; g.N = L.H; g.K = L.C; g.batches = L.L * 4;
@@ -267,13 +295,18 @@ int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const float* feat, 
     return launch_sgemm<Major::K, Major::K>(g, e, stream, "cond fwd");
 }
 
-int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const float* feat, const float* dcp, int B,
-                      float* dparams, float* dfeat, void* stream_) {
+int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* feat, const float* dcp, int B,
+                      float* dparams, float* dfeat, void* workspace, size_t workspace_bytes, void* stream_) {
     MHE_REQUIRE(valid_shape(s), "cond_bwd: bad shape");
     MHE_REQUIRE(params && feat && dcp && dparams && B >= 0, "cond_bwd: null pointer or negative B");
     if (B == 0) return MHE_OK;
     FlowLayout L(s);
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (packed) {
+        if (!tcflow::supported(L)) { set_error("cond_bwd: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
+        if (!workspace || workspace_bytes < tcflow::cond_ws_bytes(L, B)) { set_error("cond_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        return tcflow::cond_bwd(L, params, packed, feat, dcp, B, dparams, dfeat, workspace, stream);
+    }
     const long cp_ld = (long)L.L * 4 * L.H;
     {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat
         GemmArgs g; g.A = dcp; g.lda = cp_ld; g.strideA = L.H;  // A(m=h, k=b) = dcp[b*cp_ld + idx*H + h]
@@ -295,7 +328,7 @@ int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const float* feat, 
     return MHE_OK;
 }
 
-int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
+int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
                       const float* in, int R, int B, int direction,
                       float* out, float* logdet, float* saved,
                       void* workspace, size_t workspace_bytes, void* stream_) {
@@ -303,10 +336,14 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, 
     MHE_REQUIRE(R >= 0 && B > 0 && direction >= 0 && direction <= 1, "pass_fwd: bad R/B/direction");
     if (R == 0) return MHE_OK;
     MHE_REQUIRE(params && mask && cp && in && out && workspace, "pass_fwd: null pointer");
-    if (workspace_bytes < mhe_flow_workspace_bytes(s, R)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
     FlowLayout L(s);
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (R == 0) return MHE_OK;
+    if (packed) {
+        if (!tcflow::supported(L)) { set_error("pass_fwd: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
+        if (workspace_bytes < tcflow::Ws::bytes(L, R)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        return tcflow::pass_fwd(L, params, packed, mask, cp, in, R, B, direction, out, logdet, saved, workspace, stream);
+    }
+    if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 0)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
     FlowWs ws((float*)workspace, L, R);
     const size_t row_bytes = (size_t)R * L.D * sizeof(float);
     if (logdet) MHE_TRY(cuda_ok(cudaMemsetAsync(logdet, 0, (size_t)R * sizeof(float), stream), "memset logdet"));
@@ -331,7 +368,7 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const float* mask, 
     return MHE_OK;
 }
 
-int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, const float* cp,
+int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
                       const float* saved, int R, int B, int direction,
                       const float* dout, const float* dlogdet, float dlogdet_scale,
                       float* din, float* dparams, float* dcp,
@@ -340,10 +377,14 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const float* mask, 
     MHE_REQUIRE(R >= 0 && B > 0 && direction >= 0 && direction <= 1, "pass_bwd: bad R/B/direction");
     if (R == 0) return MHE_OK;
     MHE_REQUIRE(params && mask && cp && saved && dout && din && dparams && dcp && workspace, "pass_bwd: null pointer");
-    if (workspace_bytes < mhe_flow_workspace_bytes(s, R)) { set_error("pass_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
     FlowLayout L(s);
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (R == 0) return MHE_OK;
+    if (packed) {
+        if (!tcflow::supported(L)) { set_error("pass_bwd: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
+        if (workspace_bytes < tcflow::Ws::bytes(L, R)) { set_error("pass_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        return tcflow::pass_bwd(L, params, packed, mask, cp, saved, R, B, direction, dout, dlogdet, dlogdet_scale, din, dparams, dcp, workspace, stream);
+    }
+    if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 0)) { set_error("pass_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
     FlowWs ws((float*)workspace, L, R);
     const long cp_ld = (long)L.L * 4 * L.H;
     const long RH = (long)R * L.H, RD = (long)R * L.D;

@@ -1,0 +1,428 @@
+// Tensor-core path of the conditional RealNVP (reference hand/flows.py:75-122, 210-227): every contraction of
+// the coupling MLPs and of the hoisted conditioning runs on tcgen05 through tc_gemm.cuh in bf16x3 split
+// precision; activations travel between kernels as split-bf16 planes.  Same maths and same C ABI as the fp32
+// path in flow.cu — selected by passing packed weights (mhe_flow_pack_weights) to the entry points.
+#include "flow_tc.cuh"
+
+namespace mhe {
+namespace tcflow {
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+// ---- plane stores -------------------------------------------------------------------------------
+__device__ __forceinline__ void store_planes32(bf16* hi_ptr, bf16* lo_ptr, const float* v) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const bf16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+        const bf16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+        h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    uint4* ph = reinterpret_cast<uint4*>(hi_ptr);
+    uint4* pl = reinterpret_cast<uint4*>(lo_ptr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+        pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+    }
+}
+
+// ---- epilogues (one call per thread per 32-column chunk of its accumulator row) -----------------------
+struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[batch][plane][row][col]
+    bf16* out; long ld; long plane_stride; long batch_stride;
+    const float* cp; long cp_ld; long cp_off; long cp_bstride; int B;
+    __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
+        const float4* c = reinterpret_cast<const float4*>(cp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(c + j);
+            v[4 * j] = lrelu(v[4 * j] + t.x); v[4 * j + 1] = lrelu(v[4 * j + 1] + t.y);
+            v[4 * j + 2] = lrelu(v[4 * j + 2] + t.z); v[4 * j + 3] = lrelu(v[4 * j + 3] + t.w);
+        }
+        bf16* p = out + (long)b * batch_stride + (long)row * ld + col0;
+        store_planes32(p, p + plane_stride, v);
+    }
+};
+struct EpiOutHead {   // st[batch][row][col] = batch == 0 ? tanh(acc + b2) : acc + b2, col < D
+    float* out; int D; long batch_stride; const float* bias; long bias_bstride;
+    __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < D) {
+                float t = v[j] + __ldg(bias + (long)b * bias_bstride + col);
+                if (b == 0) t = tanhf(t);
+                out[(long)b * batch_stride + (long)row * D + col] = t;
+            }
+        }
+    }
+};
+struct EpiActGradPlanes {   // out = acc * lrelu'(act)  (sign of the hi plane is the sign of the activation)
+    bf16* out; const bf16* act_hi; long ld; long plane_stride; long batch_stride;
+    __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
+        const long off = (long)b * batch_stride + (long)row * ld + col0;
+        const uint4* a = reinterpret_cast<const uint4*>(act_hi + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 t = a[j];
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t e0 = w[i] & 0xFFFFu, e1 = w[i] >> 16;
+                v[8 * j + 2 * i] *= ((e0 & 0x8000u) == 0 && (e0 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
+                v[8 * j + 2 * i + 1] *= ((e1 & 0x8000u) == 0 && (e1 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
+            }
+        }
+        store_planes32(out + off, out + off + plane_stride, v);
+    }
+};
+struct EpiMaskAtomicAdd {   // gx[row][col] += mask[col] * acc, col < D
+    float* out; int D; const float* mask;
+    __device__ void operator()(int, int, int row, int col0, float* v, const GemmShape&) const {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < D) { const float w = __ldg(mask + col); if (w != 0.f) atomicAdd(out + (long)row * D + col, w * v[j]); }
+        }
+    }
+};
+struct EpiWgrad {   // dW[batch] (+)= acc;  transposed: element (row, col) goes to dW[col][row]
+    float* dW; long ld; long batch_stride; int ncols; int transposed; int atomic;
+    __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
+        float* base = dW + (long)b * batch_stride;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < ncols) {
+                float* p = transposed ? base + (long)col * ld + row : base + (long)row * ld + col;
+                if (atomic) atomicAdd(p, v[j]); else *p += v[j];
+            }
+        }
+    }
+};
+struct EpiCondFwd {   // cp[row][idx*H + col] = acc + Cb[idx][col] + b_j[col]
+    float* cp; long cp_ld; int H; const float* params; size_t cb_base, cb_stride, blk, ob0, ob1;
+    __device__ void operator()(int idx, int, int row, int col0, float* v, const GemmShape&) const {
+        const float* cb = params + cb_base + (size_t)idx * cb_stride + col0;
+        const float* bj = params + (size_t)(idx >> 1) * blk + ((idx & 1) ? ob1 : ob0) + col0;
+        float4* o = reinterpret_cast<float4*>(cp + (long)row * cp_ld + (long)idx * H + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(v[4 * j] + __ldg(cb + 4 * j) + __ldg(bj + 4 * j), v[4 * j + 1] + __ldg(cb + 4 * j + 1) + __ldg(bj + 4 * j + 1),
+                               v[4 * j + 2] + __ldg(cb + 4 * j + 2) + __ldg(bj + 4 * j + 2), v[4 * j + 3] + __ldg(cb + 4 * j + 3) + __ldg(bj + 4 * j + 3));
+    }
+};
+struct EpiAtomicRows {   // C[row][col] += acc (every batch lands on the same output)
+    float* C; long ld; int ncols;
+    __device__ void operator()(int, int, int row, int col0, float* v, const GemmShape&) const {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < ncols) atomicAdd(C + (long)row * ld + col0 + j, v[j]);
+    }
+};
+
+// ---- elementwise kernels --------------------------------------------------------------------------
+__device__ __forceinline__ void put_planes(bf16* hi, long plane_stride, float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[0] = h;
+    hi[plane_stride] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// coupling forward (see flow.cu) + masked split planes of the result for the next layer's first GEMM
+__global__ void coupling_fwd_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ mask,
+                                    const float* __restrict__ next_mask, int R, int D, int direction, float* __restrict__ y,
+                                    float* __restrict__ logdet, bf16* __restrict__ ym) {
+    const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    float ssum = 0.f;
+    for (int d = lane; d < kDp; d += 32) {
+        float out = 0.f;
+        if (d < D) {
+            const float xv = x[(long)r * D + d];
+            out = xv;
+            if (mask[d] == 0.f) {
+                const float s = st[(long)r * D + d], t = st[(long)R * D + (long)r * D + d];
+                out = direction == 0 ? fmaf(xv, expf(s), t) : (xv - t) * expf(-s);
+                ssum += s;
+            }
+            y[(long)r * D + d] = out;
+        }
+        if (ym) put_planes(ym + (long)r * kDp + d, (long)R * kDp, (d < D && next_mask) ? out * next_mask[d] : 0.f);
+    }
+    if (logdet) {
+        ssum = warp_sum(ssum);
+        if (lane == 0) logdet[r] += direction == 0 ? ssum : -ssum;
+    }
+}
+
+// coupling backward (see flow.cu) + split planes of the head gradients [2 nets][2 planes][R][64]
+__global__ void coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ mask,
+                                    const float* g, const float* __restrict__ gl, float gl_scale, int R, int D, int direction,
+                                    float* __restrict__ dpre, bf16* __restrict__ dprep, float* gx) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)R * kDp) return;
+    const int r = (int)(i / kDp), d = (int)(i % kDp);
+    float ds = 0.f, dt = 0.f;
+    if (d < D) {
+        const long k = (long)r * D + d;
+        const float gv = g[k];
+        float dx = gv;
+        if (mask[d] == 0.f) {
+            const float s = st[k], t = st[(long)R * D + k], xv = x[k];
+            const float glv = gl ? gl_scale * gl[r] : 0.f;
+            if (direction == 0) { const float e = expf(s); dx = gv * e; dt = gv; ds = gv * xv * e + glv; }
+            else { const float e = expf(-s); dx = gv * e; dt = -gv * e; ds = -gv * (xv - t) * e - glv; }
+            ds *= (1.f - s * s);
+        }
+        dpre[k] = ds;
+        dpre[(long)R * D + k] = dt;
+        gx[k] = dx;
+    }
+    const long ps = (long)R * kDp;
+    put_planes(dprep + i, ps, ds);
+    put_planes(dprep + 2 * ps + i, ps, dt);
+}
+
+// dcp[b][off + z*zstride + n] += sum_s (hi + lo)[z][s*B + b][n]
+__global__ void hyp_sum_planes_kernel(const bf16* __restrict__ in, int R, int B, int N, long plane_stride, long batch_stride,
+                                      float* __restrict__ dcp, long cp_ld, long off, long zstride) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y, z = blockIdx.z;
+    if (n >= N) return;
+    const bf16* p = in + (long)z * batch_stride;
+    float acc = 0.f;
+    for (int r = b; r < R; r += B) acc += __bfloat162float(p[(long)r * N + n]) + __bfloat162float(p[plane_stride + (long)r * N + n]);
+    dcp[(long)b * cp_ld + off + (long)z * zstride + n] += acc;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ in, int M, int N, long strideIn, float* __restrict__ out, long strideOut) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = blockIdx.z;
+    if (n >= N) return;
+    const int per = (M + gridDim.y - 1) / gridDim.y;
+    const int mb = blockIdx.y * per, me = min(M, mb + per);
+    float acc = 0.f;
+    for (int m = mb; m < me; ++m) acc += in[(long)z * strideIn + (long)m * N + n];
+    if (me > mb) atomicAdd(out + (long)z * strideOut + n, acc);
+}
+
+__global__ void cond_bias_grad_kernel(const float* __restrict__ dcp, int B, long cp_ld, int H, float* __restrict__ dparams,
+                                      size_t cb_base, size_t cb_stride, size_t blk, size_t ob0, size_t ob1) {
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= cp_ld) return;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += dcp[(long)b * cp_ld + n];
+    const int idx = (int)(n / H), h = (int)(n % H);
+    dparams[cb_base + (size_t)idx * cb_stride + h] += acc;
+    dparams[(size_t)(idx >> 1) * blk + ((idx & 1) ? ob1 : ob0) + h] += acc;
+}
+
+static int cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return MHE_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MHE_ERR_CUDA;
+}
+
+static PlaneTensor pt(const bf16* base, int cols, int rows, long pitch, long plane_stride, int batches, long batch_stride) {
+    PlaneTensor t;
+    t.base = base; t.cols = cols; t.rows = rows; t.planes = 2; t.batches = batches;
+    t.row_pitch = pitch; t.plane_stride = plane_stride; t.batch_stride = batch_stride;
+    return t;
+}
+
+// BN = 64 while the grid would not fill the chip with 128-wide tiles
+template <bool A_MN, bool B_MN, class Epi>
+static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const Epi& e, cudaStream_t s, const char* what) {
+    const long ctas128 = (long)cdiv(g.M, BM) * cdiv(g.N, 128) * g.batches * g.ksplit;
+    if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3>(A, B, g, e, s, what);
+    return launch_tc_gemm<64, A_MN, B_MN, 3>(A, B, g, e, s, what);
+}
+
+// ---- packed weights -----------------------------------------------------------------------------------
+int pack_weights(const FlowLayout& L, const float* params, void* packed, cudaStream_t stream) {
+    Packed P(L, (bf16*)packed);
+    // W0 [H][D] -> [H][64]; W1 [H][H]; W2 [D][H] -> [64][H]; Cw [H][C]
+    MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0, L.H, kDp, 2, L.L * 2, stream));
+    MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, stream));
+    MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, stream));
+    MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cw, L.H, L.C, 2, L.L * 4, stream));
+    return MHE_OK;
+}
+
+// ---- conditioning ---------------------------------------------------------------------------------------
+int cond_fwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, int B, float* cp, void* ws_, cudaStream_t stream) {
+    Packed P(L, (bf16*)packed);
+    bf16* featp = (bf16*)ws_;   // [2][B][C]
+    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, stream));
+    PlaneTensor A = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
+    PlaneTensor Bt = pt(P.cw, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
+    GemmShape g{B, L.H, L.C, L.L * 4, 1, 0, 1};
+    EpiCondFwd e{cp, (long)L.L * 4 * L.H, L.H, params, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1};
+    return gemm<false, false>(A, Bt, g, e, stream, "tc cond fwd");
+}
+
+int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, const float* dcp, int B,
+             float* dparams, float* dfeat, void* ws_, cudaStream_t stream) {
+    Packed P(L, (bf16*)packed);
+    const long cp_ld = (long)L.L * 4 * L.H;
+    bf16* featp = (bf16*)ws_;                                   // [2][B][C]
+    bf16* dcpp = featp + (((size_t)2 * B * L.C + 511) / 512) * 512;   // [2][B][cp_ld]
+    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, stream));
+    MHE_TRY(split_planes(dcp, cp_ld, 0, B, (int)cp_ld, nullptr, dcpp, B, (int)cp_ld, 2, 1, stream));
+    {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat      (A MN-major: cols = h, rows = b; B MN-major: cols = c, rows = b)
+        PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
+        PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
+        GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
+        EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, 0};
+        MHE_TRY((gemm<true, true>(A, Bt, g, e, stream, "tc cond wgrad")));
+    }
+    cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, stream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
+    MHE_TRY(check_launch("cond bias grad"));
+    if (dfeat) {   // dfeat [B][C] = sum_idx dcp[:, idx, :] Cw[idx]   (A K-major over h; B MN-major: cols = c, rows = h)
+        MHE_TRY(cuda_ok(cudaMemsetAsync(dfeat, 0, (size_t)B * L.C * sizeof(float), stream), "memset dfeat"));
+        PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
+        PlaneTensor Bt = pt(P.cw, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
+        GemmShape g{B, L.C, L.H, L.L * 4, 1, 1, 1};
+        EpiAtomicRows e{dfeat, L.C, L.C};
+        MHE_TRY((gemm<false, true>(A, Bt, g, e, stream, "tc cond dfeat")));
+    }
+    return MHE_OK;
+}
+
+// ---- coupling layers ------------------------------------------------------------------------------------
+static int layer_nets_fwd(const FlowLayout& L, const float* params, const Packed& P, const float* cp, int R, int B, int layer, Ws& ws,
+                          cudaStream_t stream) {
+    const long cp_ld = (long)L.L * 4 * L.H;
+    const long RH = (long)R * L.H, RD = (long)R * kDp;
+    {   // G0: xm [R][64] x W0^T -> a0
+        PlaneTensor A = pt(ws.xm, kDp, R, kDp, RD, 1, 0);
+        PlaneTensor Bt = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
+        GemmShape g{R, L.H, kDp, 2, 1, 0, 1};
+        EpiHiddenPlanes e{ws.a0, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
+        MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G0")));
+    }
+    {   // G1: a0 x W1^T -> a1
+        PlaneTensor A = pt(ws.a0, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor Bt = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
+        GemmShape g{R, L.H, L.H, 2, 1, 1, 1};
+        EpiHiddenPlanes e{ws.a1, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
+        MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G1")));
+    }
+    {   // G2: a1 x W2^T + b2 -> st
+        PlaneTensor A = pt(ws.a1, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor Bt = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
+        GemmShape g{R, kDp, L.H, 2, 1, 1, 1};
+        EpiOutHead e{ws.st, L.D, (long)R * L.D, params + L.block(layer, 0) + L.ob2, (long)L.blk};
+        MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G2")));
+    }
+    return MHE_OK;
+}
+
+int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,
+             int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream) {
+    Packed P(L, (bf16*)packed);
+    Ws ws(workspace, L, R);
+    const size_t row_bytes = (size_t)R * L.D * sizeof(float);
+    if (logdet) MHE_TRY(cuda_ok(cudaMemsetAsync(logdet, 0, (size_t)R * sizeof(float), stream), "memset logdet"));
+    const int first = direction == 0 ? 0 : L.L - 1;
+    MHE_TRY(split_planes(in, L.D, 0, R, L.D, mask + (size_t)first * L.D, ws.xm, R, kDp, 2, 1, stream));
+    const float* x = in;
+    for (int step = 0; step < L.L; ++step) {
+        const int layer = direction == 0 ? step : L.L - 1 - step;
+        if (saved) {
+            float* slot = saved + (size_t)step * R * L.D;
+            if (step == 0) MHE_TRY(cuda_ok(cudaMemcpyAsync(slot, in, row_bytes, cudaMemcpyDeviceToDevice, stream), "save input"));
+            x = slot;
+        }
+        MHE_TRY(layer_nets_fwd(L, params, P, cp, R, B, layer, ws, stream));
+        float* y;
+        if (saved) y = saved + (size_t)(step + 1) * R * L.D;
+        else y = (step == L.L - 1) ? out : ((x == ws.gx) ? ws.dpre : ws.gx);
+        const bool last = step == L.L - 1;
+        const int next_layer = direction == 0 ? layer + 1 : layer - 1;
+        coupling_fwd_kernel<<<cdiv(R, 8), 256, 0, stream>>>(x, ws.st, mask + (size_t)layer * L.D, last ? nullptr : mask + (size_t)next_layer * L.D, R,
+                                                          L.D, direction, y, logdet, last ? nullptr : ws.xm);
+        MHE_TRY(check_launch("tc coupling fwd"));
+        x = y;
+    }
+    if (saved) MHE_TRY(cuda_ok(cudaMemcpyAsync(out, saved + (size_t)L.L * R * L.D, row_bytes, cudaMemcpyDeviceToDevice, stream), "copy out"));
+    return MHE_OK;
+}
+
+int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* saved, int R, int B,
+             int direction, const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp,
+             void* workspace, cudaStream_t stream) {
+    Packed P(L, (bf16*)packed);
+    Ws ws(workspace, L, R);
+    const long cp_ld = (long)L.L * 4 * L.H;
+    const long RH = (long)R * L.H, RD = (long)R * kDp;
+    const float* g = dout;
+    const int ks = R >= 8192 ? 4 : 1;   // wgrad contracts over the rows: split K once it is long
+    for (int step = L.L - 1; step >= 0; --step) {
+        const int layer = direction == 0 ? step : L.L - 1 - step;
+        const float* x = saved + (size_t)step * R * L.D;
+        const float* mrow = mask + (size_t)layer * L.D;
+        float* dblk = dparams + L.block(layer, 0);
+        MHE_TRY(split_planes(x, L.D, 0, R, L.D, mrow, ws.xm, R, kDp, 2, 1, stream));
+        MHE_TRY(layer_nets_fwd(L, params, P, cp, R, B, layer, ws, stream));      // recompute a0, a1, st
+        float* gx = (step == 0) ? din : ws.gx;
+        coupling_bwd_kernel<<<cdiv((int)RD, 256), 256, 0, stream>>>(x, ws.st, mrow, g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dpre, ws.dprep, gx);
+        MHE_TRY(check_launch("tc coupling bwd"));
+        PlaneTensor dpreK = pt(ws.dprep, kDp, R, kDp, RD, 2, 2 * RD);
+        PlaneTensor w0 = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
+        PlaneTensor w1 = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
+        PlaneTensor w2 = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
+        PlaneTensor a0 = pt(ws.a0, L.H, R, L.H, RH, 2, 2 * RH), a1 = pt(ws.a1, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor dh0 = pt(ws.dh0, L.H, R, L.H, RH, 2, 2 * RH), dh1 = pt(ws.dh1, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor xm = pt(ws.xm, kDp, R, kDp, RD, 1, 0);
+        {   // dgrad G2: dh1 = (dpre W2) * lrelu'(a1);  W2 planes [64][H] read MN-major (cols = h)
+            GemmShape s{R, L.H, kDp, 2, 1, 1, 1};
+            EpiActGradPlanes e{ws.dh1, ws.a1, L.H, RH, 2 * RH};
+            MHE_TRY((gemm<false, true>(dpreK, w2, s, e, stream, "tc dgrad G2")));
+        }
+        {   // dgrad G1: dh0 = (dh1 W1) * lrelu'(a0)
+            GemmShape s{R, L.H, L.H, 2, 1, 1, 1};
+            EpiActGradPlanes e{ws.dh0, ws.a0, L.H, RH, 2 * RH};
+            MHE_TRY((gemm<false, true>(dh1, w1, s, e, stream, "tc dgrad G1")));
+        }
+        {   // dgrad G0: gx += mask * (dh0 W0), both nets;  W0 planes [H][64] read MN-major (cols = d)
+            GemmShape s{R, kDp, L.H, 2, 1, 1, 1};
+            EpiMaskAtomicAdd e{gx, L.D, mrow};
+            MHE_TRY((gemm<false, true>(dh0, w0, s, e, stream, "tc dgrad G0")));
+        }
+        {   // dW1 [out][in] += dh1^T a0
+            GemmShape s{L.H, L.H, R, 2, ks, 1, 1};
+            EpiWgrad e{dblk + L.oW1, L.H, (long)L.blk, L.H, 0, ks > 1};
+            MHE_TRY((gemm<true, true>(dh1, a0, s, e, stream, "tc wgrad W1")));
+        }
+        {   // dW0 [out][d] += dh0^T xm
+            GemmShape s{L.H, kDp, R, 2, ks, 1, 0};
+            EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, 0, ks > 1};
+            MHE_TRY((gemm<true, true>(dh0, xm, s, e, stream, "tc wgrad W0")));
+        }
+        {   // dW2 [d][h] += dpre^T a1, computed as (a1^T dpre)[h][d] and stored transposed
+            GemmShape s{L.H, kDp, R, 2, ks, 1, 1};
+            EpiWgrad e{dblk + L.oW2, L.H, (long)L.blk, L.D, 1, ks > 1};
+            MHE_TRY((gemm<true, true>(a1, dpreK, s, e, stream, "tc wgrad W2")));
+        }
+        {
+            dim3 grid(cdiv(L.D, 64), min(64, cdiv(R, 64)), 2);
+            colsum_kernel<<<grid, 64, 0, stream>>>(ws.dpre, R, L.D, (long)R * L.D, dblk + L.ob2, (long)L.blk);
+            MHE_TRY(check_launch("tc db2"));
+        }
+        {
+            dim3 grid(cdiv(L.H, 128), B, 2);
+            hyp_sum_planes_kernel<<<grid, 128, 0, stream>>>(ws.dh0, R, B, L.H, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H);
+            MHE_TRY(check_launch("tc dcp0"));
+            hyp_sum_planes_kernel<<<grid, 128, 0, stream>>>(ws.dh1, R, B, L.H, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H);
+            MHE_TRY(check_launch("tc dcp1"));
+        }
+        g = gx;
+    }
+    return MHE_OK;
+}
+
+}  // namespace tcflow
+}  // namespace mhe

@@ -1,0 +1,64 @@
+// Declarations of the tensor-core flow path (flow_tc.cu), shared with the C-ABI dispatch in flow.cu.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace mhe {
+namespace tcflow {
+
+constexpr int kDp = 64;   // flow dimension padded to one 64-wide K block / N tile
+
+inline bool supported(const FlowLayout& L) { return L.D <= kDp && L.H % 64 == 0 && L.C % 8 == 0; }
+
+// packed split-bf16 weights: w0 [L*2][2][H][64], w1 [L*2][2][H][H], w2 [L*2][2][64][H], cw [L*4][2][H][C]
+struct Packed {
+    __nv_bfloat16 *w0, *w1, *w2, *cw;
+    static size_t elems(const FlowLayout& L) {
+        return (size_t)L.L * 2 * 2 * ((size_t)L.H * kDp * 2 + (size_t)L.H * L.H) + (size_t)L.L * 4 * 2 * L.H * L.C + 4 * 512;
+    }
+    Packed(const FlowLayout& L, __nv_bfloat16* base) {
+        auto take = [&](size_t n) { __nv_bfloat16* p = base; base += (n + 511) / 512 * 512; return p; };
+        w0 = take((size_t)L.L * 2 * 2 * L.H * kDp);
+        w1 = take((size_t)L.L * 2 * 2 * L.H * L.H);
+        w2 = take((size_t)L.L * 2 * 2 * kDp * L.H);
+        cw = take((size_t)L.L * 4 * 2 * L.H * L.C);
+    }
+};
+
+// per-pass scratch: activations as planes, small fp32 buffers
+struct Ws {
+    __nv_bfloat16 *xm, *a0, *a1, *dh0, *dh1, *dprep;
+    float *st, *dpre, *gx;
+    static size_t bytes(const FlowLayout& L, int R) {
+        const size_t act = (size_t)2 * 2 * R * L.H * 2, small = (size_t)2 * 2 * R * kDp * 2;
+        return 4 * act + 2 * small + ((size_t)5 * R * L.D) * 4 + 16 * 1024;
+    }
+    Ws(void* base_, const FlowLayout& L, int R) {
+        uint8_t* base = (uint8_t*)base_;
+        auto take = [&](size_t n) { uint8_t* p = base; base += (n + 1023) / 1024 * 1024; return p; };
+        const size_t act = (size_t)2 * 2 * R * L.H * 2;
+        xm = (__nv_bfloat16*)take((size_t)2 * R * kDp * 2);
+        a0 = (__nv_bfloat16*)take(act); a1 = (__nv_bfloat16*)take(act);
+        dh0 = (__nv_bfloat16*)take(act); dh1 = (__nv_bfloat16*)take(act);
+        dprep = (__nv_bfloat16*)take((size_t)2 * 2 * R * kDp * 2);
+        st = (float*)take((size_t)2 * R * L.D * 4);
+        dpre = (float*)take((size_t)2 * R * L.D * 4);
+        gx = (float*)take((size_t)R * L.D * 4);
+    }
+};
+
+inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
+    return ((size_t)2 * B * L.C + 512 + (size_t)2 * B * L.L * 4 * L.H) * 2 + 4096;
+}
+
+int pack_weights(const FlowLayout& L, const float* params, void* packed, cudaStream_t stream);
+int cond_fwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, int B, float* cp, void* ws, cudaStream_t stream);
+int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, const float* dcp, int B, float* dparams,
+             float* dfeat, void* ws, cudaStream_t stream);
+int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,
+             int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream);
+int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* saved, int R, int B,
+             int direction, const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp,
+             void* workspace, cudaStream_t stream);
+
+}  // namespace tcflow
+}  // namespace mhe

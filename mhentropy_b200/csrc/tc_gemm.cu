@@ -112,7 +112,7 @@ int split_planes(const float* src, long src_ld, long src_batch, int rows, int co
 
 struct EpiRawStore {   // C[batch][row][col] = acc  (+= when accumulate; atomic when K is split)
     float* C; long ldc; long strideC; int accumulate; int atomic;
-    __device__ void operator()(int b, int, int row, int col0, const float* v, const GemmShape& g) const {
+    __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape& g) const {
         float* p = C + (long)b * strideC + (long)row * ldc + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -153,7 +153,7 @@ int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K,
     if (b_mn) { tb.cols = N; tb.rows = K; } else { tb.cols = K; tb.rows = N; }
     ta.row_pitch = ta.cols; tb.row_pitch = tb.cols;
     MHE_REQUIRE(ta.cols % 8 == 0 && tb.cols % 8 == 0, "tc_gemm_raw: contiguous extents must be multiples of 8");
-    GemmShape g{M, N, K, batches, ksplit};
+    GemmShape g{M, N, K, batches, ksplit, 1, 1};
     EpiRawStore e{C, N, (long)M * N, 0, ksplit > 1};
     if (ksplit > 1 && cudaMemsetAsync(C, 0, (size_t)batches * M * N * sizeof(float), stream) != cudaSuccess) return MHE_ERR_CUDA;
 #define MHE_RAW(BN_, AMN_, BMN_, NP_) return launch_tc_gemm<BN_, AMN_, BMN_, NP_>(ta, tb, g, e, stream, "tc raw")

@@ -34,6 +34,8 @@ struct PlaneTensor {          // [batches][planes][rows][cols] bf16, element str
 };
 
 int make_tensor_map(CUtensorMap* map, const PlaneTensor& t, int box_rows);
+int split_planes(const float* src, long src_ld, long src_batch, int rows, int cols, const float* colscale, __nv_bfloat16* dst, int rows_p,
+                 int cols_p, int planes, int batches, cudaStream_t stream);
 
 // ---- device primitives ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +109,8 @@ struct GemmShape {
     int M, N, K;       // logical extents (rows of A, rows/cols of B, contraction)
     int batches;       // grid.z = batches * ksplit
     int ksplit;
+    int a_batch_mul;   // batch coordinate of A = batch * a_batch_mul (0 broadcasts one A to every batch)
+    int b_batch_mul;
 };
 
 template <int BN, int NPL>
@@ -170,15 +174,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int k0 = (kb_begin + i) * BK;
 #pragma unroll
                 for (int p = 0; p < NPL; ++p) {
-                    if (!A_MN) tma_load_4d(stage_a(s, p), &mapA, full, k0, m0, p, batch);
+                    if (!A_MN) tma_load_4d(stage_a(s, p), &mapA, full, k0, m0, p, batch * g.a_batch_mul);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, &mapA, full, m0 + 64 * j, k0, p, batch);
+                        for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, &mapA, full, m0 + 64 * j, k0, p, batch * g.a_batch_mul);
                     }
-                    if (!B_MN) tma_load_4d(stage_b(s, p), &mapB, full, k0, n0, p, batch);
+                    if (!B_MN) tma_load_4d(stage_b(s, p), &mapB, full, k0, n0, p, batch * g.b_batch_mul);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, &mapB, full, n0 + 64 * j, k0, p, batch);
+                        for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, &mapB, full, n0 + 64 * j, k0, p, batch * g.b_batch_mul);
                     }
                 }
             }

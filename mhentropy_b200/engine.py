@@ -45,7 +45,13 @@ class TrainStep:
         self.dcp = f(B, cpf)
         self.djtr, self.dz, self.dlog_q = f(R, 21, 3), f(R, 61), f(R)
         self.dx, self.dz_det, self.dz0, self.dfeat = f(R, D), f(B, 16), f(R, D), f(B, flow.cond_dim)
-        self.ws_bytes = max(L.mhe_flow_workspace_bytes(self.shape, R), L.mhe_mano_workspace_bytes(R, 0))
+        self.tc = flow.precision != 'fp32'
+        self.packed = None
+        if self.tc:
+            self.packed = torch.empty(L.mhe_flow_packed_bytes(self.shape), dtype=torch.uint8, device=dev)
+        self.cws_bytes = L.mhe_flow_cond_workspace_bytes(self.shape, B) if self.tc else 0
+        self.cws = torch.empty(max(self.cws_bytes, 16), dtype=torch.uint8, device=dev)
+        self.ws_bytes = max(L.mhe_flow_workspace_bytes(self.shape, R, int(self.tc)), L.mhe_mano_workspace_bytes(R, 0))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.graph = None
         self.use_graph = use_graph
@@ -57,9 +63,12 @@ class TrainStep:
         R, B, shape, ws, wsb = self.R, self.B, self.shape, ptr(self.ws), self.ws_bytes
         z = self.z
         theta, beta = z.data_ptr(), z.data_ptr() + 48 * 4
+        pk, cws, cwsb = ptr(self.packed), ptr(self.cws), self.cws_bytes
         # ---- forward
-        check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), ptr(self.feat), B, ptr(self.cp), s), 'cond_fwd')
-        check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
+        if self.tc:   # weights change between steps: refresh their split-bf16 planes inside the step
+            check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, s), 'pack_weights')
+        check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
+        check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
                                   ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
         check(L.mhe_std_normal_logp_fwd(ptr(self.z0), ptr(self.logdet), -1.0, R, shape.dim, ptr(self.log_q), s), 'log_q')
         check(L.mhe_combine_z_fwd(ptr(self.x), ptr(self.z_det), R, B, ptr(z), s), 'combine_z')
@@ -77,10 +86,10 @@ class TrainStep:
                              ws, wsb, s), 'mano_bwd')
         check(L.mhe_combine_z_bwd(ptr(self.dz), R, B, ptr(self.dx), ptr(self.dz_det), s), 'combine_z_bwd')
         # log_q = log N(z0) - logdet  ->  dL/dlogdet = -dL/dlog_q
-        check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
+        check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
                                   ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
-        check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat), s),
-              'cond_bwd')
+        check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), pk, ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat),
+                                  cws, cwsb, s), 'cond_bwd')
 
     def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
         """Copy one batch (host or device tensors) into the static input buffers."""

@@ -74,32 +74,39 @@ class _CondFn(torch.autograd.Function):
     """cp = hoisted conditioning projections of every layer (``flows.py:107-109``)."""
 
     @staticmethod
-    def forward(ctx, feat, flat, shape):
+    def forward(ctx, feat, flat, shape, packed):
         feat = feat.contiguous()
         _lib.require_cuda_f32(feat, flat)
         B = feat.shape[0]
-        cp = torch.empty(B, lib().mhe_flow_cp_floats_per_image(shape), device=feat.device, dtype=torch.float32)
-        check(lib().mhe_flow_cond_fwd(shape, ptr(flat), ptr(feat), B, ptr(cp), stream_ptr(feat.device)), 'mhe_flow_cond_fwd')
+        dev = feat.device
+        cp = torch.empty(B, lib().mhe_flow_cp_floats_per_image(shape), device=dev, dtype=torch.float32)
+        wsb = lib().mhe_flow_cond_workspace_bytes(shape, B) if packed is not None else 0
+        ws = _lib.WORKSPACE.get(wsb, dev, 'cond') if wsb else None
+        check(lib().mhe_flow_cond_fwd(shape, ptr(flat), ptr(packed), ptr(feat), B, ptr(cp), ptr(ws), wsb, stream_ptr(dev)), 'mhe_flow_cond_fwd')
         ctx.save_for_backward(feat, flat)
-        ctx.shape = shape
+        ctx.shape, ctx.packed = shape, packed
         return cp
 
     @staticmethod
     def backward(ctx, dcp):
         feat, flat = ctx.saved_tensors
         dcp = dcp.contiguous()
+        dev = feat.device
         dflat = torch.zeros_like(flat)
         dfeat = torch.empty_like(feat) if ctx.needs_input_grad[0] else None
-        check(lib().mhe_flow_cond_bwd(ctx.shape, ptr(flat), ptr(feat), ptr(dcp), feat.shape[0], ptr(dflat), ptr(dfeat),
-                                      stream_ptr(feat.device)), 'mhe_flow_cond_bwd')
-        return dfeat, dflat, None
+        B = feat.shape[0]
+        wsb = lib().mhe_flow_cond_workspace_bytes(ctx.shape, B) if ctx.packed is not None else 0
+        ws = _lib.WORKSPACE.get(wsb, dev, 'cond') if wsb else None
+        check(lib().mhe_flow_cond_bwd(ctx.shape, ptr(flat), ptr(ctx.packed), ptr(feat), ptr(dcp), B, ptr(dflat), ptr(dfeat), ptr(ws), wsb,
+                                      stream_ptr(dev)), 'mhe_flow_cond_bwd')
+        return dfeat, dflat, None, None
 
 
 class _FlowPassFn(torch.autograd.Function):
     """One pass through the coupling layers; returns (out, logdet)."""
 
     @staticmethod
-    def forward(ctx, inp, cp, flat, mask, shape, direction, B):
+    def forward(ctx, inp, cp, flat, mask, shape, direction, B, packed):
         inp = inp.contiguous()
         _lib.require_cuda_f32(inp, cp, flat, mask)
         R, D = inp.shape
@@ -108,13 +115,13 @@ class _FlowPassFn(torch.autograd.Function):
         logdet = torch.empty(R, device=dev, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad[:3])
         saved = torch.empty((shape.layers + 1), R, D, device=dev, dtype=torch.float32) if need_grad else None
-        wsb = lib().mhe_flow_workspace_bytes(shape, R)
+        wsb = lib().mhe_flow_workspace_bytes(shape, R, int(packed is not None))
         ws = _lib.WORKSPACE.get(wsb, dev)
-        check(lib().mhe_flow_pass_fwd(shape, ptr(flat), ptr(mask), ptr(cp), ptr(inp), R, B, direction, ptr(out), ptr(logdet),
+        check(lib().mhe_flow_pass_fwd(shape, ptr(flat), ptr(packed), ptr(mask), ptr(cp), ptr(inp), R, B, direction, ptr(out), ptr(logdet),
                                       ptr(saved), ptr(ws), wsb, stream_ptr(dev)), 'mhe_flow_pass_fwd')
         if need_grad:
             ctx.save_for_backward(cp, flat, mask, saved)
-        ctx.shape, ctx.direction, ctx.B = shape, direction, B
+        ctx.shape, ctx.direction, ctx.B, ctx.packed = shape, direction, B, packed
         return out, logdet
 
     @staticmethod
@@ -128,12 +135,12 @@ class _FlowPassFn(torch.autograd.Function):
         din = torch.empty(R, D, device=dev, dtype=torch.float32)
         dflat = torch.zeros_like(flat)
         dcp = torch.zeros_like(cp)
-        wsb = lib().mhe_flow_workspace_bytes(shape, R)
+        wsb = lib().mhe_flow_workspace_bytes(shape, R, int(ctx.packed is not None))
         ws = _lib.WORKSPACE.get(wsb, dev)
-        check(lib().mhe_flow_pass_bwd(shape, ptr(flat), ptr(mask), ptr(cp), ptr(saved), R, ctx.B, ctx.direction, ptr(dout),
+        check(lib().mhe_flow_pass_bwd(shape, ptr(flat), ptr(ctx.packed), ptr(mask), ptr(cp), ptr(saved), R, ctx.B, ctx.direction, ptr(dout),
                                       ptr(dlogdet), 1.0, ptr(din), ptr(dflat), ptr(dcp), ptr(ws), wsb, stream_ptr(dev)),
               'mhe_flow_pass_bwd')
-        return din, dcp, dflat, None, None, None, None
+        return din, dcp, dflat, None, None, None, None, None
 
 
 class _StdNormalLogpFn(torch.autograd.Function):
@@ -158,6 +165,13 @@ class _StdNormalLogpFn(torch.autograd.Function):
         check(lib().mhe_std_normal_logp_bwd(ptr(z), ptr(dlogp), z.shape[0], z.shape[1], ptr(dz), stream_ptr(z.device)),
               'mhe_std_normal_logp_bwd')
         return dz, dlogp
+
+
+def lib_has_tc(shape) -> bool:
+    try:
+        return lib().mhe_flow_packed_bytes(shape) > 0
+    except _lib.MheError:
+        return False
 
 
 class RealNVP(nn.Module):
@@ -199,6 +213,10 @@ class RealNVP(nn.Module):
         self._flat = None
         self._slots = None
         self._last_flat_grad = None
+        self._packed = None
+        self._packed_sig = None
+        # 'bf16x3': tcgen05 tensor cores, split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate); 'fp32': CUDA cores, exact
+        self.precision = 'bf16x3' if (self._kernel_ok and lib_has_tc(self._shape)) else 'fp32'
 
     # ------------------------------------------------------------------ flat parameter storage
     def _named_flow_params(self):
@@ -239,6 +257,26 @@ class RealNVP(nn.Module):
             self._adopt(device)
         return self._flat
 
+    def packed_weights(self, device=None):
+        """Split-bf16 planes of the weights for the tensor-core path (None on the fp32 path); refreshed
+        whenever the parameters have been modified in place (optimizer step, load_state_dict)."""
+        if self.precision == 'fp32':
+            return None
+        if self.precision != 'bf16x3':
+            raise ValueError(f"precision must be 'fp32' or 'bf16x3', got {self.precision!r}")
+        flat = self.flat_parameters(device)
+        ps = self._slots
+        sig = (flat.data_ptr(), flat._version, ps[0][0]._version, ps[len(ps) // 2][0]._version, ps[-1][0]._version)
+        if self._packed is None or self._packed.device != flat.device or sig != self._packed_sig:
+            nbytes = lib().mhe_flow_packed_bytes(self._shape)
+            if nbytes == 0:
+                raise _lib.MheError('this flow shape is outside the tensor-core path; set precision="fp32"')
+            if self._packed is None or self._packed.device != flat.device:
+                self._packed = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+            check(lib().mhe_flow_pack_weights(self._shape, ptr(flat), ptr(self._packed), stream_ptr(flat.device)), 'mhe_flow_pack_weights')
+            self._packed_sig = sig
+        return self._packed
+
     def _split_flat(self, gflat):
         return [gflat[off:off + n].view(shape) for _, off, n, shape in self._slots]
 
@@ -261,14 +299,15 @@ class RealNVP(nn.Module):
     def cond_projections(self, cond):
         """Hoisted ``c.{0,1}(cond)`` of all layers, (B, L*4*H); kernel path only."""
         flat = self._flat_for_autograd(cond.device)
-        return _CondFn.apply(cond.float(), flat, self._shape)
+        return _CondFn.apply(cond.float(), flat, self._shape, self.packed_weights(cond.device))
 
     def _pass(self, inp, cond, direction, cp=None, images=None):
         flat = self._flat_for_autograd(inp.device)
+        packed = self.packed_weights(inp.device)
         if cp is None:
-            cp = _CondFn.apply(cond.float(), flat, self._shape)
+            cp = _CondFn.apply(cond.float(), flat, self._shape, packed)
             images = cond.shape[0]
-        return _FlowPassFn.apply(inp.float(), cp, flat, self.mask, self._shape, direction, images)
+        return _FlowPassFn.apply(inp.float(), cp, flat, self.mask, self._shape, direction, images, packed)
 
     def forward_p(self, z, cond=None):
         """z -> x (``flows.py:210-217``)."""
@@ -350,8 +389,9 @@ class RealNVP(nn.Module):
         feat (B, F) one row per image; z0 (S*B, dim) hypothesis-major.  Returns x (S*B, dim), log_q (S*B,).
         """
         flat = self._flat_for_autograd(z0.device)
-        cp = _CondFn.apply(feat.float(), flat, self._shape)
-        x, logdet = _FlowPassFn.apply(z0.float(), cp, flat, self.mask, self._shape, 0, feat.shape[0])
+        packed = self.packed_weights(z0.device)
+        cp = _CondFn.apply(feat.float(), flat, self._shape, packed)
+        x, logdet = _FlowPassFn.apply(z0.float(), cp, flat, self.mask, self._shape, 0, feat.shape[0], packed)
         log_q = _StdNormalLogpFn.apply(z0.float(), -logdet)
         return x * self.scale, log_q
 

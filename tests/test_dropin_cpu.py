@@ -97,8 +97,9 @@ def test_cuda_path_fails_loudly_without_gpu():
 def test_invalid_arguments_return_error_codes():
     L = _lib.lib()
     shape = _lib.FlowShape(45, 512, 512, 12)
-    st = L.mhe_flow_cond_fwd(shape, None, None, 4, None, None)
+    st = L.mhe_flow_cond_fwd(shape, None, None, None, 4, None, None, 0, None)
     assert st == 1 and b'null' in L.mhe_last_error_string()
     assert L.mhe_flow_param_offset(_lib.FlowShape(1, 0, 0, 0), 0, 0, 0) == ctypes.c_size_t(-1).value
+    assert L.mhe_flow_packed_bytes(shape) > 0 and L.mhe_flow_packed_bytes(_lib.FlowShape(45, 48, 16, 6)) == 0   # hidden % 64
     st = L.mhe_reproj_loss_fwd(ctypes.byref(_lib.LossCfg()), None, None, None, None, None, 7, 2, None, None, None, None, None, None, None)
     assert st == 1

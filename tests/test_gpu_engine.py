@@ -21,11 +21,13 @@ def rel(a, b):
 
 @pytest.mark.parametrize('use_graph', [False, True])
 @pytest.mark.parametrize('B,S', [(8, 10), (5, 3)])
-def test_engine_matches_autograd_path_and_oracle(use_graph, B, S):
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_engine_matches_autograd_path_and_oracle(use_graph, B, S, precision):
     mano = synthetic_mano(0)
     sd = fo.init_state_dict(seed=0)
     head = MHEntHead(mano_data=mano)
     head.q_z_giv_i.load_state_dict(sd)
+    head.q_z_giv_i.precision = precision
     head = head.to(DEV)
     batch = synthetic_batch(B, S, seed=31)
     devb = {k: v.to(DEV) for k, v in batch.items()}

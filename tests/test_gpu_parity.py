@@ -37,8 +37,12 @@ def relerr(a, b):
     return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
 
 
-def build_flow(sd, cfg):
+PRECISIONS = ['fp32', 'bf16x3']
+
+
+def build_flow(sd, cfg, precision='fp32'):
     flow = RealNVP(**cfg)
+    flow.precision = precision
     missing = flow.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     return flow.to(DEV)
@@ -48,13 +52,14 @@ SMALL = dict(dim=45, tsfm_on=32, kemb=False, jointN=21, h_dims=[64, 64], num_ste
 PROD = dict(dim=45, tsfm_on=512, kemb=False, jointN=21, h_dims=[512, 512], num_steps=6)
 
 
-def test_flow_small_against_golden(golden_dir):
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_flow_small_against_golden(golden_dir, precision):
     fx = load(golden_dir, 'flow_small.npz')
     sd = {k[2:]: v for k, v in fx.items() if k.startswith('w/')}
-    flow = build_flow(sd, SMALL)
+    flow = build_flow(sd, SMALL, precision)
     feat, z0 = T(fx['feat'], grad=True), T(fx['z0'], grad=True)
     x = flow.forward_p(z0, cond=feat)
-    assert np.abs(x.detach().cpu().numpy() - fx['x']).max() < 2e-5
+    assert np.abs(x.detach().cpu().numpy() - fx['x']).max() < (2e-5 if precision == 'fp32' else 5e-4)
     (x * T(fx['wx'])).sum().backward()
     assert relerr(feat.grad, fx['sample_dfeat']) < 1e-3
     assert relerr(z0.grad, fx['sample_dz0']) < 1e-3
@@ -63,7 +68,7 @@ def test_flow_small_against_golden(golden_dir):
     flow.zero_grad()
     xin, feat2 = T(fx['xin'], grad=True), T(fx['feat'], grad=True)
     z, lp = flow.log_prob(xin, logvar=feat2, return_z=True)
-    assert np.abs(z.detach().cpu().numpy() - fx['z']).max() < 2e-5
+    assert np.abs(z.detach().cpu().numpy() - fx['z']).max() < (2e-5 if precision == 'fp32' else 5e-4)
     assert relerr(lp, fx['log_prob']) < 1e-4
     (lp * T(fx['wl'])).sum().backward()
     assert relerr(xin.grad, fx['logprob_dx']) < 1e-3
@@ -77,13 +82,14 @@ def test_flow_small_against_golden(golden_dir):
     assert relerr(lq, fx['log_prob_of_x']) < 1e-4      # fused single-pass log q == reference's second pass
 
 
-def test_flow_prod_against_golden_and_oracle(golden_dir):
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_flow_prod_against_golden_and_oracle(golden_dir, precision):
     fx = load(golden_dir, 'flow_prod.npz')
     sd = fo.init_state_dict(seed=int(fx['seed']))
-    flow = build_flow(sd, PROD)
+    flow = build_flow(sd, PROD, precision)
     feat, z0 = T(fx['feat'], grad=True), T(fx['z0'], grad=True)
     x = flow.forward_p(z0, cond=feat)
-    assert np.abs(x.detach().cpu().numpy() - fx['x']).max() < 5e-5
+    assert np.abs(x.detach().cpu().numpy() - fx['x']).max() < (5e-5 if precision == 'fp32' else 2e-3)
     (x * T(fx['wx'])).sum().backward()
     assert relerr(feat.grad, fx['sample_dfeat']) < 1e-3
     bad = []
@@ -102,9 +108,10 @@ def test_flow_prod_against_golden_and_oracle(golden_dir):
     assert relerr(lp, fx['log_prob']) < 1e-4
 
 
-def test_flow_hoisted_conditioning_matches_repeated_features():
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_flow_hoisted_conditioning_matches_repeated_features(precision):
     sd = fo.init_state_dict(dim=45, cond_dim=32, h_dims=(64, 64), num_steps=2, seed=5)
-    flow = build_flow(sd, SMALL)
+    flow = build_flow(sd, SMALL, precision)
     g = torch.Generator().manual_seed(3)
     B, S = 3, 4
     feat = torch.randn(B, 32, generator=g).to(DEV)
@@ -113,13 +120,14 @@ def test_flow_hoisted_conditioning_matches_repeated_features():
         x_hoist = flow.sample(B * S, logvar=feat, z0=z0)
         x_rep = flow.sample(B * S, logvar=feat.repeat(S, 1), z0=z0)
         x_or = fo.sample(sd, z0.cpu(), feat.cpu().repeat(S, 1))
-    assert torch.allclose(x_hoist, x_rep, atol=1e-6)
-    assert torch.allclose(x_hoist.cpu(), x_or, atol=2e-5)
+    assert torch.allclose(x_hoist, x_rep, atol=1e-5)
+    assert torch.allclose(x_hoist.cpu(), x_or, atol=2e-5 if precision == 'fp32' else 5e-4)
 
 
-def test_flow_roundtrip_and_empty():
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_flow_roundtrip_and_empty(precision):
     sd = fo.init_state_dict(seed=1)
-    flow = build_flow(sd, PROD)
+    flow = build_flow(sd, PROD, precision)
     g = torch.Generator().manual_seed(0)
     feat = torch.randn(16, 512, generator=g).to(DEV)
     z0 = torch.randn(16 * 8, 45, generator=g).to(DEV)
@@ -128,7 +136,7 @@ def test_flow_roundtrip_and_empty():
         z, logdet = flow.backward_p(x, cond=feat)
         x2, lq = flow.sample_with_log_prob(feat, z0, 8)
         lp = flow.log_prob(x, logvar=feat)
-    assert (z - z0).abs().max() < 1e-4                  # backward_p(forward_p(z)) == z
+    assert (z - z0).abs().max() < (1e-4 if precision == 'fp32' else 2e-3)   # backward_p(forward_p(z)) == z
     assert torch.equal(x, x2)
     assert relerr(lq, lp) < 1e-4
     with torch.no_grad():
@@ -176,13 +184,15 @@ def test_mano_large_batch_vs_oracle():
 
 @pytest.mark.parametrize('name', ['mhent_small.npz', 'mhent_prod.npz'])
 @pytest.mark.parametrize('fused', [True, False])
-def test_mhent_loss_against_golden(golden_dir, name, fused):
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_mhent_loss_against_golden(golden_dir, name, fused, precision):
     fx = load(golden_dir, name)
     small = name == 'mhent_small.npz'
     cfg = dict(h_dims=[64, 64], num_steps=2, tsfm_on=32) if small else {}
     head = MHEntHead(q_z_giv_i_cfg=cfg, mano_data=synthetic_mano(0), feat_dim=32 if small else 512)
     sd = {k[2:]: torch.as_tensor(v) for k, v in fx.items() if k.startswith('w/')} if small else fo.init_state_dict(seed=int(fx['seed']))
     head.q_z_giv_i.load_state_dict(sd)
+    head.q_z_giv_i.precision = precision
     head = head.to(DEV)
     feat, z_det = T(fx['feat'], grad=True), T(fx['z_det'], grad=True)
     y = {'crop_uv': T(fx['crop_uv']), 'vis': T(fx['vis'])}
@@ -209,7 +219,8 @@ def test_mhent_loss_against_golden(golden_dir, name, fused):
         assert (num / den) ** 0.5 < 1e-3
 
 
-def test_training_step_vs_fp64_oracle_config1():
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_training_step_vs_fp64_oracle_config1(precision):
     """Config 1 shape (B=8, S=10, production flow): CUDA vs the fp64 oracle, error no worse than a small
     multiple of the fp32 oracle's own error against fp64."""
     mano = synthetic_mano(0)
@@ -230,6 +241,7 @@ def test_training_step_vs_fp64_oracle_config1():
     o32, df32, g32 = run_oracle(torch.float32)
     head = MHEntHead(mano_data=mano)
     head.q_z_giv_i.load_state_dict(sd)
+    head.q_z_giv_i.precision = precision
     head = head.to(DEV)
     feat = batch['feat'].detach().clone().to(DEV).requires_grad_(True)
     y = {'crop_uv': batch['crop_uv'].to(DEV), 'vis': batch['vis'].to(DEV)}
