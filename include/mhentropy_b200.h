@@ -82,6 +82,9 @@ size_t mhe_flow_packed_bytes(mhe_flow_shape s);
 int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, void* stream);
 /* bytes of scratch needed by the flow passes over R rows (forward and backward) on the chosen path */
 size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core);
+/* bytes of the saved-for-backward block a forward pass over R rows fills: the layer inputs on the fp32 path (hidden
+ * activations are recomputed), layer inputs + head outputs + hidden activations on the tensor-core path          */
+size_t mhe_flow_saved_bytes(mhe_flow_shape s, int R, int tensor_core);
 /* bytes of scratch the tensor-core conditioning GEMMs need for B images (0 when that path is unsupported) */
 size_t mhe_flow_cond_workspace_bytes(mhe_flow_shape s, int B);
 
@@ -98,8 +101,7 @@ int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const void* packed,
  *   direction 0: z -> x, layers 0..L-1,  x' = m x + (1-m)(x e^s + t),  logdet += sum s   (flows.py:210-217)
  *   direction 1: x -> z, layers L-1..0,  z' = (1-m)(z - t) e^-s + m z,  logdet -= sum s   (flows.py:219-227)
  * in [R][D] -> out [R][D], logdet [R] (may be NULL).  Row r uses cp of image r % B.
- * saved: NULL, or [(L+1)][R][D] receiving each layer's input (processing order) and the output —
- * the only activations the backward needs (hidden activations are recomputed).                   */
+ * saved: NULL, or a block of mhe_flow_saved_bytes() receiving what the backward needs.            */
 int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
                       const float* in, int R, int B, int direction,
                       float* out, float* logdet, float* saved,

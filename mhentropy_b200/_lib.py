@@ -45,6 +45,7 @@ _SIGNATURES = {
     'mhe_flow_param_offset': (c_size_t, [FlowShape, c_int, c_int, c_int]),
     'mhe_flow_cp_floats_per_image': (c_size_t, [FlowShape]),
     'mhe_flow_workspace_bytes': (c_size_t, [FlowShape, c_int, c_int]),
+    'mhe_flow_saved_bytes': (c_size_t, [FlowShape, c_int, c_int]),
     'mhe_flow_cond_workspace_bytes': (c_size_t, [FlowShape, c_int]),
     'mhe_flow_packed_bytes': (c_size_t, [FlowShape]),
     'mhe_flow_pack_weights': (c_int, [FlowShape, _P, _P, _P]),

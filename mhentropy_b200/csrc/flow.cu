@@ -257,6 +257,13 @@ size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core) {
     return FlowWs::floats(L, R) * sizeof(float);
 }
 
+size_t mhe_flow_saved_bytes(mhe_flow_shape s, int R, int tensor_core) {
+    if (!valid_shape(s) || R < 0) return 0;
+    FlowLayout L(s);
+    if (tensor_core) return tcflow::supported(L) ? tcflow::Saved::bytes(L, R) : 0;
+    return (size_t)(L.L + 1) * R * L.D * sizeof(float);
+}
+
 size_t mhe_flow_cond_workspace_bytes(mhe_flow_shape s, int B) {
     if (!valid_shape(s) || B < 0) return 0;
     FlowLayout L(s);

@@ -58,23 +58,27 @@ struct EpiOutHead {   // st[batch][row][col] = batch == 0 ? tanh(acc + b2) : acc
         }
     }
 };
-struct EpiActGradPlanes {   // out = acc * lrelu'(act)  (sign of the hi plane is the sign of the activation)
-    bf16* out; const bf16* act_hi; long ld; long plane_stride; long batch_stride;
+struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes; dcp[row % B][...] += dh  (sum over the hypotheses of an image)
+    bf16* out; const bf16* act_hi; long ld; long plane_stride; long batch_stride; long act_plane_stride; long act_batch_stride;
+    float* dcp; long cp_ld; long cp_off; long cp_bstride; int B;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
-        const long off = (long)b * batch_stride + (long)row * ld + col0;
-        const uint4* a = reinterpret_cast<const uint4*>(act_hi + off);
+        const uint4* a = reinterpret_cast<const uint4*>(act_hi + (long)b * act_batch_stride + (long)row * ld + col0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint4 t = a[j];
             const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero (the hi plane carries the activation's sign)
                 const uint32_t e0 = w[i] & 0xFFFFu, e1 = w[i] >> 16;
                 v[8 * j + 2 * i] *= ((e0 & 0x8000u) == 0 && (e0 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
                 v[8 * j + 2 * i + 1] *= ((e1 & 0x8000u) == 0 && (e1 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
             }
         }
+        float* g = dcp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(g + j, v[j]);
+        const long off = (long)b * batch_stride + (long)row * ld + col0;
         store_planes32(out + off, out + off + plane_stride, v);
     }
 };
@@ -157,55 +161,44 @@ __global__ void coupling_fwd_kernel(const float* __restrict__ x, const float* __
     }
 }
 
-// coupling backward (see flow.cu) + split planes of the head gradients [2 nets][2 planes][R][64]
-__global__ void coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ mask,
+// coupling backward (see flow.cu) + split planes of the head gradients [2 nets][2 planes][R][64] + the bias
+// gradient db2 += colsum(dpre).  Block = 4 row slots x 64 columns, 32 rows per block.
+__global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ mask,
                                     const float* g, const float* __restrict__ gl, float gl_scale, int R, int D, int direction,
-                                    float* __restrict__ dpre, bf16* __restrict__ dprep, float* gx) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long)R * kDp) return;
-    const int r = (int)(i / kDp), d = (int)(i % kDp);
-    float ds = 0.f, dt = 0.f;
-    if (d < D) {
-        const long k = (long)r * D + d;
-        const float gv = g[k];
-        float dx = gv;
-        if (mask[d] == 0.f) {
-            const float s = st[k], t = st[(long)R * D + k], xv = x[k];
-            const float glv = gl ? gl_scale * gl[r] : 0.f;
-            if (direction == 0) { const float e = expf(s); dx = gv * e; dt = gv; ds = gv * xv * e + glv; }
-            else { const float e = expf(-s); dx = gv * e; dt = -gv * e; ds = -gv * (xv - t) * e - glv; }
-            ds *= (1.f - s * s);
-        }
-        dpre[k] = ds;
-        dpre[(long)R * D + k] = dt;
-        gx[k] = dx;
-    }
+                                    bf16* __restrict__ dprep, float* gx, float* __restrict__ db2, long db2_stride) {
+    __shared__ float red[2][4][kDp];
+    const int d = threadIdx.x & (kDp - 1), slot = threadIdx.x >> 6;
     const long ps = (long)R * kDp;
-    put_planes(dprep + i, ps, ds);
-    put_planes(dprep + 2 * ps + i, ps, dt);
-}
-
-// dcp[b][off + z*zstride + n] += sum_s (hi + lo)[z][s*B + b][n]
-__global__ void hyp_sum_planes_kernel(const bf16* __restrict__ in, int R, int B, int N, long plane_stride, long batch_stride,
-                                      float* __restrict__ dcp, long cp_ld, long off, long zstride) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y, z = blockIdx.z;
-    if (n >= N) return;
-    const bf16* p = in + (long)z * batch_stride;
-    float acc = 0.f;
-    for (int r = b; r < R; r += B) acc += __bfloat162float(p[(long)r * N + n]) + __bfloat162float(p[plane_stride + (long)r * N + n]);
-    dcp[(long)b * cp_ld + off + (long)z * zstride + n] += acc;
-}
-
-__global__ void colsum_kernel(const float* __restrict__ in, int M, int N, long strideIn, float* __restrict__ out, long strideOut) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.z;
-    if (n >= N) return;
-    const int per = (M + gridDim.y - 1) / gridDim.y;
-    const int mb = blockIdx.y * per, me = min(M, mb + per);
-    float acc = 0.f;
-    for (int m = mb; m < me; ++m) acc += in[(long)z * strideIn + (long)m * N + n];
-    if (me > mb) atomicAdd(out + (long)z * strideOut + n, acc);
+    const float m = d < D ? mask[d] : 1.f;
+    float sds = 0.f, sdt = 0.f;
+    for (int rr = slot; rr < 32; rr += 4) {
+        const int r = blockIdx.x * 32 + rr;
+        if (r >= R) break;
+        float ds = 0.f, dt = 0.f;
+        if (d < D) {
+            const long k = (long)r * D + d;
+            const float gv = g[k];
+            float dx = gv;
+            if (m == 0.f) {
+                const float s = st[k], t = st[(long)R * D + k], xv = x[k];
+                const float glv = gl ? gl_scale * gl[r] : 0.f;
+                if (direction == 0) { const float e = expf(s); dx = gv * e; dt = gv; ds = gv * xv * e + glv; }
+                else { const float e = expf(-s); dx = gv * e; dt = -gv * e; ds = -gv * (xv - t) * e - glv; }
+                ds *= (1.f - s * s);
+            }
+            gx[k] = dx;
+        }
+        const long i = (long)r * kDp + d;
+        put_planes(dprep + i, ps, ds);
+        put_planes(dprep + 2 * ps + i, ps, dt);
+        sds += ds; sdt += dt;
+    }
+    red[0][slot][d] = sds; red[1][slot][d] = sdt;
+    __syncthreads();
+    if (slot == 0 && d < D && m == 0.f) {
+        atomicAdd(db2 + d, red[0][0][d] + red[0][1][d] + red[0][2][d] + red[0][3][d]);
+        atomicAdd(db2 + db2_stride + d, red[1][0][d] + red[1][1][d] + red[1][2][d] + red[1][3][d]);
+    }
 }
 
 __global__ void cond_bias_grad_kernel(const float* __restrict__ dcp, int B, long cp_ld, int H, float* __restrict__ dparams,
@@ -292,29 +285,34 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
 }
 
 // ---- coupling layers ------------------------------------------------------------------------------------
-static int layer_nets_fwd(const FlowLayout& L, const float* params, const Packed& P, const float* cp, int R, int B, int layer, Ws& ws,
-                          cudaStream_t stream) {
+struct LayerBufs {   // where one layer's activations live (workspace, or the saved-for-backward block)
+    bf16 *xm, *a0, *a1;
+    float* st;
+};
+
+static int layer_nets_fwd(const FlowLayout& L, const float* params, const Packed& P, const float* cp, int R, int B, int layer,
+                          const LayerBufs& bf, cudaStream_t stream) {
     const long cp_ld = (long)L.L * 4 * L.H;
     const long RH = (long)R * L.H, RD = (long)R * kDp;
     {   // G0: xm [R][64] x W0^T -> a0
-        PlaneTensor A = pt(ws.xm, kDp, R, kDp, RD, 1, 0);
+        PlaneTensor A = pt(bf.xm, kDp, R, kDp, RD, 1, 0);
         PlaneTensor Bt = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
         GemmShape g{R, L.H, kDp, 2, 1, 0, 1};
-        EpiHiddenPlanes e{ws.a0, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
+        EpiHiddenPlanes e{bf.a0, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
         MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G0")));
     }
     {   // G1: a0 x W1^T -> a1
-        PlaneTensor A = pt(ws.a0, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor A = pt(bf.a0, L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor Bt = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
         GemmShape g{R, L.H, L.H, 2, 1, 1, 1};
-        EpiHiddenPlanes e{ws.a1, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
+        EpiHiddenPlanes e{bf.a1, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
         MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G1")));
     }
     {   // G2: a1 x W2^T + b2 -> st
-        PlaneTensor A = pt(ws.a1, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor A = pt(bf.a1, L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor Bt = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
         GemmShape g{R, kDp, L.H, 2, 1, 1, 1};
-        EpiOutHead e{ws.st, L.D, (long)R * L.D, params + L.block(layer, 0) + L.ob2, (long)L.blk};
+        EpiOutHead e{bf.st, L.D, (long)R * L.D, params + L.block(layer, 0) + L.ob2, (long)L.blk};
         MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G2")));
     }
     return MHE_OK;
@@ -324,67 +322,66 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
              int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream) {
     Packed P(L, (bf16*)packed);
     Ws ws(workspace, L, R);
+    Saved S(saved, L, R);
     const size_t row_bytes = (size_t)R * L.D * sizeof(float);
     if (logdet) MHE_TRY(cuda_ok(cudaMemsetAsync(logdet, 0, (size_t)R * sizeof(float), stream), "memset logdet"));
     const int first = direction == 0 ? 0 : L.L - 1;
-    MHE_TRY(split_planes(in, L.D, 0, R, L.D, mask + (size_t)first * L.D, ws.xm, R, kDp, 2, 1, stream));
-    const float* x = in;
+    if (saved) MHE_TRY(cuda_ok(cudaMemcpyAsync(S.x(0), in, row_bytes, cudaMemcpyDeviceToDevice, stream), "save input"));
+    MHE_TRY(split_planes(in, L.D, 0, R, L.D, mask + (size_t)first * L.D, saved ? S.xm(0) : ws.xm, R, kDp, 2, 1, stream));
+    const float* x = saved ? S.x(0) : in;
     for (int step = 0; step < L.L; ++step) {
         const int layer = direction == 0 ? step : L.L - 1 - step;
-        if (saved) {
-            float* slot = saved + (size_t)step * R * L.D;
-            if (step == 0) MHE_TRY(cuda_ok(cudaMemcpyAsync(slot, in, row_bytes, cudaMemcpyDeviceToDevice, stream), "save input"));
-            x = slot;
-        }
-        MHE_TRY(layer_nets_fwd(L, params, P, cp, R, B, layer, ws, stream));
-        float* y;
-        if (saved) y = saved + (size_t)(step + 1) * R * L.D;
-        else y = (step == L.L - 1) ? out : ((x == ws.gx) ? ws.dpre : ws.gx);
         const bool last = step == L.L - 1;
+        LayerBufs bf = saved ? LayerBufs{S.xm(step), S.a0(step), S.a1(step), S.st(step)} : LayerBufs{ws.xm, ws.a0, ws.a1, ws.st};
+        MHE_TRY(layer_nets_fwd(L, params, P, cp, R, B, layer, bf, stream));
+        float* y;
+        if (saved) y = S.x(step + 1);
+        else y = last ? out : ((x == ws.gx) ? ws.dpre : ws.gx);
+        bf16* ym = last ? nullptr : (saved ? S.xm(step + 1) : ws.xm);
         const int next_layer = direction == 0 ? layer + 1 : layer - 1;
-        coupling_fwd_kernel<<<cdiv(R, 8), 256, 0, stream>>>(x, ws.st, mask + (size_t)layer * L.D, last ? nullptr : mask + (size_t)next_layer * L.D, R,
-                                                          L.D, direction, y, logdet, last ? nullptr : ws.xm);
+        coupling_fwd_kernel<<<cdiv(R, 8), 256, 0, stream>>>(x, bf.st, mask + (size_t)layer * L.D, last ? nullptr : mask + (size_t)next_layer * L.D, R,
+                                                          L.D, direction, y, logdet, ym);
         MHE_TRY(check_launch("tc coupling fwd"));
         x = y;
     }
-    if (saved) MHE_TRY(cuda_ok(cudaMemcpyAsync(out, saved + (size_t)L.L * R * L.D, row_bytes, cudaMemcpyDeviceToDevice, stream), "copy out"));
+    if (saved) MHE_TRY(cuda_ok(cudaMemcpyAsync(out, S.x(L.L), row_bytes, cudaMemcpyDeviceToDevice, stream), "copy out"));
     return MHE_OK;
 }
 
+// The backward reads the hidden activations the forward saved (no recomputation on this path).
 int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* saved, int R, int B,
              int direction, const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp,
              void* workspace, cudaStream_t stream) {
     Packed P(L, (bf16*)packed);
     Ws ws(workspace, L, R);
+    Saved S(const_cast<float*>(saved), L, R);
     const long cp_ld = (long)L.L * 4 * L.H;
     const long RH = (long)R * L.H, RD = (long)R * kDp;
     const float* g = dout;
     const int ks = R >= 8192 ? 4 : 1;   // wgrad contracts over the rows: split K once it is long
     for (int step = L.L - 1; step >= 0; --step) {
         const int layer = direction == 0 ? step : L.L - 1 - step;
-        const float* x = saved + (size_t)step * R * L.D;
         const float* mrow = mask + (size_t)layer * L.D;
         float* dblk = dparams + L.block(layer, 0);
-        MHE_TRY(split_planes(x, L.D, 0, R, L.D, mrow, ws.xm, R, kDp, 2, 1, stream));
-        MHE_TRY(layer_nets_fwd(L, params, P, cp, R, B, layer, ws, stream));      // recompute a0, a1, st
         float* gx = (step == 0) ? din : ws.gx;
-        coupling_bwd_kernel<<<cdiv((int)RD, 256), 256, 0, stream>>>(x, ws.st, mrow, g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dpre, ws.dprep, gx);
+        coupling_bwd_kernel<<<cdiv(R, 32), 256, 0, stream>>>(S.x(step), S.st(step), mrow, g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dprep, gx,
+                                                           dblk + L.ob2, (long)L.blk);
         MHE_TRY(check_launch("tc coupling bwd"));
         PlaneTensor dpreK = pt(ws.dprep, kDp, R, kDp, RD, 2, 2 * RD);
         PlaneTensor w0 = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
         PlaneTensor w1 = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
         PlaneTensor w2 = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
-        PlaneTensor a0 = pt(ws.a0, L.H, R, L.H, RH, 2, 2 * RH), a1 = pt(ws.a1, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor a0 = pt(S.a0(step), L.H, R, L.H, RH, 2, 2 * RH), a1 = pt(S.a1(step), L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor dh0 = pt(ws.dh0, L.H, R, L.H, RH, 2, 2 * RH), dh1 = pt(ws.dh1, L.H, R, L.H, RH, 2, 2 * RH);
-        PlaneTensor xm = pt(ws.xm, kDp, R, kDp, RD, 1, 0);
-        {   // dgrad G2: dh1 = (dpre W2) * lrelu'(a1);  W2 planes [64][H] read MN-major (cols = h)
+        PlaneTensor xm = pt(S.xm(step), kDp, R, kDp, RD, 1, 0);
+        {   // dgrad G2: dh1 = (dpre W2) * lrelu'(a1);  W2 planes [64][H] read MN-major (cols = h);  dcp1 += sum_s dh1
             GemmShape s{R, L.H, kDp, 2, 1, 1, 1};
-            EpiActGradPlanes e{ws.dh1, ws.a1, L.H, RH, 2 * RH};
+            EpiActGradPlanes e{ws.dh1, S.a1(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
             MHE_TRY((gemm<false, true>(dpreK, w2, s, e, stream, "tc dgrad G2")));
         }
-        {   // dgrad G1: dh0 = (dh1 W1) * lrelu'(a0)
+        {   // dgrad G1: dh0 = (dh1 W1) * lrelu'(a0);  dcp0 += sum_s dh0
             GemmShape s{R, L.H, L.H, 2, 1, 1, 1};
-            EpiActGradPlanes e{ws.dh0, ws.a0, L.H, RH, 2 * RH};
+            EpiActGradPlanes e{ws.dh0, S.a0(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
             MHE_TRY((gemm<false, true>(dh1, w1, s, e, stream, "tc dgrad G1")));
         }
         {   // dgrad G0: gx += mask * (dh0 W0), both nets;  W0 planes [H][64] read MN-major (cols = d)
@@ -406,18 +403,6 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
             GemmShape s{L.H, kDp, R, 2, ks, 1, 1};
             EpiWgrad e{dblk + L.oW2, L.H, (long)L.blk, L.D, 1, ks > 1};
             MHE_TRY((gemm<true, true>(a1, dpreK, s, e, stream, "tc wgrad W2")));
-        }
-        {
-            dim3 grid(cdiv(L.D, 64), min(64, cdiv(R, 64)), 2);
-            colsum_kernel<<<grid, 64, 0, stream>>>(ws.dpre, R, L.D, (long)R * L.D, dblk + L.ob2, (long)L.blk);
-            MHE_TRY(check_launch("tc db2"));
-        }
-        {
-            dim3 grid(cdiv(L.H, 128), B, 2);
-            hyp_sum_planes_kernel<<<grid, 128, 0, stream>>>(ws.dh0, R, B, L.H, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H);
-            MHE_TRY(check_launch("tc dcp0"));
-            hyp_sum_planes_kernel<<<grid, 128, 0, stream>>>(ws.dh1, R, B, L.H, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H);
-            MHE_TRY(check_launch("tc dcp1"));
         }
         g = gx;
     }

@@ -46,6 +46,32 @@ struct Ws {
     }
 };
 
+// saved-for-backward block of the tensor-core path: layer inputs, head outputs and the hidden activations
+//   x  fp32 [(L+1)][R][D] | st fp32 [L][2][R][D] | xm bf16 [L][2][R][64] | a0, a1 bf16 [L][2 nets][2 planes][R][H]
+struct Saved {
+    float *x_, *st_;
+    __nv_bfloat16 *xm_, *a0_, *a1_;
+    size_t RD, RDp, RH;
+    static size_t bytes(const FlowLayout& L, int R) {
+        const size_t RD = (size_t)R * L.D, RDp = (size_t)R * kDp, RH = (size_t)R * L.H;
+        return ((size_t)(L.L + 1) * RD + (size_t)L.L * 2 * RD) * 4 + ((size_t)L.L * 2 * RDp + 2 * (size_t)L.L * 4 * RH) * 2 + 8 * 1024;
+    }
+    Saved(float* base_, const FlowLayout& L, int R) : RD((size_t)R * L.D), RDp((size_t)R * kDp), RH((size_t)R * L.H) {
+        uint8_t* base = (uint8_t*)base_;
+        auto take = [&](size_t n) { uint8_t* p = base; base += (n + 1023) / 1024 * 1024; return p; };
+        x_ = (float*)take((size_t)(L.L + 1) * RD * 4);
+        st_ = (float*)take((size_t)L.L * 2 * RD * 4);
+        xm_ = (__nv_bfloat16*)take((size_t)L.L * 2 * RDp * 2);
+        a0_ = (__nv_bfloat16*)take((size_t)L.L * 4 * RH * 2);
+        a1_ = (__nv_bfloat16*)take((size_t)L.L * 4 * RH * 2);
+    }
+    float* x(int step) const { return x_ + (size_t)step * RD; }
+    float* st(int step) const { return st_ + (size_t)step * 2 * RD; }
+    __nv_bfloat16* xm(int step) const { return xm_ + (size_t)step * 2 * RDp; }
+    __nv_bfloat16* a0(int step) const { return a0_ + (size_t)step * 4 * RH; }
+    __nv_bfloat16* a1(int step) const { return a1_ + (size_t)step * 4 * RH; }
+};
+
 inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
     return ((size_t)2 * B * L.C + 512 + (size_t)2 * B * L.L * 4 * L.H) * 2 + 4096;
 }

@@ -45,23 +45,118 @@ struct ManoWs {
     }
 };
 
+// ---- warp-per-row pose state ---------------------------------------------------------------------------
+// One warp owns one row; the per-row state lives in shared memory and the lanes split the work:
+// PCA outputs / joint regression over lanes, one Rodrigues per lane, the kinematic chain level by level with
+// one lane per finger.  The primitives are the host-checked ones of mano_math.cuh.
+struct WarpPose {
+    float pose[kPose];
+    float R[kJ][9], J[kJ][3], Gr[kJ][9], Gt[kJ][3], A[kJ][12];
+    float dGr[kJ][9], dGt[kJ][3], dJ[kJ][3], dR[kJ][9], dpose[kPose];
+    float dA[kJ][12], dpm[kWsPm], dGt_out[kJ * 3], T[12], red[8];
+};
+constexpr int kPoseWarps = 4;
+
+__device__ __forceinline__ void pose_fwd_warp(const mhe_mano_consts& c, const float* __restrict__ theta, const float* __restrict__ beta,
+                                              WarpPose& W, int lane) {
+    for (int j = lane; j < 45; j += 32) {
+        float acc = __ldg(c.hands_mean + j);
+        for (int k = 0; k < 45; ++k) acc = fmaf(theta[3 + k], __ldg(c.comps + k * 45 + j), acc);
+        W.pose[3 + j] = acc;
+    }
+    if (lane < 3) W.pose[lane] = theta[lane];
+    for (int i = lane; i < kJ * 3; i += 32) {
+        float acc = __ldg(c.jt + i);
+        for (int b = 0; b < kShape; ++b) acc = fmaf(__ldg(c.js + i * kShape + b), beta[b], acc);
+        W.J[i / 3][i % 3] = acc;
+    }
+    __syncwarp();
+    if (lane < kJ) rodrigues_fwd(&W.pose[3 * lane], W.R[lane]);
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < 9; ++i) W.Gr[0][i] = W.R[0][i];
+        for (int cc = 0; cc < 3; ++cc) W.Gt[0][cc] = W.J[0][cc];
+    }
+    __syncwarp();
+    for (int level = 0; level < 3; ++level) {
+        if (lane < 5) {
+            const int k = 1 + 3 * lane + level, p = parent_of(k);
+            mat3_mul(W.Gr[p], W.R[k], W.Gr[k]);
+            const float d[3] = {W.J[k][0] - W.J[p][0], W.J[k][1] - W.J[p][1], W.J[k][2] - W.J[p][2]};
+            float o[3];
+            mat3_vec(W.Gr[p], d, o);
+            for (int cc = 0; cc < 3; ++cc) W.Gt[k][cc] = o[cc] + W.Gt[p][cc];
+        }
+        __syncwarp();
+    }
+    if (lane < kJ) {
+        for (int i = 0; i < 9; ++i) W.A[lane][i] = W.Gr[lane][i];
+        float o[3];
+        mat3_vec(W.Gr[lane], W.J[lane], o);
+        for (int cc = 0; cc < 3; ++cc) W.A[lane][9 + cc] = W.Gt[lane][cc] - o[cc];
+    }
+    __syncwarp();
+}
+
+// blend shapes + LBS of tip vertex v by a whole warp: vp (3) and T (12, in W.T) are left in every lane / smem
+__device__ __forceinline__ void tip_skin_warp(const mhe_mano_consts& c, int v, const float* __restrict__ beta, WarpPose& W, int lane, float* vp) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = lane; k < kPoseMap; k += 32) {
+        const float p = W.R[1 + k / 9][k % 9] - ((k % 9) % 4 == 0 ? 1.f : 0.f);
+        a0 = fmaf(__ldg(c.posedirs_t + (long)k * kVC + v * 3 + 0), p, a0);
+        a1 = fmaf(__ldg(c.posedirs_t + (long)k * kVC + v * 3 + 1), p, a1);
+        a2 = fmaf(__ldg(c.posedirs_t + (long)k * kVC + v * 3 + 2), p, a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    float sh[3];
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+        float acc = __ldg(c.v_template + v * 3 + cc);
+        for (int b = 0; b < kShape; ++b) acc = fmaf(__ldg(c.shapedirs + (v * 3 + cc) * kShape + b), beta[b], acc);
+        sh[cc] = acc;
+    }
+    vp[0] = sh[0] + a0; vp[1] = sh[1] + a1; vp[2] = sh[2] + a2;
+    if (lane < 12) {
+        float t = 0.f;
+        for (int k = 0; k < kJ; ++k) t = fmaf(__ldg(c.weights + v * kJ + k), W.A[k][lane], t);
+        W.T[lane] = t;
+    }
+    __syncwarp();
+}
+
 // ---- forward ------------------------------------------------------------------------------------
-__global__ void mano_pose_fwd_kernel(mhe_mano_consts c, const float* __restrict__ theta, int ld_theta,
-                                     const float* __restrict__ beta, int ld_beta, int R, int order,
+// warp per row: pose -> pm / A / centre for the skinning kernel (when requested) and the 16 chain joints;
+// with `tips` also the five tip vertices, so the joints-only path is this single kernel.
+__global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_fwd_kernel(mhe_mano_consts c, const float* __restrict__ theta, int ld_theta,
+                                     const float* __restrict__ beta, int ld_beta, int R, int order, int tips,
                                      float* __restrict__ pm, float* __restrict__ A, float* __restrict__ cen,
                                      float* __restrict__ jtr) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ WarpPose s_w[kPoseWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kPoseWarps + warp;
     if (r >= R) return;
-    PoseState st;
-    pose_fwd(c.comps, c.hands_mean, c.jt, c.js, theta + (long)r * ld_theta, beta + (long)r * ld_beta, st);
-    for (int k = 1; k < kJ; ++k)
-        for (int i = 0; i < 9; ++i) pm[(long)r * kWsPm + (k - 1) * 9 + i] = st.R[k][i] - ((i % 4 == 0) ? 1.f : 0.f);
-    for (int k = 0; k < kJ; ++k) skin_transform(st, k, A + (long)r * kWsA + k * 12);
-    for (int cc = 0; cc < 3; ++cc) cen[(long)r * kWsCen + cc] = st.Gt[kCenterJoint][cc];
-    for (int i = 0; i < kNJ; ++i) {
-        const int src = c_jtr_src[order][i];
-        if (src < kJ)
-            for (int cc = 0; cc < 3; ++cc) jtr[((long)r * kNJ + i) * 3 + cc] = (st.Gt[src][cc] - st.Gt[kCenterJoint][cc]) * kMM;
+    WarpPose& W = s_w[warp];
+    const float* be = beta + (long)r * ld_beta;
+    pose_fwd_warp(c, theta + (long)r * ld_theta, be, W, lane);
+    if (pm) for (int k = lane; k < kPoseMap; k += 32) pm[(long)r * kWsPm + k] = W.R[1 + k / 9][k % 9] - ((k % 9) % 4 == 0 ? 1.f : 0.f);
+    if (A) for (int i = lane; i < kWsA; i += 32) A[(long)r * kWsA + i] = W.A[i / 12][i % 12];
+    if (cen && lane < 3) cen[(long)r * kWsCen + lane] = W.Gt[kCenterJoint][lane];
+    if (jtr) {
+        for (int i = lane; i < kNJ * 3; i += 32) {
+            const int src = c_jtr_src[order][i / 3];
+            if (src < kJ) jtr[(long)r * kNJ * 3 + i] = (W.Gt[src][i % 3] - W.Gt[kCenterJoint][i % 3]) * kMM;
+        }
+        if (tips) {
+            for (int t = 0; t < 5; ++t) {
+                float vp[3];
+                tip_skin_warp(c, c_tip_vert[t], be, W, lane, vp);
+                if (lane < 3) {
+                    const float o = (W.T[lane * 3 + 0] * vp[0] + W.T[lane * 3 + 1] * vp[1] + W.T[lane * 3 + 2] * vp[2] + W.T[9 + lane] - W.Gt[kCenterJoint][lane]) * kMM;
+                    for (int i = 0; i < kNJ; ++i) if (c_jtr_src[order][i] == kJ + t) jtr[((long)r * kNJ + i) * 3 + lane] = o;
+                }
+                __syncwarp();
+            }
+        }
     }
 }
 
@@ -167,22 +262,6 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
     }
 }
 
-// joints-only path: skin just the five tip vertices. thread per (row, tip).
-__global__ void mano_tips_fwd_kernel(mhe_mano_consts c, const float* __restrict__ beta, int ld_beta, int R, int order,
-                                     const float* __restrict__ pm_g, const float* __restrict__ A_g, const float* __restrict__ cen_g,
-                                     float* __restrict__ jtr) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R * 5) return;
-    const int r = idx / 5, t = idx % 5;
-    const int v = c_tip_vert[t];
-    float vp[3], T[12];
-    skin_vertex(c, v, pm_g + (long)r * kWsPm, A_g + (long)r * kWsA, beta + (long)r * ld_beta, vp, T);
-    for (int i = 0; i < kNJ; ++i)
-        if (c_jtr_src[order][i] == kJ + t)
-            for (int cc = 0; cc < 3; ++cc)
-                jtr[((long)r * kNJ + i) * 3 + cc] = (T[cc * 3 + 0] * vp[0] + T[cc * 3 + 1] * vp[1] + T[cc * 3 + 2] * vp[2] + T[9 + cc] - cen_g[(long)r * kWsCen + cc]) * kMM;
-}
-
 // wrapper's regressed joints: joints2[r][i] = sum_v jreg[k][v] verts[r][v] or a tip vertex. block per row, 8 warps.
 __global__ void __launch_bounds__(256) mano_joints2_fwd_kernel(mhe_mano_consts c, const float* __restrict__ verts, int R, int order, float* __restrict__ joints2) {
     const int r = blockIdx.x;
@@ -275,74 +354,133 @@ __global__ void __launch_bounds__(192) mano_skin_bwd_kernel(mhe_mano_consts c, i
     }
 }
 
-// joints-only backward through the five tip vertices. thread per row (5 tips sequentially; tiny).
-__global__ void mano_tips_bwd_kernel(mhe_mano_consts c, const float* __restrict__ beta, int ld_beta, int R, int order,
-                                     const float* __restrict__ pm_g, const float* __restrict__ A_g, const float* __restrict__ djtr,
-                                     float* __restrict__ dA, float* __restrict__ dpm, float* __restrict__ dbv, float* __restrict__ dcen) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    float* dAr = dA + (long)r * 192;
-    float* dpmr = dpm + (long)r * 136;
-    float* dbr = dbv + (long)r * 12;
-    for (int i = 0; i < 192; ++i) dAr[i] = 0.f;
-    for (int i = 0; i < 136; ++i) dpmr[i] = 0.f;
-    for (int i = 0; i < 12; ++i) dbr[i] = 0.f;
-    float dc[3] = {0.f, 0.f, 0.f};
-    for (int t = 0; t < 5; ++t) {
-        const int v = c_tip_vert[t];
-        float dv[3] = {0.f, 0.f, 0.f};
-        for (int i = 0; i < kNJ; ++i)
-            if (c_jtr_src[order][i] == kJ + t) for (int cc = 0; cc < 3; ++cc) dv[cc] = djtr[((long)r * kNJ + i) * 3 + cc] * kMM;
-        float vp[3], T[12];
-        skin_vertex(c, v, pm_g + (long)r * kWsPm, A_g + (long)r * kWsA, beta + (long)r * ld_beta, vp, T);
-        for (int k = 0; k < kJ; ++k) {
-            const float w = __ldg(c.weights + v * kJ + k);
-            if (w == 0.f) continue;
-            for (int i = 0; i < 3; ++i) {
-                for (int j = 0; j < 3; ++j) dAr[k * 12 + i * 3 + j] = fmaf(w * dv[i], vp[j], dAr[k * 12 + i * 3 + j]);
-                dAr[k * 12 + 9 + i] = fmaf(w, dv[i], dAr[k * 12 + 9 + i]);
+// one step of the chain backward for joint k with parent p (see mano_math.cuh pose_bwd)
+__device__ __forceinline__ void chain_bwd_step(WarpPose& W, int k, int p) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float a = 0.f, b = 0.f;
+            for (int l = 0; l < 3; ++l) {
+                a = fmaf(W.Gr[p][l * 3 + i], W.dGr[k][l * 3 + j], a);
+                b = fmaf(W.dGr[k][i * 3 + l], W.R[k][j * 3 + l], b);
             }
+            W.dR[k][i * 3 + j] += a;
+            W.dGr[p][i * 3 + j] += b;
         }
-        float dvp[3];
-        mat3t_vec(T, dv, dvp);
-        for (int k = 0; k < kPoseMap; ++k)
-            dpmr[k] += __ldg(c.posedirs_t + (long)k * kVC + v * 3) * dvp[0] + __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 1) * dvp[1] + __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 2) * dvp[2];
-        for (int b = 0; b < kShape; ++b)
-            dbr[b] += __ldg(c.shapedirs + (v * 3 + 0) * kShape + b) * dvp[0] + __ldg(c.shapedirs + (v * 3 + 1) * kShape + b) * dvp[1] + __ldg(c.shapedirs + (v * 3 + 2) * kShape + b) * dvp[2];
-        for (int cc = 0; cc < 3; ++cc) dc[cc] -= dv[cc];
-    }
-    for (int cc = 0; cc < 3; ++cc) dcen[(long)r * 4 + cc] = dc[cc];
+    const float d[3] = {W.J[k][0] - W.J[p][0], W.J[k][1] - W.J[p][1], W.J[k][2] - W.J[p][2]};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) W.dGr[p][i * 3 + j] = fmaf(W.dGt[k][i], d[j], W.dGr[p][i * 3 + j]);
+    float o[3];
+    mat3t_vec(W.Gr[p], W.dGt[k], o);
+    for (int cc = 0; cc < 3; ++cc) { W.dJ[k][cc] += o[cc]; W.dJ[p][cc] -= o[cc]; W.dGt[p][cc] += W.dGt[k][cc]; }
 }
 
-// chain backward, thread per row. dA/dpm/dbv/dcen may be NULL (no vertex gradients at all).
-__global__ void mano_pose_bwd_kernel(mhe_mano_consts c, const float* __restrict__ theta, int ld_theta, const float* __restrict__ beta, int ld_beta,
-                                     int R, int order, const float* __restrict__ djtr, const float* __restrict__ dA, const float* __restrict__ dpm,
-                                     const float* __restrict__ dbv, const float* __restrict__ dcen,
+// Backward of the pose / chain, warp per row.  Vertex gradients arrive either through the workspace
+// (dA, dpm, dbv, dcen written by the mesh kernels) or, with tips_in_kernel, are formed here from djtr for the
+// five tip vertices (the joints-only training path: one kernel for the whole MANO backward).
+__global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano_consts c, const float* __restrict__ theta, int ld_theta,
+                                     const float* __restrict__ beta, int ld_beta, int R, int order, int tips_in_kernel,
+                                     const float* __restrict__ djtr, const float* __restrict__ dA_g, const float* __restrict__ dpm_g,
+                                     const float* __restrict__ dbv_g, const float* __restrict__ dcen_g,
                                      float* __restrict__ dtheta, int ld_dtheta, float* __restrict__ dbeta, int ld_dbeta, int accumulate) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ WarpPose s_w[kPoseWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kPoseWarps + warp;
     if (r >= R) return;
-    PoseState st;
-    pose_fwd(c.comps, c.hands_mean, c.jt, c.js, theta + (long)r * ld_theta, beta + (long)r * ld_beta, st);
-    float dGt[kJ * 3];
-    for (int i = 0; i < kJ * 3; ++i) dGt[i] = 0.f;
-    float dc[3] = {0.f, 0.f, 0.f};
-    if (dcen) for (int cc = 0; cc < 3; ++cc) dc[cc] = dcen[(long)r * 4 + cc];
-    if (djtr) {
+    WarpPose& W = s_w[warp];
+    const float* be = beta + (long)r * ld_beta;
+    pose_fwd_warp(c, theta + (long)r * ld_theta, be, W, lane);
+
+    // vertex-side gradients -> W.dA, W.dpm, dbeta seed, centre gradient
+    float db = 0.f;                       // lane b < 10 owns dbeta[b]
+    float dc = 0.f;                       // lane cc < 3 owns the centre gradient component
+    for (int i = lane; i < kWsA; i += 32) W.dA[i / 12][i % 12] = (dA_g && !tips_in_kernel) ? dA_g[(long)r * 192 + i] : 0.f;
+    for (int k = lane; k < kWsPm; k += 32) W.dpm[k] = (dpm_g && !tips_in_kernel) ? dpm_g[(long)r * 136 + k] : 0.f;
+    if (!tips_in_kernel) {
+        if (dbv_g && lane < kShape) db = dbv_g[(long)r * 12 + lane];
+        if (dcen_g && lane < 3) dc = dcen_g[(long)r * 4 + lane];
+    }
+    __syncwarp();
+    if (tips_in_kernel && djtr) {
+        for (int t = 0; t < 5; ++t) {
+            const int v = c_tip_vert[t];
+            int slot = 0;
+            for (int i = 0; i < kNJ; ++i) if (c_jtr_src[order][i] == kJ + t) slot = i;
+            const float dv0 = djtr[((long)r * kNJ + slot) * 3 + 0] * kMM, dv1 = djtr[((long)r * kNJ + slot) * 3 + 1] * kMM,
+                        dv2 = djtr[((long)r * kNJ + slot) * 3 + 2] * kMM;
+            const float dv[3] = {dv0, dv1, dv2};
+            float vp[3];
+            tip_skin_warp(c, v, be, W, lane, vp);
+            for (int e = lane; e < kWsA; e += 32) {
+                const int k = e / 12, ee = e % 12;
+                const float w = __ldg(c.weights + v * kJ + k);
+                W.dA[k][ee] += w * (ee < 9 ? dv[ee / 3] * vp[ee % 3] : dv[ee - 9]);
+            }
+            float dvp[3];
+            mat3t_vec(W.T, dv, dvp);
+            for (int k = lane; k < kPoseMap; k += 32)
+                W.dpm[k] += __ldg(c.posedirs_t + (long)k * kVC + v * 3) * dvp[0] + __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 1) * dvp[1] +
+                            __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 2) * dvp[2];
+            if (lane < kShape)
+                db += __ldg(c.shapedirs + (v * 3 + 0) * kShape + lane) * dvp[0] + __ldg(c.shapedirs + (v * 3 + 1) * kShape + lane) * dvp[1] +
+                      __ldg(c.shapedirs + (v * 3 + 2) * kShape + lane) * dvp[2];
+            if (lane < 3) dc -= dv[lane];
+            __syncwarp();
+        }
+    }
+    // joint-position gradients: chain joints of djtr, and the centring (every output is relative to joint 4)
+    for (int i = lane; i < kJ * 3; i += 32) W.dGt_out[i] = 0.f;
+    __syncwarp();
+    if (djtr && lane < 3) {
         for (int i = 0; i < kNJ; ++i) {
             const int src = c_jtr_src[order][i];
-            for (int cc = 0; cc < 3; ++cc) {
-                const float g = djtr[((long)r * kNJ + i) * 3 + cc] * kMM;
-                if (src < kJ) { dGt[src * 3 + cc] += g; dc[cc] -= g; }  // tips' centring share is already in dcen
+            if (src < kJ) {
+                const float g = djtr[((long)r * kNJ + i) * 3 + lane] * kMM;
+                W.dGt_out[src * 3 + lane] += g;
+                dc -= g;                 // the tips' share of the centring is already in dc
             }
         }
     }
-    for (int cc = 0; cc < 3; ++cc) dGt[kCenterJoint * 3 + cc] += dc[cc];
-    float dth[kPose], db[kShape];
-    for (int i = 0; i < kPose; ++i) dth[i] = 0.f;
-    for (int i = 0; i < kShape; ++i) db[i] = dbv ? dbv[(long)r * 12 + i] : 0.f;
-    pose_bwd(c.comps, c.js, st, dGt, dA ? dA + (long)r * 192 : nullptr, dpm ? dpm + (long)r * 136 : nullptr, dth, db);
-    for (int i = 0; i < kPose; ++i) { float* d = dtheta + (long)r * ld_dtheta + i; *d = accumulate ? *d + dth[i] : dth[i]; }
-    for (int i = 0; i < kShape; ++i) { float* d = dbeta + (long)r * ld_dbeta + i; *d = accumulate ? *d + db[i] : db[i]; }
+    __syncwarp();
+    if (lane < 3) W.dGt_out[kCenterJoint * 3 + lane] += dc;
+    __syncwarp();
+    // chain backward
+    if (lane < kJ) {
+        const int k = lane;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) W.dGr[k][i * 3 + j] = W.dA[k][i * 3 + j] - W.dA[k][9 + i] * W.J[k][j];
+        float o[3];
+        mat3t_vec(W.Gr[k], &W.dA[k][9], o);
+        for (int cc = 0; cc < 3; ++cc) { W.dGt[k][cc] = W.dGt_out[k * 3 + cc] + W.dA[k][9 + cc]; W.dJ[k][cc] = -o[cc]; }
+        for (int i = 0; i < 9; ++i) W.dR[k][i] = (k >= 1) ? W.dpm[(k - 1) * 9 + i] : 0.f;
+    }
+    __syncwarp();
+    for (int level = 2; level >= 1; --level) {      // children of distinct parents: one lane per finger
+        if (lane < 5) { const int k = 1 + 3 * lane + level; chain_bwd_step(W, k, k - 1); }
+        __syncwarp();
+    }
+    if (lane == 0) {                                 // the five level-0 joints share parent 0: serial
+        for (int f = 0; f < 5; ++f) chain_bwd_step(W, 1 + 3 * f, 0);
+        for (int i = 0; i < 9; ++i) W.dR[0][i] += W.dGr[0][i];
+        for (int cc = 0; cc < 3; ++cc) W.dJ[0][cc] += W.dGt[0][cc];
+    }
+    __syncwarp();
+    if (lane < kShape) {
+        for (int i = 0; i < kJ * 3; ++i) db = fmaf(__ldg(c.js + i * kShape + lane), W.dJ[i / 3][i % 3], db);
+        float* d = dbeta + (long)r * ld_dbeta + lane;
+        *d = accumulate ? *d + db : db;
+    }
+    if (lane < kJ) rodrigues_bwd(&W.pose[3 * lane], W.dR[lane], &W.dpose[3 * lane]);
+    __syncwarp();
+    for (int i = lane; i < kPose; i += 32) {
+        float g;
+        if (i < 3) g = W.dpose[i];
+        else {
+            g = 0.f;
+            for (int j = 0; j < 45; ++j) g = fmaf(__ldg(c.comps + (i - 3) * 45 + j), W.dpose[3 + j], g);
+        }
+        float* d = dtheta + (long)r * ld_dtheta + i;
+        *d = accumulate ? *d + g : g;
+    }
 }
 
 }  // namespace mhe
@@ -364,7 +502,8 @@ int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
     if (R == 0) return MHE_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     ManoWs ws((float*)workspace, R, false);
-    mano_pose_fwd_kernel<<<cdiv(R, 64), 64, 0, stream>>>(*c, theta, ld_theta, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, jtr);
+    mano_pose_fwd_kernel<<<cdiv(R, kPoseWarps), kPoseWarps * 32, 0, stream>>>(*c, theta, ld_theta, beta, ld_beta, R, joint_order, verts ? 0 : 1,
+                                                                                 verts ? ws.pm : nullptr, verts ? ws.A : nullptr, verts ? ws.cen : nullptr, jtr);
     MHE_TRY(check_launch("mano pose fwd"));
     if (verts) {
         if (R >= 8 * 148) {
@@ -379,9 +518,6 @@ int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
             mano_joints2_fwd_kernel<<<R, 256, 0, stream>>>(*c, verts, R, joint_order, joints2);
             MHE_TRY(check_launch("mano joints2 fwd"));
         }
-    } else {
-        mano_tips_fwd_kernel<<<cdiv(R * 5, 128), 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, jtr);
-        MHE_TRY(check_launch("mano tips fwd"));
     }
     return MHE_OK;
 }
@@ -398,13 +534,11 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
     if (R == 0) return MHE_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     ManoWs ws((float*)workspace, R, mesh);
-    // recompute the forward state the skinning gradient needs (jtr output of the pose kernel is not needed: pass scratch)
-    const bool need_skin = mesh || djtr;
-    if (need_skin) {
-        mano_pose_fwd_kernel<<<cdiv(R, 64), 64, 0, stream>>>(*c, theta, ld_theta, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, ws.dpm /*scratch >= 63 floats/row*/);
-        MHE_TRY(check_launch("mano pose recompute"));
-    }
     if (mesh) {
+        // recompute the forward state the mesh gradient needs
+        mano_pose_fwd_kernel<<<cdiv(R, kPoseWarps), kPoseWarps * 32, 0, stream>>>(*c, theta, ld_theta, beta, ld_beta, R, joint_order, 0, ws.pm, ws.A,
+                                                                                     ws.cen, nullptr);
+        MHE_TRY(check_launch("mano pose recompute"));
         dim3 grid(cdiv(kV, 128), cdiv(R, 2));
         mano_skin_fwd_kernel<2><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, nullptr, nullptr, ws.vp);
         MHE_TRY(check_launch("mano vposed recompute"));
@@ -420,16 +554,14 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
         {   // dbv [R][10] = dvp [R][2334] shapedirs [2334][10]
             GemmArgs g; g.A = ws.dvp; g.lda = 2336; g.B = c->shapedirs; g.ldb = kShape; g.M = R; g.N = kShape; g.K = kVC;
             EpiStore e{ws.dbv, 12, 0};
-            MHE_TRY((launch_sgemm<Major::K, Major::MN>(g, e, stream, "mano dbv")));
+            MHE_TRY((launch_sgemm<Major::K, Major::K>(g, e, stream, "mano dbv")));
         }
-    } else if (djtr) {
-        mano_tips_bwd_kernel<<<cdiv(R, 64), 64, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, djtr, ws.dA, ws.dpm, ws.dbv, ws.dcen);
-        MHE_TRY(check_launch("mano tips bwd"));
     }
-    mano_pose_bwd_kernel<<<cdiv(R, 64), 64, 0, stream>>>(*c, theta, ld_theta, beta, ld_beta, R, joint_order, djtr,
-                                                          need_skin ? ws.dA : nullptr, need_skin ? ws.dpm : nullptr,
-                                                          need_skin ? ws.dbv : nullptr, need_skin ? ws.dcen : nullptr,
-                                                          dtheta, ld_dtheta, dbeta, ld_dbeta, accumulate);
+    // mesh path: vertex gradients come through the workspace (tips already folded into dvt);
+    // joints-only path: the tips are handled inside the kernel
+    mano_pose_bwd_kernel<<<cdiv(R, kPoseWarps), kPoseWarps * 32, 0, stream>>>(*c, theta, ld_theta, beta, ld_beta, R, joint_order, mesh ? 0 : 1, djtr,
+                                                                                 mesh ? ws.dA : nullptr, mesh ? ws.dpm : nullptr, mesh ? ws.dbv : nullptr,
+                                                                                 mesh ? ws.dcen : nullptr, dtheta, ld_dtheta, dbeta, ld_dbeta, accumulate);
     return check_launch("mano pose bwd");
 }
 

@@ -91,6 +91,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, with both descriptors given as (low word, shared high word)
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
@@ -190,20 +200,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = instr_desc(BN, A_MN, B_MN);
+            // Descriptors differ between MMAs only in the 14-bit start address: build the constant part once and
+            // add 16-byte-unit offsets, so the single issuing thread spends a few instructions per MMA.
+            constexpr uint32_t kHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));          // SBO | version | SWIZZLE_128B
+            constexpr uint32_t kLoA = A_MN ? ((8192u >> 4) << 16) : ((16u >> 4) << 16);            // LBO field
+            constexpr uint32_t kLoB = B_MN ? ((8192u >> 4) << 16) : ((16u >> 4) << 16);
+            constexpr uint32_t kStepA = A_MN ? (2048u >> 4) : (32u >> 4);                          // per UMMA_K step
+            constexpr uint32_t kStepB = B_MN ? (2048u >> 4) : (32u >> 4);
+            uint32_t accumulate = 0;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % NS;
                 const uint32_t ph = (i / NS) & 1;
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 tcgen05_fence_after();
+                const uint32_t a_lo0 = kLoA | (stage_a(s, 0) >> 4), b_lo0 = kLoB | (stage_b(s, 0) >> 4);
 #pragma unroll
                 for (int pr = 0; pr < NPAIR; ++pr) {
-                    const int pa = (pr == 2) ? 1 : 0;     // pairs: (hi,hi) (hi,lo) (lo,hi)
-                    const int pb = (pr == 1) ? 1 : 0;
+                    const uint32_t a_lo = a_lo0 + ((pr == 2) ? (uint32_t)(Plan::kABytes >> 4) : 0u);   // pairs: (hi,hi) (hi,lo) (lo,hi)
+                    const uint32_t b_lo = b_lo0 + ((pr == 1) ? (uint32_t)(Plan::kBBytes >> 4) : 0u);
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        const uint64_t da = A_MN ? smem_desc(stage_a(s, pa) + ks * 2048, 8192, 1024) : smem_desc(stage_a(s, pa) + ks * 32, 16, 1024);
-                        const uint64_t db = B_MN ? smem_desc(stage_b(s, pb) + ks * 2048, 8192, 1024) : smem_desc(stage_b(s, pb) + ks * 32, 16, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (i | pr | ks) != 0 ? 1u : 0u);
+                        umma_bf16_lohi(tmem_d, a_lo + ks * kStepA, b_lo + ks * kStepB, kHi, idesc, accumulate);
+                        accumulate = 1;
                     }
                 }
                 tcgen05_commit(smem_u32(&bar_empty[s]));   // frees the stage once these MMAs have read it

@@ -35,7 +35,6 @@ class TrainStep:
         self.crop_uv, self.vis = f(B, 42), f(B, 21)
         # forward state
         self.cp, self.x, self.logdet, self.log_q = f(B, cpf), f(R, D), f(R), f(R)
-        self.saved = f(self.shape.layers + 1, R, D)
         self.z, self.jtr = f(R, 61), f(R, 21, 3)
         self.verts = f(R, 778, 3) if want_verts else None
         self.uv, self.row_lp = f(R, 42), f(R)
@@ -46,6 +45,7 @@ class TrainStep:
         self.djtr, self.dz, self.dlog_q = f(R, 21, 3), f(R, 61), f(R)
         self.dx, self.dz_det, self.dz0, self.dfeat = f(R, D), f(B, 16), f(R, D), f(B, flow.cond_dim)
         self.tc = flow.precision != 'fp32'
+        self.saved = torch.empty(L.mhe_flow_saved_bytes(self.shape, R, int(self.tc)), dtype=torch.uint8, device=dev)
         self.packed = None
         if self.tc:
             self.packed = torch.empty(L.mhe_flow_packed_bytes(self.shape), dtype=torch.uint8, device=dev)

@@ -114,21 +114,22 @@ class _FlowPassFn(torch.autograd.Function):
         out = torch.empty_like(inp)
         logdet = torch.empty(R, device=dev, dtype=torch.float32)
         need_grad = any(ctx.needs_input_grad[:3])
-        saved = torch.empty((shape.layers + 1), R, D, device=dev, dtype=torch.float32) if need_grad else None
+        tcore = int(packed is not None)
+        saved = torch.empty(lib().mhe_flow_saved_bytes(shape, R, tcore), device=dev, dtype=torch.uint8) if need_grad else None
         wsb = lib().mhe_flow_workspace_bytes(shape, R, int(packed is not None))
         ws = _lib.WORKSPACE.get(wsb, dev)
         check(lib().mhe_flow_pass_fwd(shape, ptr(flat), ptr(packed), ptr(mask), ptr(cp), ptr(inp), R, B, direction, ptr(out), ptr(logdet),
                                       ptr(saved), ptr(ws), wsb, stream_ptr(dev)), 'mhe_flow_pass_fwd')
         if need_grad:
             ctx.save_for_backward(cp, flat, mask, saved)
-        ctx.shape, ctx.direction, ctx.B, ctx.packed = shape, direction, B, packed
+        ctx.shape, ctx.direction, ctx.B, ctx.packed, ctx.dims = shape, direction, B, packed, (R, D)
         return out, logdet
 
     @staticmethod
     def backward(ctx, dout, dlogdet):
         cp, flat, mask, saved = ctx.saved_tensors
         shape = ctx.shape
-        R, D = saved.shape[1], saved.shape[2]
+        R, D = ctx.dims
         dev = saved.device
         dout = torch.zeros(R, D, device=dev) if dout is None else dout.contiguous()
         dlogdet = None if dlogdet is None else dlogdet.contiguous()
