@@ -1,4 +1,5 @@
 // Library-wide bits of the C ABI: error text, version, launch counter.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mhe {
@@ -11,6 +12,12 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MHE_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 
 // ---- timing probe ------------------------------------------------------------------------------

@@ -85,6 +85,29 @@ inline bool valid_shape(mhe_flow_shape s) {
     return s.dim >= 2 && s.dim <= 64 && s.hidden >= 1 && s.cond >= 1 && s.layers >= 1 && s.layers <= 64;
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// Kernels of the dependent launch chain are launched with programmatic stream serialization: the next kernel's
+// CTAs may start while the previous kernel drains, run their private prologue (barrier init, TMEM allocation,
+// descriptor prefetch) and then block in pdl_wait() until the previous kernel has completed and flushed.
+// Rule: nothing before pdl_wait() reads or writes global memory.  MHE_PDL=0 in the environment disables it.
+bool pdl_enabled();
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #if defined(__CUDACC__)
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : kLeakySlope * v; }
 // derivative of leaky_relu expressed through its OUTPUT a = lrelu(h): a > 0 <=> h > 0 (slope > 0)

@@ -137,6 +137,8 @@ __device__ __forceinline__ void put_planes(bf16* hi, long plane_stride, float v)
 __global__ void coupling_fwd_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ mask,
                                     const float* __restrict__ next_mask, int R, int D, int direction, float* __restrict__ y,
                                     float* __restrict__ logdet, bf16* __restrict__ ym) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (r >= R) return;
@@ -167,6 +169,8 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restri
                                     const float* g, const float* __restrict__ gl, float gl_scale, int R, int D, int direction,
                                     bf16* __restrict__ dprep, float* gx, float* __restrict__ db2, long db2_stride) {
     __shared__ float red[2][4][kDp];
+    pdl_launch_dependents();
+    pdl_wait();
     const int d = threadIdx.x & (kDp - 1), slot = threadIdx.x >> 6;
     const long ps = (long)R * kDp;
     const float m = d < D ? mask[d] : 1.f;
@@ -231,6 +235,29 @@ static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const E
     const long ctas128 = (long)cdiv(g.M, BM) * cdiv(g.N, 128) * g.batches * g.ksplit;
     if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3>(A, B, g, e, s, what);
     return launch_tc_gemm<64, A_MN, B_MN, 3>(A, B, g, e, s, what);
+}
+
+// ---- side stream for the weight-gradient GEMMs ---------------------------------------------------------
+// dW GEMMs are off the critical path of the backward (nothing downstream in the pass reads them), so they are
+// forked onto an internal stream, layer by layer, and joined at the end of the pass.  Fork/join uses events, which
+// also makes the branches parallel nodes when the caller captures the pass into a CUDA graph.
+struct Aux {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready[64] = {}, done[64] = {};
+    bool ok = false;
+};
+static Aux& aux_ctx() {
+    static Aux a;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        bool ok = cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 64 && ok; ++i)
+            ok = cudaEventCreateWithFlags(&a.ready[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&a.done[i], cudaEventDisableTiming) == cudaSuccess;
+        a.ok = ok;
+    }
+    return a;
 }
 
 // ---- packed weights -----------------------------------------------------------------------------------
@@ -339,8 +366,8 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
         else y = last ? out : ((x == ws.gx) ? ws.dpre : ws.gx);
         bf16* ym = last ? nullptr : (saved ? S.xm(step + 1) : ws.xm);
         const int next_layer = direction == 0 ? layer + 1 : layer - 1;
-        coupling_fwd_kernel<<<cdiv(R, 8), 256, 0, stream>>>(x, bf.st, mask + (size_t)layer * L.D, last ? nullptr : mask + (size_t)next_layer * L.D, R,
-                                                          L.D, direction, y, logdet, ym);
+        MHE_TRY(cuda_ok(launch_chain(coupling_fwd_kernel, dim3(cdiv(R, 8)), dim3(256), 0, stream, x, (const float*)bf.st, mask + (size_t)layer * L.D,
+                                     last ? (const float*)nullptr : mask + (size_t)next_layer * L.D, R, L.D, direction, y, logdet, ym), "tc coupling fwd"));
         MHE_TRY(check_launch("tc coupling fwd"));
         x = y;
     }
@@ -359,30 +386,40 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     const long RH = (long)R * L.H, RD = (long)R * kDp;
     const float* g = dout;
     const int ks = R >= 8192 ? 4 : 1;   // wgrad contracts over the rows: split K once it is long
+    Aux& aux = aux_ctx();
+    const bool fork = aux.ok && L.L <= 64;
+    cudaStream_t wstream = fork ? aux.stream : stream;
     for (int step = L.L - 1; step >= 0; --step) {
         const int layer = direction == 0 ? step : L.L - 1 - step;
+        const int pb = step & 1;
         const float* mrow = mask + (size_t)layer * L.D;
         float* dblk = dparams + L.block(layer, 0);
         float* gx = (step == 0) ? din : ws.gx;
-        coupling_bwd_kernel<<<cdiv(R, 32), 256, 0, stream>>>(S.x(step), S.st(step), mrow, g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dprep, gx,
-                                                           dblk + L.ob2, (long)L.blk);
+        // this parity's gradient planes were last read by the side-stream GEMMs of step + 2
+        if (fork && step + 2 < L.L) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[step + 2], 0), "wait wgrad"));
+        MHE_TRY(cuda_ok(launch_chain(coupling_bwd_kernel, dim3(cdiv(R, 32)), dim3(256), 0, stream, (const float*)S.x(step), (const float*)S.st(step), mrow,
+                                     g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dprep[pb], gx, dblk + L.ob2, (long)L.blk), "tc coupling bwd"));
         MHE_TRY(check_launch("tc coupling bwd"));
-        PlaneTensor dpreK = pt(ws.dprep, kDp, R, kDp, RD, 2, 2 * RD);
+        PlaneTensor dpreK = pt(ws.dprep[pb], kDp, R, kDp, RD, 2, 2 * RD);
         PlaneTensor w0 = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
         PlaneTensor w1 = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
         PlaneTensor w2 = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
         PlaneTensor a0 = pt(S.a0(step), L.H, R, L.H, RH, 2, 2 * RH), a1 = pt(S.a1(step), L.H, R, L.H, RH, 2, 2 * RH);
-        PlaneTensor dh0 = pt(ws.dh0, L.H, R, L.H, RH, 2, 2 * RH), dh1 = pt(ws.dh1, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor dh0 = pt(ws.dh0[pb], L.H, R, L.H, RH, 2, 2 * RH), dh1 = pt(ws.dh1[pb], L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor xm = pt(S.xm(step), kDp, R, kDp, RD, 1, 0);
         {   // dgrad G2: dh1 = (dpre W2) * lrelu'(a1);  W2 planes [64][H] read MN-major (cols = h);  dcp1 += sum_s dh1
             GemmShape s{R, L.H, kDp, 2, 1, 1, 1};
-            EpiActGradPlanes e{ws.dh1, S.a1(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
+            EpiActGradPlanes e{ws.dh1[pb], S.a1(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
             MHE_TRY((gemm<false, true>(dpreK, w2, s, e, stream, "tc dgrad G2")));
         }
         {   // dgrad G1: dh0 = (dh1 W1) * lrelu'(a0);  dcp0 += sum_s dh0
             GemmShape s{R, L.H, L.H, 2, 1, 1, 1};
-            EpiActGradPlanes e{ws.dh0, S.a0(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
+            EpiActGradPlanes e{ws.dh0[pb], S.a0(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
             MHE_TRY((gemm<false, true>(dh1, w1, s, e, stream, "tc dgrad G1")));
+        }
+        if (fork) {
+            MHE_TRY(cuda_ok(cudaEventRecord(aux.ready[step], stream), "fork wgrad"));
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(wstream, aux.ready[step], 0), "fork wgrad"));
         }
         {   // dgrad G0: gx += mask * (dh0 W0), both nets;  W0 planes [H][64] read MN-major (cols = d)
             GemmShape s{R, kDp, L.H, 2, 1, 1, 1};
@@ -392,19 +429,24 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         {   // dW1 [out][in] += dh1^T a0
             GemmShape s{L.H, L.H, R, 2, ks, 1, 1};
             EpiWgrad e{dblk + L.oW1, L.H, (long)L.blk, L.H, 0, ks > 1};
-            MHE_TRY((gemm<true, true>(dh1, a0, s, e, stream, "tc wgrad W1")));
+            MHE_TRY((gemm<true, true>(dh1, a0, s, e, wstream, "tc wgrad W1")));
         }
         {   // dW0 [out][d] += dh0^T xm
             GemmShape s{L.H, kDp, R, 2, ks, 1, 0};
             EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, 0, ks > 1};
-            MHE_TRY((gemm<true, true>(dh0, xm, s, e, stream, "tc wgrad W0")));
+            MHE_TRY((gemm<true, true>(dh0, xm, s, e, wstream, "tc wgrad W0")));
         }
         {   // dW2 [d][h] += dpre^T a1, computed as (a1^T dpre)[h][d] and stored transposed
             GemmShape s{L.H, kDp, R, 2, ks, 1, 1};
             EpiWgrad e{dblk + L.oW2, L.H, (long)L.blk, L.D, 1, ks > 1};
-            MHE_TRY((gemm<true, true>(a1, dpreK, s, e, stream, "tc wgrad W2")));
+            MHE_TRY((gemm<true, true>(a1, dpreK, s, e, wstream, "tc wgrad W2")));
         }
+        if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[step], wstream), "join wgrad"));
         g = gx;
+    }
+    if (fork) {   // join: everything the side stream did belongs to this pass
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0], 0), "join wgrad"));
+        if (L.L > 1) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[1], 0), "join wgrad"));
     }
     return MHE_OK;
 }

@@ -26,11 +26,11 @@ struct Packed {
 
 // per-pass scratch: activations as planes, small fp32 buffers
 struct Ws {
-    __nv_bfloat16 *xm, *a0, *a1, *dh0, *dh1, *dprep;
-    float *st, *dpre, *gx;
+    __nv_bfloat16 *xm, *a0, *a1, *dh0[2], *dh1[2], *dprep[2];   // gradient planes are double-buffered by layer parity:
+    float *st, *dpre, *gx;                                        // the weight-gradient GEMMs of a layer run on a side stream
     static size_t bytes(const FlowLayout& L, int R) {
         const size_t act = (size_t)2 * 2 * R * L.H * 2, small = (size_t)2 * 2 * R * kDp * 2;
-        return 4 * act + 2 * small + ((size_t)5 * R * L.D) * 4 + 16 * 1024;
+        return 6 * act + 4 * small + ((size_t)5 * R * L.D) * 4 + 32 * 1024;
     }
     Ws(void* base_, const FlowLayout& L, int R) {
         uint8_t* base = (uint8_t*)base_;
@@ -38,8 +38,10 @@ struct Ws {
         const size_t act = (size_t)2 * 2 * R * L.H * 2;
         xm = (__nv_bfloat16*)take((size_t)2 * R * kDp * 2);
         a0 = (__nv_bfloat16*)take(act); a1 = (__nv_bfloat16*)take(act);
-        dh0 = (__nv_bfloat16*)take(act); dh1 = (__nv_bfloat16*)take(act);
-        dprep = (__nv_bfloat16*)take((size_t)2 * 2 * R * kDp * 2);
+        for (int i = 0; i < 2; ++i) {
+            dh0[i] = (__nv_bfloat16*)take(act); dh1[i] = (__nv_bfloat16*)take(act);
+            dprep[i] = (__nv_bfloat16*)take((size_t)2 * 2 * R * kDp * 2);
+        }
         st = (float*)take((size_t)2 * R * L.D * 4);
         dpre = (float*)take((size_t)2 * R * L.D * 4);
         gx = (float*)take((size_t)R * L.D * 4);

@@ -554,7 +554,7 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
         {   // dbv [R][10] = dvp [R][2334] shapedirs [2334][10]
             GemmArgs g; g.A = ws.dvp; g.lda = 2336; g.B = c->shapedirs; g.ldb = kShape; g.M = R; g.N = kShape; g.K = kVC;
             EpiStore e{ws.dbv, 12, 0};
-            MHE_TRY((launch_sgemm<Major::K, Major::K>(g, e, stream, "mano dbv")));
+            MHE_TRY((launch_sgemm<Major::K, Major::MN>(g, e, stream, "mano dbv")));
         }
     }
     // mesh path: vertex gradients come through the workspace (tips already folded into dvt);

@@ -144,6 +144,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_accum;
     __shared__ uint32_t tmem_base_slot;
 
+    pdl_launch_dependents();   // let the next kernel of the chain start its prologue; it blocks in pdl_wait()
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -169,6 +170,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
+    pdl_wait();                // everything above is CTA-private; from here on we touch the predecessor's outputs
 
     auto stage_a = [&](int s, int p) { return smem0 + s * Plan::kStageBytes + p * Plan::kABytes; };
     auto stage_b = [&](int s, int p) { return smem0 + s * Plan::kStageBytes + NPL * Plan::kABytes + p * Plan::kBBytes; };
@@ -277,7 +279,10 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
     }
     ProbeScope probe(what, stream);
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), g.batches * g.ksplit);
-    kern<<<grid, kThreads, Plan::kBytes, stream>>>(*ma, *mb, g, epi);
+    if (launch_chain(kern, grid, dim3(kThreads), (size_t)Plan::kBytes, stream, *ma, *mb, g, epi) != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+        return MHE_ERR_CUDA;
+    }
     return check_launch(what);
 }
 
