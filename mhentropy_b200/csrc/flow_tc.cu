@@ -30,6 +30,7 @@ __device__ __forceinline__ void store_planes32(bf16* hi_ptr, bf16* lo_ptr, const
 
 // ---- epilogues (one call per thread per 32-column chunk of its accumulator row) -----------------------
 struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[batch][plane][row][col]
+    static constexpr bool kDirect = true, kStaged = false;
     bf16* out; long ld; long plane_stride; long batch_stride;
     const float* cp; long cp_ld; long cp_off; long cp_bstride; int B;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
@@ -43,22 +44,26 @@ struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[ba
         bf16* p = out + (long)b * batch_stride + (long)row * ld + col0;
         store_planes32(p, p + plane_stride, v);
     }
+    __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
 };
+__device__ __forceinline__ float fast_tanh(float x) {   // 1 - 2/(e^{2x}+1); abs error ~1e-7, saturates cleanly
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
 struct EpiOutHead {   // st[batch][row][col] = batch == 0 ? tanh(acc + b2) : acc + b2, col < D
+    static constexpr bool kDirect = false, kStaged = true;
     float* out; int D; long batch_stride; const float* bias; long bias_bstride;
-    __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < D) {
-                float t = v[j] + __ldg(bias + (long)b * bias_bstride + col);
-                if (b == 0) t = tanhf(t);
-                out[(long)b * batch_stride + (long)row * D + col] = t;
-            }
+    __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
+    __device__ void elem(int b, int, int row, int col, float v, const GemmShape&) const {
+        if (col < D) {
+            float t = v + __ldg(bias + (long)b * bias_bstride + col);
+            if (b == 0) t = fast_tanh(t);
+            out[(long)b * batch_stride + (long)row * D + col] = t;
         }
     }
 };
 struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes; dcp[row % B][...] += dh  (sum over the hypotheses of an image)
+    static constexpr bool kDirect = true, kStaged = true;
     bf16* out; const bf16* act_hi; long ld; long plane_stride; long batch_stride; long act_plane_stride; long act_batch_stride;
     float* dcp; long cp_ld; long cp_off; long cp_bstride; int B;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
@@ -75,38 +80,48 @@ struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes; dcp[row % B][..
                 v[8 * j + 2 * i + 1] *= ((e1 & 0x8000u) == 0 && (e1 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
             }
         }
-        float* g = dcp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(g + j, v[j]);
         const long off = (long)b * batch_stride + (long)row * ld + col0;
         store_planes32(out + off, out + off + plane_stride, v);
     }
+    // staged pass over the same (already masked) values: lanes along the columns -> coalesced atomics
+    __device__ void elem(int b, int, int row, int col, float v, const GemmShape&) const {
+        atomicAdd(dcp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col, v);
+    }
 };
 struct EpiMaskAtomicAdd {   // gx[row][col] += mask[col] * acc, col < D
+    static constexpr bool kDirect = false, kStaged = true;
     float* out; int D; const float* mask;
-    __device__ void operator()(int, int, int row, int col0, float* v, const GemmShape&) const {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < D) { const float w = __ldg(mask + col); if (w != 0.f) atomicAdd(out + (long)row * D + col, w * v[j]); }
+    __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
+    __device__ void elem(int, int, int row, int col, float v, const GemmShape&) const {
+        if (col < D) { const float w = __ldg(mask + col); if (w != 0.f) atomicAdd(out + (long)row * D + col, w * v); }
+    }
+};
+struct EpiWgrad {   // dW[batch][row][col] (+)= acc, col < ncols
+    static constexpr bool kDirect = false, kStaged = true;
+    float* dW; long ld; long batch_stride; int ncols; int atomic;
+    __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
+    __device__ void elem(int b, int, int row, int col, float v, const GemmShape&) const {
+        if (col < ncols) {
+            float* p = dW + (long)b * batch_stride + (long)row * ld + col;
+            if (atomic) atomicAdd(p, v); else *p += v;
         }
     }
 };
-struct EpiWgrad {   // dW[batch] (+)= acc;  transposed: element (row, col) goes to dW[col][row]
-    float* dW; long ld; long batch_stride; int ncols; int transposed; int atomic;
+struct EpiWgradT {   // element (row, col) goes to dW[batch][col][row]: lanes = rows are already contiguous in memory
+    static constexpr bool kDirect = true, kStaged = false;
+    float* dW; long ld; long batch_stride; int ncols; int atomic;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
-        float* base = dW + (long)b * batch_stride;
+        float* base = dW + (long)b * batch_stride + row;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const int col = col0 + j;
-            if (col < ncols) {
-                float* p = transposed ? base + (long)col * ld + row : base + (long)row * ld + col;
-                if (atomic) atomicAdd(p, v[j]); else *p += v[j];
-            }
+            if (col < ncols) { float* p = base + (long)col * ld; if (atomic) atomicAdd(p, v[j]); else *p += v[j]; }
         }
     }
+    __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
 };
 struct EpiCondFwd {   // cp[row][idx*H + col] = acc + Cb[idx][col] + b_j[col]
+    static constexpr bool kDirect = true, kStaged = false;
     float* cp; long cp_ld; int H; const float* params; size_t cb_base, cb_stride, blk, ob0, ob1;
     __device__ void operator()(int idx, int, int row, int col0, float* v, const GemmShape&) const {
         const float* cb = params + cb_base + (size_t)idx * cb_stride + col0;
@@ -117,12 +132,14 @@ struct EpiCondFwd {   // cp[row][idx*H + col] = acc + Cb[idx][col] + b_j[col]
             o[j] = make_float4(v[4 * j] + __ldg(cb + 4 * j) + __ldg(bj + 4 * j), v[4 * j + 1] + __ldg(cb + 4 * j + 1) + __ldg(bj + 4 * j + 1),
                                v[4 * j + 2] + __ldg(cb + 4 * j + 2) + __ldg(bj + 4 * j + 2), v[4 * j + 3] + __ldg(cb + 4 * j + 3) + __ldg(bj + 4 * j + 3));
     }
+    __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
 };
 struct EpiAtomicRows {   // C[row][col] += acc (every batch lands on the same output)
+    static constexpr bool kDirect = false, kStaged = true;
     float* C; long ld; int ncols;
-    __device__ void operator()(int, int, int row, int col0, float* v, const GemmShape&) const {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (col0 + j < ncols) atomicAdd(C + (long)row * ld + col0 + j, v[j]);
+    __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
+    __device__ void elem(int, int, int row, int col, float v, const GemmShape&) const {
+        if (col < ncols) atomicAdd(C + (long)row * ld + col, v);
     }
 };
 
@@ -242,8 +259,8 @@ static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const E
 // forked onto an internal stream, layer by layer, and joined at the end of the pass.  Fork/join uses events, which
 // also makes the branches parallel nodes when the caller captures the pass into a CUDA graph.
 struct Aux {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ready[64] = {}, done[64] = {};
+    cudaStream_t stream[2] = {nullptr, nullptr};   // [0]: the HxH gradient, [1]: the two thin ones
+    cudaEvent_t ready[64] = {}, done[2][64] = {};
     bool ok = false;
 };
 static Aux& aux_ctx() {
@@ -251,10 +268,12 @@ static Aux& aux_ctx() {
     static bool tried = false;
     if (!tried) {
         tried = true;
-        bool ok = cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) == cudaSuccess;
+        bool ok = cudaStreamCreateWithFlags(&a.stream[0], cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&a.stream[1], cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 64 && ok; ++i)
             ok = cudaEventCreateWithFlags(&a.ready[i], cudaEventDisableTiming) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&a.done[i], cudaEventDisableTiming) == cudaSuccess;
+                 cudaEventCreateWithFlags(&a.done[0][i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&a.done[1][i], cudaEventDisableTiming) == cudaSuccess;
         a.ok = ok;
     }
     return a;
@@ -295,7 +314,7 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
-        EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, 0};
+        EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0};
         MHE_TRY((gemm<true, true>(A, Bt, g, e, stream, "tc cond wgrad")));
     }
     cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, stream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
@@ -388,7 +407,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     const int ks = R >= 8192 ? 4 : 1;   // wgrad contracts over the rows: split K once it is long
     Aux& aux = aux_ctx();
     const bool fork = aux.ok && L.L <= 64;
-    cudaStream_t wstream = fork ? aux.stream : stream;
+    cudaStream_t wstream = fork ? aux.stream[0] : stream, wstream2 = fork ? aux.stream[1] : stream;
     for (int step = L.L - 1; step >= 0; --step) {
         const int layer = direction == 0 ? step : L.L - 1 - step;
         const int pb = step & 1;
@@ -396,7 +415,10 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         float* dblk = dparams + L.block(layer, 0);
         float* gx = (step == 0) ? din : ws.gx;
         // this parity's gradient planes were last read by the side-stream GEMMs of step + 2
-        if (fork && step + 2 < L.L) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[step + 2], 0), "wait wgrad"));
+        if (fork && step + 2 < L.L) {
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0][step + 2], 0), "wait wgrad"));
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[1][step + 2], 0), "wait wgrad"));
+        }
         MHE_TRY(cuda_ok(launch_chain(coupling_bwd_kernel, dim3(cdiv(R, 32)), dim3(256), 0, stream, (const float*)S.x(step), (const float*)S.st(step), mrow,
                                      g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dprep[pb], gx, dblk + L.ob2, (long)L.blk), "tc coupling bwd"));
         MHE_TRY(check_launch("tc coupling bwd"));
@@ -420,6 +442,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         if (fork) {
             MHE_TRY(cuda_ok(cudaEventRecord(aux.ready[step], stream), "fork wgrad"));
             MHE_TRY(cuda_ok(cudaStreamWaitEvent(wstream, aux.ready[step], 0), "fork wgrad"));
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(wstream2, aux.ready[step], 0), "fork wgrad"));
         }
         {   // dgrad G0: gx += mask * (dh0 W0), both nets;  W0 planes [H][64] read MN-major (cols = d)
             GemmShape s{R, kDp, L.H, 2, 1, 1, 1};
@@ -428,25 +451,28 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         }
         {   // dW1 [out][in] += dh1^T a0
             GemmShape s{L.H, L.H, R, 2, ks, 1, 1};
-            EpiWgrad e{dblk + L.oW1, L.H, (long)L.blk, L.H, 0, ks > 1};
+            EpiWgrad e{dblk + L.oW1, L.H, (long)L.blk, L.H, ks > 1};
             MHE_TRY((gemm<true, true>(dh1, a0, s, e, wstream, "tc wgrad W1")));
         }
         {   // dW0 [out][d] += dh0^T xm
             GemmShape s{L.H, kDp, R, 2, ks, 1, 0};
-            EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, 0, ks > 1};
-            MHE_TRY((gemm<true, true>(dh0, xm, s, e, wstream, "tc wgrad W0")));
+            EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, ks > 1};
+            MHE_TRY((gemm<true, true>(dh0, xm, s, e, wstream2, "tc wgrad W0")));
         }
         {   // dW2 [d][h] += dpre^T a1, computed as (a1^T dpre)[h][d] and stored transposed
             GemmShape s{L.H, kDp, R, 2, ks, 1, 1};
-            EpiWgrad e{dblk + L.oW2, L.H, (long)L.blk, L.D, 1, ks > 1};
-            MHE_TRY((gemm<true, true>(a1, dpreK, s, e, wstream, "tc wgrad W2")));
+            EpiWgradT e{dblk + L.oW2, L.H, (long)L.blk, L.D, ks > 1};
+            MHE_TRY((gemm<true, true>(a1, dpreK, s, e, wstream2, "tc wgrad W2")));
         }
-        if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[step], wstream), "join wgrad"));
+        if (fork) {
+            MHE_TRY(cuda_ok(cudaEventRecord(aux.done[0][step], wstream), "join wgrad"));
+            MHE_TRY(cuda_ok(cudaEventRecord(aux.done[1][step], wstream2), "join wgrad"));
+        }
         g = gx;
     }
     if (fork) {   // join: everything the side stream did belongs to this pass
-        MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0], 0), "join wgrad"));
-        if (L.L > 1) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[1], 0), "join wgrad"));
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0][0], 0), "join wgrad"));
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[1][0], 0), "join wgrad"));
     }
     return MHE_OK;
 }

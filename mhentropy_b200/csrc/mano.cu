@@ -506,7 +506,7 @@ int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
                                                                                  verts ? ws.pm : nullptr, verts ? ws.A : nullptr, verts ? ws.cen : nullptr, jtr);
     MHE_TRY(check_launch("mano pose fwd"));
     if (verts) {
-        if (R >= 8 * 148) {
+        if (R >= 512) {
             dim3 grid(cdiv(kV, 128), cdiv(R, 8));
             mano_skin_fwd_kernel<8><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr);
         } else {

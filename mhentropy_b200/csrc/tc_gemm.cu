@@ -102,15 +102,42 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long src_ld, 
     if (planes > 1) d[per] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// dense, unpadded, 4 elements per thread (weights): src [batches][n4*4] -> hi / lo planes
+__global__ void split_planes_vec4_kernel(const float4* __restrict__ src, long src_batch4, long n4, __nv_bfloat16* __restrict__ dst) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int b = blockIdx.y;
+    const float4 v = __ldg(src + (long)b * src_batch4 + i);
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
+                        l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+    uint2 hh, ll;
+    hh.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    hh.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    ll.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    ll.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+    uint2* d = reinterpret_cast<uint2*>(dst + (long)b * 2 * n4 * 4) + i;
+    d[0] = hh;
+    d[n4] = ll;
+}
+
 int split_planes(const float* src, long src_ld, long src_batch, int rows, int cols, const float* colscale, __nv_bfloat16* dst, int rows_p,
                  int cols_p, int planes, int batches, cudaStream_t stream) {
     if (rows_p <= 0 || cols_p <= 0 || batches <= 0) return MHE_OK;
+    const long n = (long)rows * cols;
+    if (planes == 2 && !colscale && rows == rows_p && cols == cols_p && src_ld == cols && n % 4 == 0 && src_batch % 4 == 0 &&
+        ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
+        dim3 grid(cdiv((int)(n / 4), 256), batches);
+        split_planes_vec4_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), src_batch / 4, n / 4, dst);
+        return check_launch("split planes vec4");
+    }
     dim3 grid(cdiv((int)((long)rows_p * cols_p), 256), batches);
     split_planes_kernel<<<grid, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p, planes);
     return check_launch("split planes");
 }
 
 struct EpiRawStore {   // C[batch][row][col] = acc  (+= when accumulate; atomic when K is split)
+    static constexpr bool kDirect = true, kStaged = false;
     float* C; long ldc; long strideC; int accumulate; int atomic;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape& g) const {
         float* p = C + (long)b * strideC + (long)row * ldc + col0;
@@ -123,6 +150,7 @@ struct EpiRawStore {   // C[batch][row][col] = acc  (+= when accumulate; atomic 
             }
         }
     }
+    __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
 };
 
 }  // namespace tc

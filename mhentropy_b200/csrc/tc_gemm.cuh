@@ -143,6 +143,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_accum;
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_stage[Epi::kStaged ? 4 : 1][32][33];   // epilogue transpose buffers, one per epilogue warp
 
     pdl_launch_dependents();   // let the next kernel of the chain start its prologue; it blocks in pdl_wait()
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -245,7 +246,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
-            if (row < g.M && n0 + c0 < g.N) epi(batch, split, row, n0 + c0, v, g);
+            if (n0 + c0 >= g.N) continue;                  // warp-uniform
+            if constexpr (Epi::kDirect) {
+                // lane = accumulator row: each thread owns 32 consecutive columns (vector stores)
+                if (row < g.M) epi(batch, split, row, n0 + c0, v, g);
+            }
+            if constexpr (Epi::kStaged) {
+                // transpose through shared memory so that lanes run along the columns: coalesced read-modify-write /
+                // atomics on the output row
+                float (*st)[33] = s_stage[warp - 2];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) st[lane][j] = v[j];
+                __syncwarp();
+                const int col = n0 + c0 + lane;
+                const int rows = min(32, g.M - (m0 + q * 32));
+                if (col < g.N)
+                    for (int rr = 0; rr < rows; ++rr) epi.elem(batch, split, m0 + q * 32 + rr, col, st[rr][lane], g);
+                __syncwarp();
+            }
         }
     }
     tcgen05_fence_before();
