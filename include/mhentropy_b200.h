@@ -74,8 +74,9 @@ size_t mhe_flow_param_offset(mhe_flow_shape s, int layer, int net, int which);
 size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s);
 /* Two arithmetic paths share every flow entry point:
  *   packed == NULL : exact fp32 on the CUDA cores;
- *   packed != NULL : tcgen05 tensor cores in bf16x3 split precision (hi*hi + hi*lo + lo*hi, fp32 accumulate);
- *                    `packed` holds the weights as split-bf16 planes, refreshed by mhe_flow_pack_weights()
+ *   packed != NULL : tcgen05 tensor cores in 3-pass split precision (hi*hi + hi*lo + lo*hi, fp32 accumulate): half planes
+ *                    for weights / activations, bfloat16 planes for gradients;
+ *                    `packed` holds the weights as split planes, refreshed by mhe_flow_pack_weights()
  *                    whenever the parameters change.  Needs dim <= 64, hidden % 64 == 0, cond % 8 == 0
  *                    (mhe_flow_packed_bytes() returns 0 otherwise).                                   */
 size_t mhe_flow_packed_bytes(mhe_flow_shape s);
@@ -206,15 +207,17 @@ int mhe_normalize_project(const mhe_loss_cfg* cfg, const float* joints, const fl
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core building blocks (tcgen05 + TMA), exposed for tests and tools.
- * fp32 values travel as split-bf16 planes x = hi + lo: bf16 [batches][planes][rows_p][cols_p].
+ * fp32 values travel as split 16-bit planes x = hi + lo, [batches][planes][rows_p][cols_p]: IEEE half planes (f16 = 1,
+ * ~22 significant bits, for range-safe data: weights, activations) or bfloat16 planes (f16 = 0, ~16 bits, full fp32
+ * range: gradients).  The flow uses half planes for every forward operand and bfloat16 planes for gradients.
  * ------------------------------------------------------------------------------------------ */
 /* src fp32 [batches][rows][cols] dense -> dst planes, zero padded to rows_p x cols_p (cols_p % 8 == 0). */
-int mhe_split_planes(const float* src, int rows, int cols, void* dst, int rows_p, int cols_p, int planes, int batches, void* stream);
+int mhe_split_planes(const float* src, int rows, int cols, void* dst, int rows_p, int cols_p, int planes, int batches, int f16, void* stream);
 /* C [batches][M][N] fp32 = A * B from dense plane tensors.  a_mn / b_mn = 0: A is [M][K], B is [N][K] (K-major);
- * = 1: A is [K][M], B is [K][N] (MN-major).  planes = 1: plain bf16; 2: bf16x3 (hi*hi + hi*lo + lo*hi).
+ * = 1: A is [K][M], B is [K][N] (MN-major).  planes = 1: one 16-bit pass; 2: three passes (hi*hi + hi*lo + lo*hi).  f16 selects half or bfloat16 planes.
  * bn in {64, 128} is the N tile; ksplit > 1 splits K across CTAs with atomic accumulation.          */
 int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K, int batches, int planes, int a_mn, int b_mn, int bn,
-                    int ksplit, void* stream);
+                    int ksplit, int f16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,14 +10,16 @@ using namespace tc;
 typedef __nv_bfloat16 bf16;
 
 // ---- plane stores -------------------------------------------------------------------------------
+// Forward operands (weights, activations) are half planes, gradients bfloat16 planes (see tc_gemm.cuh).
+template <bool F16>
 __device__ __forceinline__ void store_planes32(bf16* hi_ptr, bf16* lo_ptr, const float* v) {
     uint32_t h[16], l[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const bf16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-        const bf16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-        h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        const uint16_t h0 = to16<F16>(v[2 * j]), h1 = to16<F16>(v[2 * j + 1]);
+        const uint16_t l0 = to16<F16>(v[2 * j] - from16<F16>(h0)), l1 = to16<F16>(v[2 * j + 1] - from16<F16>(h1));
+        h[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        l[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
     }
     uint4* ph = reinterpret_cast<uint4*>(hi_ptr);
     uint4* pl = reinterpret_cast<uint4*>(lo_ptr);
@@ -42,7 +44,7 @@ struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[ba
             v[4 * j + 2] = lrelu(v[4 * j + 2] + t.z); v[4 * j + 3] = lrelu(v[4 * j + 3] + t.w);
         }
         bf16* p = out + (long)b * batch_stride + (long)row * ld + col0;
-        store_planes32(p, p + plane_stride, v);
+        store_planes32<true>(p, p + plane_stride, v);
     }
     __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
 };
@@ -74,14 +76,14 @@ struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes; dcp[row % B][..
             const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero (the hi plane carries the activation's sign)
+                // half > 0  <=>  sign bit clear and magnitude non-zero (the hi plane carries the activation's sign)
                 const uint32_t e0 = w[i] & 0xFFFFu, e1 = w[i] >> 16;
                 v[8 * j + 2 * i] *= ((e0 & 0x8000u) == 0 && (e0 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
                 v[8 * j + 2 * i + 1] *= ((e1 & 0x8000u) == 0 && (e1 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
             }
         }
         const long off = (long)b * batch_stride + (long)row * ld + col0;
-        store_planes32(out + off, out + off + plane_stride, v);
+        store_planes32<false>(out + off, out + off + plane_stride, v);
     }
     // staged pass over the same (already masked) values: lanes along the columns -> coalesced atomics
     __device__ void elem(int b, int, int row, int col, float v, const GemmShape&) const {
@@ -144,10 +146,12 @@ struct EpiAtomicRows {   // C[row][col] += acc (every batch lands on the same ou
 };
 
 // ---- elementwise kernels --------------------------------------------------------------------------
+template <bool F16>
 __device__ __forceinline__ void put_planes(bf16* hi, long plane_stride, float v) {
-    const bf16 h = __float2bfloat16_rn(v);
-    hi[0] = h;
-    hi[plane_stride] = __float2bfloat16_rn(v - __bfloat162float(h));
+    uint16_t* p = reinterpret_cast<uint16_t*>(hi);
+    const uint16_t h = to16<F16>(v);
+    p[0] = h;
+    p[plane_stride] = to16<F16>(v - from16<F16>(h));
 }
 
 // coupling forward (see flow.cu) + masked split planes of the result for the next layer's first GEMM
@@ -172,7 +176,7 @@ __global__ void coupling_fwd_kernel(const float* __restrict__ x, const float* __
             }
             y[(long)r * D + d] = out;
         }
-        if (ym) put_planes(ym + (long)r * kDp + d, (long)R * kDp, (d < D && next_mask) ? out * next_mask[d] : 0.f);
+        if (ym) put_planes<true>(ym + (long)r * kDp + d, (long)R * kDp, (d < D && next_mask) ? out * next_mask[d] : 0.f);
     }
     if (logdet) {
         ssum = warp_sum(ssum);
@@ -210,8 +214,8 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restri
             gx[k] = dx;
         }
         const long i = (long)r * kDp + d;
-        put_planes(dprep + i, ps, ds);
-        put_planes(dprep + 2 * ps + i, ps, dt);
+        put_planes<false>(dprep + i, ps, ds);
+        put_planes<false>(dprep + 2 * ps + i, ps, dt);
         sds += ds; sdt += dt;
     }
     red[0][slot][d] = sds; red[1][slot][d] = sdt;
@@ -246,12 +250,12 @@ static PlaneTensor pt(const bf16* base, int cols, int rows, long pitch, long pla
     return t;
 }
 
-// BN = 64 while the grid would not fill the chip with 128-wide tiles
-template <bool A_MN, bool B_MN, class Epi>
+// BN = 64 while the grid would not fill the chip with 128-wide tiles.  A_F16 / B_F16: half (forward operand) or bfloat16 (gradient) planes.
+template <bool A_MN, bool B_MN, bool A_F16, bool B_F16, class Epi>
 static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const Epi& e, cudaStream_t s, const char* what) {
     const long ctas128 = (long)cdiv(g.M, BM) * cdiv(g.N, 128) * g.batches * g.ksplit;
-    if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3>(A, B, g, e, s, what);
-    return launch_tc_gemm<64, A_MN, B_MN, 3>(A, B, g, e, s, what);
+    if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3, A_F16, B_F16>(A, B, g, e, s, what);
+    return launch_tc_gemm<64, A_MN, B_MN, 3, A_F16, B_F16>(A, B, g, e, s, what);
 }
 
 // ---- side stream for the weight-gradient GEMMs ---------------------------------------------------------
@@ -283,10 +287,10 @@ static Aux& aux_ctx() {
 int pack_weights(const FlowLayout& L, const float* params, void* packed, cudaStream_t stream) {
     Packed P(L, (bf16*)packed);
     // W0 [H][D] -> [H][64]; W1 [H][H]; W2 [D][H] -> [64][H]; Cw [H][C]
-    MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0, L.H, kDp, 2, L.L * 2, stream));
-    MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, stream));
-    MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, stream));
-    MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cw, L.H, L.C, 2, L.L * 4, stream));
+    MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0, L.H, kDp, 2, L.L * 2, true, stream));
+    MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, true, stream));
+    MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, true, stream));
+    MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cw, L.H, L.C, 2, L.L * 4, true, stream));
     return MHE_OK;
 }
 
@@ -294,12 +298,12 @@ int pack_weights(const FlowLayout& L, const float* params, void* packed, cudaStr
 int cond_fwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, int B, float* cp, void* ws_, cudaStream_t stream) {
     Packed P(L, (bf16*)packed);
     bf16* featp = (bf16*)ws_;   // [2][B][C]
-    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, stream));
+    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, true, stream));
     PlaneTensor A = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
     PlaneTensor Bt = pt(P.cw, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
     GemmShape g{B, L.H, L.C, L.L * 4, 1, 0, 1};
     EpiCondFwd e{cp, (long)L.L * 4 * L.H, L.H, params, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1};
-    return gemm<false, false>(A, Bt, g, e, stream, "tc cond fwd");
+    return gemm<false, false, true, true>(A, Bt, g, e, stream, "tc cond fwd");
 }
 
 int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, const float* dcp, int B,
@@ -308,14 +312,14 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
     const long cp_ld = (long)L.L * 4 * L.H;
     bf16* featp = (bf16*)ws_;                                   // [2][B][C]
     bf16* dcpp = featp + (((size_t)2 * B * L.C + 511) / 512) * 512;   // [2][B][cp_ld]
-    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, stream));
-    MHE_TRY(split_planes(dcp, cp_ld, 0, B, (int)cp_ld, nullptr, dcpp, B, (int)cp_ld, 2, 1, stream));
+    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, true, stream));
+    MHE_TRY(split_planes(dcp, cp_ld, 0, B, (int)cp_ld, nullptr, dcpp, B, (int)cp_ld, 2, 1, false, stream));
     {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat      (A MN-major: cols = h, rows = b; B MN-major: cols = c, rows = b)
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
         EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0};
-        MHE_TRY((gemm<true, true>(A, Bt, g, e, stream, "tc cond wgrad")));
+        MHE_TRY((gemm<true, true, false, true>(A, Bt, g, e, stream, "tc cond wgrad")));
     }
     cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, stream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
     MHE_TRY(check_launch("cond bias grad"));
@@ -325,7 +329,7 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         PlaneTensor Bt = pt(P.cw, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
         GemmShape g{B, L.C, L.H, L.L * 4, 1, 1, 1};
         EpiAtomicRows e{dfeat, L.C, L.C};
-        MHE_TRY((gemm<false, true>(A, Bt, g, e, stream, "tc cond dfeat")));
+        MHE_TRY((gemm<false, true, false, true>(A, Bt, g, e, stream, "tc cond dfeat")));
     }
     return MHE_OK;
 }
@@ -345,21 +349,21 @@ static int layer_nets_fwd(const FlowLayout& L, const float* params, const Packed
         PlaneTensor Bt = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
         GemmShape g{R, L.H, kDp, 2, 1, 0, 1};
         EpiHiddenPlanes e{bf.a0, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
-        MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G0")));
+        MHE_TRY((gemm<false, false, true, true>(A, Bt, g, e, stream, "tc flow G0")));
     }
     {   // G1: a0 x W1^T -> a1
         PlaneTensor A = pt(bf.a0, L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor Bt = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
         GemmShape g{R, L.H, L.H, 2, 1, 1, 1};
         EpiHiddenPlanes e{bf.a1, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
-        MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G1")));
+        MHE_TRY((gemm<false, false, true, true>(A, Bt, g, e, stream, "tc flow G1")));
     }
     {   // G2: a1 x W2^T + b2 -> st
         PlaneTensor A = pt(bf.a1, L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor Bt = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
         GemmShape g{R, kDp, L.H, 2, 1, 1, 1};
         EpiOutHead e{bf.st, L.D, (long)R * L.D, params + L.block(layer, 0) + L.ob2, (long)L.blk};
-        MHE_TRY((gemm<false, false>(A, Bt, g, e, stream, "tc flow G2")));
+        MHE_TRY((gemm<false, false, true, true>(A, Bt, g, e, stream, "tc flow G2")));
     }
     return MHE_OK;
 }
@@ -373,7 +377,7 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
     if (logdet) MHE_TRY(cuda_ok(cudaMemsetAsync(logdet, 0, (size_t)R * sizeof(float), stream), "memset logdet"));
     const int first = direction == 0 ? 0 : L.L - 1;
     if (saved) MHE_TRY(cuda_ok(cudaMemcpyAsync(S.x(0), in, row_bytes, cudaMemcpyDeviceToDevice, stream), "save input"));
-    MHE_TRY(split_planes(in, L.D, 0, R, L.D, mask + (size_t)first * L.D, saved ? S.xm(0) : ws.xm, R, kDp, 2, 1, stream));
+    MHE_TRY(split_planes(in, L.D, 0, R, L.D, mask + (size_t)first * L.D, saved ? S.xm(0) : ws.xm, R, kDp, 2, 1, true, stream));
     const float* x = saved ? S.x(0) : in;
     for (int step = 0; step < L.L; ++step) {
         const int layer = direction == 0 ? step : L.L - 1 - step;
@@ -432,12 +436,12 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         {   // dgrad G2: dh1 = (dpre W2) * lrelu'(a1);  W2 planes [64][H] read MN-major (cols = h);  dcp1 += sum_s dh1
             GemmShape s{R, L.H, kDp, 2, 1, 1, 1};
             EpiActGradPlanes e{ws.dh1[pb], S.a1(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
-            MHE_TRY((gemm<false, true>(dpreK, w2, s, e, stream, "tc dgrad G2")));
+            MHE_TRY((gemm<false, true, false, true>(dpreK, w2, s, e, stream, "tc dgrad G2")));
         }
         {   // dgrad G1: dh0 = (dh1 W1) * lrelu'(a0);  dcp0 += sum_s dh0
             GemmShape s{R, L.H, L.H, 2, 1, 1, 1};
             EpiActGradPlanes e{ws.dh0[pb], S.a0(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
-            MHE_TRY((gemm<false, true>(dh1, w1, s, e, stream, "tc dgrad G1")));
+            MHE_TRY((gemm<false, true, false, true>(dh1, w1, s, e, stream, "tc dgrad G1")));
         }
         if (fork) {
             MHE_TRY(cuda_ok(cudaEventRecord(aux.ready[step], stream), "fork wgrad"));
@@ -447,22 +451,22 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         {   // dgrad G0: gx += mask * (dh0 W0), both nets;  W0 planes [H][64] read MN-major (cols = d)
             GemmShape s{R, kDp, L.H, 2, 1, 1, 1};
             EpiMaskAtomicAdd e{gx, L.D, mrow};
-            MHE_TRY((gemm<false, true>(dh0, w0, s, e, stream, "tc dgrad G0")));
+            MHE_TRY((gemm<false, true, false, true>(dh0, w0, s, e, stream, "tc dgrad G0")));
         }
         {   // dW1 [out][in] += dh1^T a0
             GemmShape s{L.H, L.H, R, 2, ks, 1, 1};
             EpiWgrad e{dblk + L.oW1, L.H, (long)L.blk, L.H, ks > 1};
-            MHE_TRY((gemm<true, true>(dh1, a0, s, e, wstream, "tc wgrad W1")));
+            MHE_TRY((gemm<true, true, false, true>(dh1, a0, s, e, wstream, "tc wgrad W1")));
         }
         {   // dW0 [out][d] += dh0^T xm
             GemmShape s{L.H, kDp, R, 2, ks, 1, 0};
             EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, ks > 1};
-            MHE_TRY((gemm<true, true>(dh0, xm, s, e, wstream2, "tc wgrad W0")));
+            MHE_TRY((gemm<true, true, false, true>(dh0, xm, s, e, wstream2, "tc wgrad W0")));
         }
         {   // dW2 [d][h] += dpre^T a1, computed as (a1^T dpre)[h][d] and stored transposed
             GemmShape s{L.H, kDp, R, 2, ks, 1, 1};
             EpiWgradT e{dblk + L.oW2, L.H, (long)L.blk, L.D, ks > 1};
-            MHE_TRY((gemm<true, true>(a1, dpreK, s, e, wstream2, "tc wgrad W2")));
+            MHE_TRY((gemm<true, true, true, false>(a1, dpreK, s, e, wstream2, "tc wgrad W2")));
         }
         if (fork) {
             MHE_TRY(cuda_ok(cudaEventRecord(aux.done[0][step], wstream), "join wgrad"));

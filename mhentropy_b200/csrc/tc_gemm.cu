@@ -82,10 +82,11 @@ const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status) {
     return m;
 }
 
-// fp32 [batches][rows][cols] (src_ld pitch) -> bf16 planes [batches][planes][rows_p][cols_p], zero padded,
+// fp32 [batches][rows][cols] (src_ld pitch) -> 16-bit planes [batches][planes][rows_p][cols_p], zero padded,
 // optional per-column multiplier (the coupling mask).
+template <bool F16>
 __global__ void split_planes_kernel(const float* __restrict__ src, long src_ld, long src_batch, int rows, int cols, const float* __restrict__ colscale,
-                                    __nv_bfloat16* __restrict__ dst, int rows_p, int cols_p, int planes) {
+                                    uint16_t* __restrict__ dst, int rows_p, int cols_p, int planes) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long per = (long)rows_p * cols_p;
     if (idx >= per) return;
@@ -96,43 +97,45 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long src_ld, 
         v = src[(long)b * src_batch + (long)r * src_ld + c];
         if (colscale) v *= colscale[c];
     }
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    __nv_bfloat16* d = dst + (long)b * planes * per + idx;
+    const uint16_t hi = to16<F16>(v);
+    uint16_t* d = dst + (long)b * planes * per + idx;
     d[0] = hi;
-    if (planes > 1) d[per] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    if (planes > 1) d[per] = to16<F16>(v - from16<F16>(hi));
 }
 
 // dense, unpadded, 4 elements per thread (weights): src [batches][n4*4] -> hi / lo planes
-__global__ void split_planes_vec4_kernel(const float4* __restrict__ src, long src_batch4, long n4, __nv_bfloat16* __restrict__ dst) {
+template <bool F16>
+__global__ void split_planes_vec4_kernel(const float4* __restrict__ src, long src_batch4, long n4, uint16_t* __restrict__ dst) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const int b = blockIdx.y;
     const float4 v = __ldg(src + (long)b * src_batch4 + i);
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                        l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+    const uint16_t h0 = to16<F16>(v.x), h1 = to16<F16>(v.y), h2 = to16<F16>(v.z), h3 = to16<F16>(v.w);
+    const uint16_t l0 = to16<F16>(v.x - from16<F16>(h0)), l1 = to16<F16>(v.y - from16<F16>(h1)), l2 = to16<F16>(v.z - from16<F16>(h2)),
+                   l3 = to16<F16>(v.w - from16<F16>(h3));
     uint2 hh, ll;
-    hh.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    hh.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-    ll.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    ll.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+    hh.x = (uint32_t)h0 | ((uint32_t)h1 << 16); hh.y = (uint32_t)h2 | ((uint32_t)h3 << 16);
+    ll.x = (uint32_t)l0 | ((uint32_t)l1 << 16); ll.y = (uint32_t)l2 | ((uint32_t)l3 << 16);
     uint2* d = reinterpret_cast<uint2*>(dst + (long)b * 2 * n4 * 4) + i;
     d[0] = hh;
     d[n4] = ll;
 }
 
-int split_planes(const float* src, long src_ld, long src_batch, int rows, int cols, const float* colscale, __nv_bfloat16* dst, int rows_p,
-                 int cols_p, int planes, int batches, cudaStream_t stream) {
+int split_planes(const float* src, long src_ld, long src_batch, int rows, int cols, const float* colscale, __nv_bfloat16* dst_, int rows_p,
+                 int cols_p, int planes, int batches, bool f16, cudaStream_t stream) {
     if (rows_p <= 0 || cols_p <= 0 || batches <= 0) return MHE_OK;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(dst_);
     const long n = (long)rows * cols;
     if (planes == 2 && !colscale && rows == rows_p && cols == cols_p && src_ld == cols && n % 4 == 0 && src_batch % 4 == 0 &&
         ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
         dim3 grid(cdiv((int)(n / 4), 256), batches);
-        split_planes_vec4_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), src_batch / 4, n / 4, dst);
+        if (f16) split_planes_vec4_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), src_batch / 4, n / 4, dst);
+        else split_planes_vec4_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), src_batch / 4, n / 4, dst);
         return check_launch("split planes vec4");
     }
     dim3 grid(cdiv((int)((long)rows_p * cols_p), 256), batches);
-    split_planes_kernel<<<grid, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p, planes);
+    if (f16) split_planes_kernel<true><<<grid, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p, planes);
+    else split_planes_kernel<false><<<grid, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p, planes);
     return check_launch("split planes");
 }
 
@@ -161,16 +164,16 @@ using namespace mhe::tc;
 
 extern "C" {
 
-int mhe_split_planes(const float* src, int rows, int cols, void* dst, int rows_p, int cols_p, int planes, int batches, void* stream) {
+int mhe_split_planes(const float* src, int rows, int cols, void* dst, int rows_p, int cols_p, int planes, int batches, int f16, void* stream) {
     MHE_REQUIRE(src && dst && rows >= 0 && cols >= 0 && rows_p >= rows && cols_p >= cols && cols_p % 8 == 0 && (planes == 1 || planes == 2),
                 "split_planes: bad args");
-    return split_planes(src, cols, (long)rows * cols, rows, cols, nullptr, (__nv_bfloat16*)dst, rows_p, cols_p, planes, batches, (cudaStream_t)stream);
+    return split_planes(src, cols, (long)rows * cols, rows, cols, nullptr, (__nv_bfloat16*)dst, rows_p, cols_p, planes, batches, f16 != 0, (cudaStream_t)stream);
 }
 
 // Raw tensor-core GEMM for tests: A, B are plane tensors [batches][planes][rows][cols] (dense), C fp32 [batches][M][N].
 // a_mn / b_mn select MN-major operands (A stored [K][M], B stored [K][N]); otherwise A is [M][K], B is [N][K].
 int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K, int batches, int planes, int a_mn, int b_mn, int bn,
-                    int ksplit, void* stream_) {
+                    int ksplit, int f16, void* stream_) {
     MHE_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && batches > 0 && (planes == 1 || planes == 2) && (bn == 64 || bn == 128) && ksplit >= 1,
                 "tc_gemm_raw: bad args");
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -184,7 +187,8 @@ int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K,
     GemmShape g{M, N, K, batches, ksplit, 1, 1};
     EpiRawStore e{C, N, (long)M * N, 0, ksplit > 1};
     if (ksplit > 1 && cudaMemsetAsync(C, 0, (size_t)batches * M * N * sizeof(float), stream) != cudaSuccess) return MHE_ERR_CUDA;
-#define MHE_RAW(BN_, AMN_, BMN_, NP_) return launch_tc_gemm<BN_, AMN_, BMN_, NP_>(ta, tb, g, e, stream, "tc raw")
+#define MHE_RAW(BN_, AMN_, BMN_, NP_) do { if (f16) return launch_tc_gemm<BN_, AMN_, BMN_, NP_, true, true>(ta, tb, g, e, stream, "tc raw"); \
+                                             return launch_tc_gemm<BN_, AMN_, BMN_, NP_, false, false>(ta, tb, g, e, stream, "tc raw"); } while (0)
 #define MHE_RAW_NP(BN_, AMN_, BMN_) do { if (planes == 1) MHE_RAW(BN_, AMN_, BMN_, 1); else MHE_RAW(BN_, AMN_, BMN_, 3); } while (0)
 #define MHE_RAW_MAJ(BN_) do { if (!a_mn && !b_mn) MHE_RAW_NP(BN_, false, false); else if (!a_mn && b_mn) MHE_RAW_NP(BN_, false, true); \
                               else if (a_mn && !b_mn) MHE_RAW_NP(BN_, true, false); else MHE_RAW_NP(BN_, true, true); } while (0)

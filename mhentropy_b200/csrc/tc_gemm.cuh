@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace mhe {
@@ -34,8 +35,23 @@ struct PlaneTensor {          // [batches][planes][rows][cols] bf16, element str
 };
 
 int make_tensor_map(CUtensorMap* map, const PlaneTensor& t, int box_rows);
+// 16-bit split planes of fp32 data: x = hi + lo.  f16 = true stores IEEE half (11-bit significands, ~22 bits kept; for
+// range-safe data: weights, activations), false stores bfloat16 (8-bit significands, ~16 bits kept; full fp32 range: gradients).
 int split_planes(const float* src, long src_ld, long src_batch, int rows, int cols, const float* colscale, __nv_bfloat16* dst, int rows_p,
-                 int cols_p, int planes, int batches, cudaStream_t stream);
+                 int cols_p, int planes, int batches, bool f16, cudaStream_t stream);
+
+#if defined(__CUDACC__)
+template <bool F16>
+__device__ __forceinline__ uint16_t to16(float v) {
+    if (F16) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+template <bool F16>
+__device__ __forceinline__ float from16(uint16_t u) {
+    if (F16) return __half2float(__ushort_as_half(u));
+    return __bfloat162float(__ushort_as_bfloat16(u));
+}
+#endif
 
 // ---- device primitives ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,8 +96,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32, M = 128
-__host__ __device__ constexpr uint32_t instr_desc(int n, bool a_mn, bool b_mn) {
-    return (1u << 4) /*c = f32*/ | (1u << 7) /*a = bf16*/ | (1u << 10) /*b = bf16*/ |
+// operand formats: F16 = 0, BF16 = 1 (they may differ between A and B)
+__host__ __device__ constexpr uint32_t instr_desc(int n, bool a_mn, bool b_mn, bool a_f16 = false, bool b_f16 = false) {
+    return (1u << 4) /*c = f32*/ | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) |
            ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -134,7 +151,7 @@ struct SmemPlan {
 
 // C[batch] (M x N) = sum_pairs A_pa (M x K) * B_pb (K x N).  Epi::operator()(batch, split, row, col0, v[32], shape)
 // is called by every epilogue thread once per 32-column chunk with its accumulator row.
-template <int BN, bool A_MN, bool B_MN, int NPAIR, class Epi>
+template <int BN, bool A_MN, bool B_MN, int NPAIR, bool A_F16, bool B_F16, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi) {
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
@@ -202,7 +219,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(BN, A_MN, B_MN);
+            constexpr uint32_t idesc = instr_desc(BN, A_MN, B_MN, A_F16, B_F16);
             // Descriptors differ between MMAs only in the 14-bit start address: build the constant part once and
             // add 16-byte-unit offsets, so the single issuing thread spends a few instructions per MMA.
             constexpr uint32_t kHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));          // SBO | version | SWIZZLE_128B
@@ -276,7 +293,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // launch helper: builds (cached) tensor maps and launches.  A: rows = M (K-major) or K (MN-major), etc.
 const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status);
 
-template <int BN, bool A_MN, bool B_MN, int NPAIR, class Epi>
+template <int BN, bool A_MN, bool B_MN, int NPAIR, bool A_F16, bool B_F16, class Epi>
 inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const GemmShape& g, const Epi& epi, cudaStream_t stream, const char* what) {
     if (g.M <= 0 || g.N <= 0 || g.batches <= 0) return MHE_OK;
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
@@ -286,7 +303,7 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
     if (st != MHE_OK) return st;
     const CUtensorMap* mb = cached_map(B, B_MN ? 64 : BN, &st);
     if (st != MHE_OK) return st;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, NPAIR, Epi>;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, NPAIR, A_F16, B_F16, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes) != cudaSuccess) {

@@ -17,7 +17,7 @@ def bench(name, M, N, K, b, a_mn, b_mn, bn, ksplit=1, reps=40):
     B = planes(b, K if b_mn else N, N if b_mn else K)
     C = torch.zeros(b, M, N, device=DEV)
     s = _lib.stream_ptr()
-    call = lambda: _lib.check(L.mhe_tc_gemm_raw(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, b, 2, int(a_mn), int(b_mn), bn, ksplit, _lib.stream_ptr()), 'gemm')
+    call = lambda: _lib.check(L.mhe_tc_gemm_raw(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), M, N, K, b, 2, int(a_mn), int(b_mn), bn, ksplit, 0, _lib.stream_ptr()), 'gemm')
     for _ in range(3):
         call()
     torch.cuda.synchronize()
