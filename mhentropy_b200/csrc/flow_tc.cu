@@ -226,6 +226,18 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restri
     }
 }
 
+// half planes -> bfloat16 planes of the same values (for the backward GEMMs): n elements per plane, batches of [2 planes][n]
+__global__ void replane_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long n, int batches) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * batches) return;
+    const long b = i / n, k = i % n;
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + b * 2 * n;
+    const float v = from16<true>(s16[k]) + from16<true>(s16[n + k]);
+    put_planes<false>(dst + b * 2 * n + k, n, v);
+}
+
 __global__ void cond_bias_grad_kernel(const float* __restrict__ dcp, int B, long cp_ld, int H, float* __restrict__ dparams,
                                       size_t cb_base, size_t cb_stride, size_t blk, size_t ob0, size_t ob1) {
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,12 +262,12 @@ static PlaneTensor pt(const bf16* base, int cols, int rows, long pitch, long pla
     return t;
 }
 
-// BN = 64 while the grid would not fill the chip with 128-wide tiles.  A_F16 / B_F16: half (forward operand) or bfloat16 (gradient) planes.
-template <bool A_MN, bool B_MN, bool A_F16, bool B_F16, class Epi>
+// BN = 64 while the grid would not fill the chip with 128-wide tiles.  F16: both operands are half planes (forward GEMMs) or both bfloat16 planes (backward GEMMs).
+template <bool A_MN, bool B_MN, bool F16, class Epi>
 static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const Epi& e, cudaStream_t s, const char* what) {
     const long ctas128 = (long)cdiv(g.M, BM) * cdiv(g.N, 128) * g.batches * g.ksplit;
-    if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3, A_F16, B_F16>(A, B, g, e, s, what);
-    return launch_tc_gemm<64, A_MN, B_MN, 3, A_F16, B_F16>(A, B, g, e, s, what);
+    if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
+    return launch_tc_gemm<64, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
 }
 
 // ---- side stream for the weight-gradient GEMMs ---------------------------------------------------------
@@ -291,6 +303,10 @@ int pack_weights(const FlowLayout& L, const float* params, void* packed, cudaStr
     MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, true, stream));
     MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, true, stream));
     MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cw, L.H, L.C, 2, L.L * 4, true, stream));
+    MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0b, L.H, kDp, 2, L.L * 2, false, stream));
+    MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1b, L.H, L.H, 2, L.L * 2, false, stream));
+    MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2b, kDp, L.H, 2, L.L * 2, false, stream));
+    MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cwb, L.H, L.C, 2, L.L * 4, false, stream));
     return MHE_OK;
 }
 
@@ -303,7 +319,7 @@ int cond_fwd(const FlowLayout& L, const float* params, const void* packed, const
     PlaneTensor Bt = pt(P.cw, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
     GemmShape g{B, L.H, L.C, L.L * 4, 1, 0, 1};
     EpiCondFwd e{cp, (long)L.L * 4 * L.H, L.H, params, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1};
-    return gemm<false, false, true, true>(A, Bt, g, e, stream, "tc cond fwd");
+    return gemm<false, false, true>(A, Bt, g, e, stream, "tc cond fwd");
 }
 
 int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, const float* dcp, int B,
@@ -312,24 +328,24 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
     const long cp_ld = (long)L.L * 4 * L.H;
     bf16* featp = (bf16*)ws_;                                   // [2][B][C]
     bf16* dcpp = featp + (((size_t)2 * B * L.C + 511) / 512) * 512;   // [2][B][cp_ld]
-    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, true, stream));
+    MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, false, stream));   // bfloat16: partner of dcp planes
     MHE_TRY(split_planes(dcp, cp_ld, 0, B, (int)cp_ld, nullptr, dcpp, B, (int)cp_ld, 2, 1, false, stream));
     {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat      (A MN-major: cols = h, rows = b; B MN-major: cols = c, rows = b)
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
         EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0};
-        MHE_TRY((gemm<true, true, false, true>(A, Bt, g, e, stream, "tc cond wgrad")));
+        MHE_TRY((gemm<true, true, false>(A, Bt, g, e, stream, "tc cond wgrad")));
     }
     cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, stream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
     MHE_TRY(check_launch("cond bias grad"));
     if (dfeat) {   // dfeat [B][C] = sum_idx dcp[:, idx, :] Cw[idx]   (A K-major over h; B MN-major: cols = c, rows = h)
         MHE_TRY(cuda_ok(cudaMemsetAsync(dfeat, 0, (size_t)B * L.C * sizeof(float), stream), "memset dfeat"));
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
-        PlaneTensor Bt = pt(P.cw, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
+        PlaneTensor Bt = pt(P.cwb, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
         GemmShape g{B, L.C, L.H, L.L * 4, 1, 1, 1};
         EpiAtomicRows e{dfeat, L.C, L.C};
-        MHE_TRY((gemm<false, true, false, true>(A, Bt, g, e, stream, "tc cond dfeat")));
+        MHE_TRY((gemm<false, true, false>(A, Bt, g, e, stream, "tc cond dfeat")));
     }
     return MHE_OK;
 }
@@ -349,21 +365,21 @@ static int layer_nets_fwd(const FlowLayout& L, const float* params, const Packed
         PlaneTensor Bt = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
         GemmShape g{R, L.H, kDp, 2, 1, 0, 1};
         EpiHiddenPlanes e{bf.a0, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
-        MHE_TRY((gemm<false, false, true, true>(A, Bt, g, e, stream, "tc flow G0")));
+        MHE_TRY((gemm<false, false, true>(A, Bt, g, e, stream, "tc flow G0")));
     }
     {   // G1: a0 x W1^T -> a1
         PlaneTensor A = pt(bf.a0, L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor Bt = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
         GemmShape g{R, L.H, L.H, 2, 1, 1, 1};
         EpiHiddenPlanes e{bf.a1, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
-        MHE_TRY((gemm<false, false, true, true>(A, Bt, g, e, stream, "tc flow G1")));
+        MHE_TRY((gemm<false, false, true>(A, Bt, g, e, stream, "tc flow G1")));
     }
     {   // G2: a1 x W2^T + b2 -> st
         PlaneTensor A = pt(bf.a1, L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor Bt = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
         GemmShape g{R, kDp, L.H, 2, 1, 1, 1};
         EpiOutHead e{bf.st, L.D, (long)R * L.D, params + L.block(layer, 0) + L.ob2, (long)L.blk};
-        MHE_TRY((gemm<false, false, true, true>(A, Bt, g, e, stream, "tc flow G2")));
+        MHE_TRY((gemm<false, false, true>(A, Bt, g, e, stream, "tc flow G2")));
     }
     return MHE_OK;
 }
@@ -427,21 +443,21 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
                                      g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dprep[pb], gx, dblk + L.ob2, (long)L.blk), "tc coupling bwd"));
         MHE_TRY(check_launch("tc coupling bwd"));
         PlaneTensor dpreK = pt(ws.dprep[pb], kDp, R, kDp, RD, 2, 2 * RD);
-        PlaneTensor w0 = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
-        PlaneTensor w1 = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
-        PlaneTensor w2 = pt(P.w2 + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
-        PlaneTensor a0 = pt(S.a0(step), L.H, R, L.H, RH, 2, 2 * RH), a1 = pt(S.a1(step), L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor w0 = pt(P.w0b + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
+        PlaneTensor w1 = pt(P.w1b + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
+        PlaneTensor w2 = pt(P.w2b + (size_t)layer * 2 * 2 * kDp * L.H, L.H, kDp, L.H, (long)kDp * L.H, 2, (long)2 * kDp * L.H);
+        PlaneTensor a0 = pt(ws.a0b, L.H, R, L.H, RH, 2, 2 * RH), a1 = pt(ws.a1b, L.H, R, L.H, RH, 2, 2 * RH);
         PlaneTensor dh0 = pt(ws.dh0[pb], L.H, R, L.H, RH, 2, 2 * RH), dh1 = pt(ws.dh1[pb], L.H, R, L.H, RH, 2, 2 * RH);
-        PlaneTensor xm = pt(S.xm(step), kDp, R, kDp, RD, 1, 0);
+        PlaneTensor xm = pt(ws.xmb, kDp, R, kDp, RD, 1, 0);
         {   // dgrad G2: dh1 = (dpre W2) * lrelu'(a1);  W2 planes [64][H] read MN-major (cols = h);  dcp1 += sum_s dh1
             GemmShape s{R, L.H, kDp, 2, 1, 1, 1};
             EpiActGradPlanes e{ws.dh1[pb], S.a1(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
-            MHE_TRY((gemm<false, true, false, true>(dpreK, w2, s, e, stream, "tc dgrad G2")));
+            MHE_TRY((gemm<false, true, false>(dpreK, w2, s, e, stream, "tc dgrad G2")));
         }
         {   // dgrad G1: dh0 = (dh1 W1) * lrelu'(a0);  dcp0 += sum_s dh0
             GemmShape s{R, L.H, L.H, 2, 1, 1, 1};
             EpiActGradPlanes e{ws.dh0[pb], S.a0(step), L.H, RH, 2 * RH, RH, 2 * RH, dcp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
-            MHE_TRY((gemm<false, true, false, true>(dh1, w1, s, e, stream, "tc dgrad G1")));
+            MHE_TRY((gemm<false, true, false>(dh1, w1, s, e, stream, "tc dgrad G1")));
         }
         if (fork) {
             MHE_TRY(cuda_ok(cudaEventRecord(aux.ready[step], stream), "fork wgrad"));
@@ -451,22 +467,29 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         {   // dgrad G0: gx += mask * (dh0 W0), both nets;  W0 planes [H][64] read MN-major (cols = d)
             GemmShape s{R, kDp, L.H, 2, 1, 1, 1};
             EpiMaskAtomicAdd e{gx, L.D, mrow};
-            MHE_TRY((gemm<false, true, false, true>(dh0, w0, s, e, stream, "tc dgrad G0")));
+            MHE_TRY((gemm<false, true, false>(dh0, w0, s, e, stream, "tc dgrad G0")));
         }
+        // the saved activations are half planes; the side streams re-plane them to bfloat16 for their GEMMs
+        replane_kernel<<<cdiv((int)(2 * RH), 256), 256, 0, wstream>>>(S.a0(step), ws.a0b, RH, 2);
+        MHE_TRY(check_launch("replane a0"));
+        replane_kernel<<<cdiv((int)(2 * RH), 256), 256, 0, wstream2>>>(S.a1(step), ws.a1b, RH, 2);
+        MHE_TRY(check_launch("replane a1"));
+        replane_kernel<<<cdiv((int)RD, 256), 256, 0, wstream2>>>(S.xm(step), ws.xmb, RD, 1);
+        MHE_TRY(check_launch("replane xm"));
         {   // dW1 [out][in] += dh1^T a0
             GemmShape s{L.H, L.H, R, 2, ks, 1, 1};
             EpiWgrad e{dblk + L.oW1, L.H, (long)L.blk, L.H, ks > 1};
-            MHE_TRY((gemm<true, true, false, true>(dh1, a0, s, e, wstream, "tc wgrad W1")));
+            MHE_TRY((gemm<true, true, false>(dh1, a0, s, e, wstream, "tc wgrad W1")));
         }
         {   // dW0 [out][d] += dh0^T xm
             GemmShape s{L.H, kDp, R, 2, ks, 1, 0};
             EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, ks > 1};
-            MHE_TRY((gemm<true, true, false, true>(dh0, xm, s, e, wstream2, "tc wgrad W0")));
+            MHE_TRY((gemm<true, true, false>(dh0, xm, s, e, wstream2, "tc wgrad W0")));
         }
         {   // dW2 [d][h] += dpre^T a1, computed as (a1^T dpre)[h][d] and stored transposed
             GemmShape s{L.H, kDp, R, 2, ks, 1, 1};
             EpiWgradT e{dblk + L.oW2, L.H, (long)L.blk, L.D, ks > 1};
-            MHE_TRY((gemm<true, true, true, false>(a1, dpreK, s, e, wstream2, "tc wgrad W2")));
+            MHE_TRY((gemm<true, true, false>(a1, dpreK, s, e, wstream2, "tc wgrad W2")));
         }
         if (fork) {
             MHE_TRY(cuda_ok(cudaEventRecord(aux.done[0][step], wstream), "join wgrad"));

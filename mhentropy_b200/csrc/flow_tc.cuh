@@ -9,28 +9,31 @@ constexpr int kDp = 64;   // flow dimension padded to one 64-wide K block / N ti
 
 inline bool supported(const FlowLayout& L) { return L.D <= kDp && L.H % 64 == 0 && L.C % 8 == 0; }
 
-// packed split-bf16 weights: w0 [L*2][2][H][64], w1 [L*2][2][H][H], w2 [L*2][2][64][H], cw [L*4][2][H][C]
+// packed split weights, once as half planes (forward GEMMs) and once as bfloat16 planes (backward GEMMs; A and B of one MMA
+// must share a format): w0 [L*2][2][H][64], w1 [L*2][2][H][H], w2 [L*2][2][64][H], cw [L*4][2][H][C]
 struct Packed {
-    __nv_bfloat16 *w0, *w1, *w2, *cw;
+    __nv_bfloat16 *w0, *w1, *w2, *cw;       // half planes
+    __nv_bfloat16 *w0b, *w1b, *w2b, *cwb;   // bfloat16 planes
     static size_t elems(const FlowLayout& L) {
-        return (size_t)L.L * 2 * 2 * ((size_t)L.H * kDp * 2 + (size_t)L.H * L.H) + (size_t)L.L * 4 * 2 * L.H * L.C + 4 * 512;
+        return 2 * ((size_t)L.L * 2 * 2 * ((size_t)L.H * kDp * 2 + (size_t)L.H * L.H) + (size_t)L.L * 4 * 2 * L.H * L.C) + 8 * 512;
     }
     Packed(const FlowLayout& L, __nv_bfloat16* base) {
         auto take = [&](size_t n) { __nv_bfloat16* p = base; base += (n + 511) / 512 * 512; return p; };
-        w0 = take((size_t)L.L * 2 * 2 * L.H * kDp);
-        w1 = take((size_t)L.L * 2 * 2 * L.H * L.H);
-        w2 = take((size_t)L.L * 2 * 2 * kDp * L.H);
-        cw = take((size_t)L.L * 4 * 2 * L.H * L.C);
+        w0 = take((size_t)L.L * 2 * 2 * L.H * kDp); w1 = take((size_t)L.L * 2 * 2 * L.H * L.H);
+        w2 = take((size_t)L.L * 2 * 2 * kDp * L.H); cw = take((size_t)L.L * 4 * 2 * L.H * L.C);
+        w0b = take((size_t)L.L * 2 * 2 * L.H * kDp); w1b = take((size_t)L.L * 2 * 2 * L.H * L.H);
+        w2b = take((size_t)L.L * 2 * 2 * kDp * L.H); cwb = take((size_t)L.L * 4 * 2 * L.H * L.C);
     }
 };
 
 // per-pass scratch: activations as planes, small fp32 buffers
 struct Ws {
     __nv_bfloat16 *xm, *a0, *a1, *dh0[2], *dh1[2], *dprep[2];   // gradient planes are double-buffered by layer parity:
-    float *st, *dpre, *gx;                                        // the weight-gradient GEMMs of a layer run on a side stream
+    __nv_bfloat16 *a0b, *a1b, *xmb;                              // the weight-gradient GEMMs of a layer run on side streams,
+    float *st, *dpre, *gx;                                        // on bfloat16 re-planed copies of the saved activations
     static size_t bytes(const FlowLayout& L, int R) {
         const size_t act = (size_t)2 * 2 * R * L.H * 2, small = (size_t)2 * 2 * R * kDp * 2;
-        return 6 * act + 4 * small + ((size_t)5 * R * L.D) * 4 + 32 * 1024;
+        return 8 * act + 5 * small + ((size_t)5 * R * L.D) * 4 + 48 * 1024;
     }
     Ws(void* base_, const FlowLayout& L, int R) {
         uint8_t* base = (uint8_t*)base_;
@@ -42,6 +45,7 @@ struct Ws {
             dh0[i] = (__nv_bfloat16*)take(act); dh1[i] = (__nv_bfloat16*)take(act);
             dprep[i] = (__nv_bfloat16*)take((size_t)2 * 2 * R * kDp * 2);
         }
+        a0b = (__nv_bfloat16*)take(act); a1b = (__nv_bfloat16*)take(act); xmb = (__nv_bfloat16*)take((size_t)2 * R * kDp * 2);
         st = (float*)take((size_t)2 * R * L.D * 4);
         dpre = (float*)take((size_t)2 * R * L.D * 4);
         gx = (float*)take((size_t)R * L.D * 4);

@@ -187,8 +187,8 @@ int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K,
     GemmShape g{M, N, K, batches, ksplit, 1, 1};
     EpiRawStore e{C, N, (long)M * N, 0, ksplit > 1};
     if (ksplit > 1 && cudaMemsetAsync(C, 0, (size_t)batches * M * N * sizeof(float), stream) != cudaSuccess) return MHE_ERR_CUDA;
-#define MHE_RAW(BN_, AMN_, BMN_, NP_) do { if (f16) return launch_tc_gemm<BN_, AMN_, BMN_, NP_, true, true>(ta, tb, g, e, stream, "tc raw"); \
-                                             return launch_tc_gemm<BN_, AMN_, BMN_, NP_, false, false>(ta, tb, g, e, stream, "tc raw"); } while (0)
+#define MHE_RAW(BN_, AMN_, BMN_, NP_) do { if (f16) return launch_tc_gemm<BN_, AMN_, BMN_, NP_, true>(ta, tb, g, e, stream, "tc raw"); \
+                                             return launch_tc_gemm<BN_, AMN_, BMN_, NP_, false>(ta, tb, g, e, stream, "tc raw"); } while (0)
 #define MHE_RAW_NP(BN_, AMN_, BMN_) do { if (planes == 1) MHE_RAW(BN_, AMN_, BMN_, 1); else MHE_RAW(BN_, AMN_, BMN_, 3); } while (0)
 #define MHE_RAW_MAJ(BN_) do { if (!a_mn && !b_mn) MHE_RAW_NP(BN_, false, false); else if (!a_mn && b_mn) MHE_RAW_NP(BN_, false, true); \
                               else if (a_mn && !b_mn) MHE_RAW_NP(BN_, true, false); else MHE_RAW_NP(BN_, true, true); } while (0)

@@ -151,7 +151,7 @@ struct SmemPlan {
 
 // C[batch] (M x N) = sum_pairs A_pa (M x K) * B_pb (K x N).  Epi::operator()(batch, split, row, col0, v[32], shape)
 // is called by every epilogue thread once per 32-column chunk with its accumulator row.
-template <int BN, bool A_MN, bool B_MN, int NPAIR, bool A_F16, bool B_F16, class Epi>
+template <int BN, bool A_MN, bool B_MN, int NPAIR, bool F16, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi) {
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
@@ -219,7 +219,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(BN, A_MN, B_MN, A_F16, B_F16);
+            constexpr uint32_t idesc = instr_desc(BN, A_MN, B_MN, F16, F16);   // A and B must share one format (mixing traps)
             // Descriptors differ between MMAs only in the 14-bit start address: build the constant part once and
             // add 16-byte-unit offsets, so the single issuing thread spends a few instructions per MMA.
             constexpr uint32_t kHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));          // SBO | version | SWIZZLE_128B
@@ -293,7 +293,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // launch helper: builds (cached) tensor maps and launches.  A: rows = M (K-major) or K (MN-major), etc.
 const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status);
 
-template <int BN, bool A_MN, bool B_MN, int NPAIR, bool A_F16, bool B_F16, class Epi>
+template <int BN, bool A_MN, bool B_MN, int NPAIR, bool F16, class Epi>
 inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const GemmShape& g, const Epi& epi, cudaStream_t stream, const char* what) {
     if (g.M <= 0 || g.N <= 0 || g.batches <= 0) return MHE_OK;
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
@@ -303,7 +303,7 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
     if (st != MHE_OK) return st;
     const CUtensorMap* mb = cached_map(B, B_MN ? 64 : BN, &st);
     if (st != MHE_OK) return st;
-    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, NPAIR, A_F16, B_F16, Epi>;
+    auto kern = tc_gemm_kernel<BN, A_MN, B_MN, NPAIR, F16, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes) != cudaSuccess) {
