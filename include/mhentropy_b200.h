@@ -80,7 +80,8 @@ size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s);
  *                    whenever the parameters change.  Needs dim <= 64, hidden % 64 == 0, cond % 8 == 0
  *                    (mhe_flow_packed_bytes() returns 0 otherwise).                                   */
 size_t mhe_flow_packed_bytes(mhe_flow_shape s);
-int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, void* stream);
+/* which: 1 = the half planes the forward GEMMs read, 2 = the bfloat16 planes the backward GEMMs read, 3 = both */
+int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, int which, void* stream);
 /* bytes of scratch needed by the flow passes over R rows (forward and backward) on the chosen path */
 size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core);
 /* bytes of the saved-for-backward block a forward pass over R rows fills: the layer inputs on the fp32 path (hidden

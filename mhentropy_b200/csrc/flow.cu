@@ -276,11 +276,11 @@ size_t mhe_flow_packed_bytes(mhe_flow_shape s) {
     return tcflow::supported(L) ? tcflow::Packed::elems(L) * 2 : 0;
 }
 
-int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, void* stream) {
-    MHE_REQUIRE(valid_shape(s) && params && packed, "pack_weights: bad args");
+int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, int which, void* stream) {
+    MHE_REQUIRE(valid_shape(s) && params && packed && which >= 1 && which <= 3, "pack_weights: bad args");
     FlowLayout L(s);
     if (!tcflow::supported(L)) { set_error("pack_weights: shape outside the tensor-core path (dim <= 64, hidden %% 64 == 0, cond %% 8 == 0)"); return MHE_ERR_UNSUPPORTED; }
-    return tcflow::pack_weights(L, params, packed, (cudaStream_t)stream);
+    return tcflow::pack_weights(L, params, packed, which, (cudaStream_t)stream);
 }
 
 int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* feat, int B, float* cp,

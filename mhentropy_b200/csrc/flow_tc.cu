@@ -32,7 +32,7 @@ __device__ __forceinline__ void store_planes32(bf16* hi_ptr, bf16* lo_ptr, const
 
 // ---- epilogues (one call per thread per 32-column chunk of its accumulator row) -----------------------
 struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[batch][plane][row][col]
-    static constexpr bool kDirect = true, kStaged = false;
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
     bf16* out; long ld; long plane_stride; long batch_stride;
     const float* cp; long cp_ld; long cp_off; long cp_bstride; int B;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
@@ -53,7 +53,7 @@ __device__ __forceinline__ float fast_tanh(float x) {   // 1 - 2/(e^{2x}+1); abs
     return 1.f - __fdividef(2.f, e + 1.f);
 }
 struct EpiOutHead {   // st[batch][row][col] = batch == 0 ? tanh(acc + b2) : acc + b2, col < D
-    static constexpr bool kDirect = false, kStaged = true;
+    static constexpr bool kDirect = false, kStaged = true, kRmw = false;
     float* out; int D; long batch_stride; const float* bias; long bias_bstride;
     __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
     __device__ void elem(int b, int, int row, int col, float v, const GemmShape&) const {
@@ -65,7 +65,7 @@ struct EpiOutHead {   // st[batch][row][col] = batch == 0 ? tanh(acc + b2) : acc
     }
 };
 struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes; dcp[row % B][...] += dh  (sum over the hypotheses of an image)
-    static constexpr bool kDirect = true, kStaged = true;
+    static constexpr bool kDirect = true, kStaged = true, kRmw = false;
     bf16* out; const bf16* act_hi; long ld; long plane_stride; long batch_stride; long act_plane_stride; long act_batch_stride;
     float* dcp; long cp_ld; long cp_off; long cp_bstride; int B;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
@@ -91,39 +91,43 @@ struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes; dcp[row % B][..
     }
 };
 struct EpiMaskAtomicAdd {   // gx[row][col] += mask[col] * acc, col < D
-    static constexpr bool kDirect = false, kStaged = true;
+    static constexpr bool kDirect = false, kStaged = true, kRmw = false;
     float* out; int D; const float* mask;
     __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
     __device__ void elem(int, int, int row, int col, float v, const GemmShape&) const {
         if (col < D) { const float w = __ldg(mask + col); if (w != 0.f) atomicAdd(out + (long)row * D + col, w * v); }
     }
 };
-struct EpiWgrad {   // dW[batch][row][col] (+)= acc, col < ncols
-    static constexpr bool kDirect = false, kStaged = true;
+struct EpiWgrad {   // dW[batch][row][col] += acc, col < ncols  (staged: lanes along the columns; loads batched before stores)
+    static constexpr bool kDirect = false, kStaged = true, kRmw = true;
     float* dW; long ld; long batch_stride; int ncols; int atomic;
     __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
-    __device__ void elem(int b, int, int row, int col, float v, const GemmShape&) const {
-        if (col < ncols) {
-            float* p = dW + (long)b * batch_stride + (long)row * ld + col;
-            if (atomic) atomicAdd(p, v); else *p += v;
-        }
+    __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
+    __device__ float* rmw_ptr(int b, int row0, int col, long& stride) const {
+        stride = ld;
+        return col < ncols ? dW + (long)b * batch_stride + (long)row0 * ld + col : nullptr;
     }
 };
 struct EpiWgradT {   // element (row, col) goes to dW[batch][col][row]: lanes = rows are already contiguous in memory
-    static constexpr bool kDirect = true, kStaged = false;
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
     float* dW; long ld; long batch_stride; int ncols; int atomic;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
         float* base = dW + (long)b * batch_stride + row;
+        if (atomic) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < ncols) { float* p = base + (long)col * ld; if (atomic) atomicAdd(p, v[j]); else *p += v[j]; }
+            for (int j = 0; j < 32; ++j) if (col0 + j < ncols) atomicAdd(base + (long)(col0 + j) * ld, v[j]);
+            return;
         }
+        float old[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) old[j] = (col0 + j < ncols) ? base[(long)(col0 + j) * ld] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < ncols) base[(long)(col0 + j) * ld] = old[j] + v[j];
     }
     __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
 };
 struct EpiCondFwd {   // cp[row][idx*H + col] = acc + Cb[idx][col] + b_j[col]
-    static constexpr bool kDirect = true, kStaged = false;
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
     float* cp; long cp_ld; int H; const float* params; size_t cb_base, cb_stride, blk, ob0, ob1;
     __device__ void operator()(int idx, int, int row, int col0, float* v, const GemmShape&) const {
         const float* cb = params + cb_base + (size_t)idx * cb_stride + col0;
@@ -137,7 +141,7 @@ struct EpiCondFwd {   // cp[row][idx*H + col] = acc + Cb[idx][col] + b_j[col]
     __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
 };
 struct EpiAtomicRows {   // C[row][col] += acc (every batch lands on the same output)
-    static constexpr bool kDirect = false, kStaged = true;
+    static constexpr bool kDirect = false, kStaged = true, kRmw = false;
     float* C; long ld; int ncols;
     __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
     __device__ void elem(int, int, int row, int col, float v, const GemmShape&) const {
@@ -296,17 +300,21 @@ static Aux& aux_ctx() {
 }
 
 // ---- packed weights -----------------------------------------------------------------------------------
-int pack_weights(const FlowLayout& L, const float* params, void* packed, cudaStream_t stream) {
+int pack_weights(const FlowLayout& L, const float* params, void* packed, int which, cudaStream_t stream) {
     Packed P(L, (bf16*)packed);
     // W0 [H][D] -> [H][64]; W1 [H][H]; W2 [D][H] -> [64][H]; Cw [H][C]
-    MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0, L.H, kDp, 2, L.L * 2, true, stream));
-    MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, true, stream));
-    MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, true, stream));
-    MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cw, L.H, L.C, 2, L.L * 4, true, stream));
-    MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0b, L.H, kDp, 2, L.L * 2, false, stream));
-    MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1b, L.H, L.H, 2, L.L * 2, false, stream));
-    MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2b, kDp, L.H, 2, L.L * 2, false, stream));
-    MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cwb, L.H, L.C, 2, L.L * 4, false, stream));
+    if (which & 1) {   // half planes: forward GEMMs
+        MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cw, L.H, L.C, 2, L.L * 4, true, stream));
+        MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0, L.H, kDp, 2, L.L * 2, true, stream));
+        MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, true, stream));
+        MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, true, stream));
+    }
+    if (which & 2) {   // bfloat16 planes: backward GEMMs
+        MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0b, L.H, kDp, 2, L.L * 2, false, stream));
+        MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1b, L.H, L.H, 2, L.L * 2, false, stream));
+        MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2b, kDp, L.H, 2, L.L * 2, false, stream));
+        MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cwb, L.H, L.C, 2, L.L * 4, false, stream));
+    }
     return MHE_OK;
 }
 

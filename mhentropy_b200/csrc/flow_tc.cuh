@@ -82,7 +82,7 @@ inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
     return ((size_t)2 * B * L.C + 512 + (size_t)2 * B * L.L * 4 * L.H) * 2 + 4096;
 }
 
-int pack_weights(const FlowLayout& L, const float* params, void* packed, cudaStream_t stream);
+int pack_weights(const FlowLayout& L, const float* params, void* packed, int which, cudaStream_t stream);
 int cond_fwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, int B, float* cp, void* ws, cudaStream_t stream);
 int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, const float* dcp, int B, float* dparams,
              float* dfeat, void* ws, cudaStream_t stream);

@@ -140,7 +140,7 @@ int split_planes(const float* src, long src_ld, long src_batch, int rows, int co
 }
 
 struct EpiRawStore {   // C[batch][row][col] = acc  (+= when accumulate; atomic when K is split)
-    static constexpr bool kDirect = true, kStaged = false;
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
     float* C; long ldc; long strideC; int accumulate; int atomic;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape& g) const {
         float* p = C + (long)b * strideC + (long)row * ldc + col0;

@@ -277,8 +277,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 __syncwarp();
                 const int col = n0 + c0 + lane;
                 const int rows = min(32, g.M - (m0 + q * 32));
-                if (col < g.N)
-                    for (int rr = 0; rr < rows; ++rr) epi.elem(batch, split, m0 + q * 32 + rr, col, st[rr][lane], g);
+                if constexpr (Epi::kRmw) {
+                    // C += acc with every load issued before the first store: a naive `*p += v` loop serialises on
+                    // possible aliasing and pays one memory round trip per row
+                    long stride;
+                    float* p0 = epi.rmw_ptr(batch, m0 + q * 32, col, stride);
+                    if (p0 && rows > 0) {
+                        if (epi.atomic) {
+                            for (int rr = 0; rr < rows; ++rr) atomicAdd(p0 + rr * stride, st[rr][lane]);
+                        } else {
+                            float old[32];
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) old[rr] = rr < rows ? p0[rr * stride] : 0.f;
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) if (rr < rows) p0[rr * stride] = old[rr] + st[rr][lane];
+                        }
+                    }
+                } else {
+                    if (col < g.N)
+                        for (int rr = 0; rr < rows; ++rr) epi.elem(batch, split, m0 + q * 32 + rr, col, st[rr][lane], g);
+                }
                 __syncwarp();
             }
         }

@@ -53,6 +53,7 @@ class TrainStep:
         self.cws = torch.empty(max(self.cws_bytes, 16), dtype=torch.uint8, device=dev)
         self.ws_bytes = max(L.mhe_flow_workspace_bytes(self.shape, R, int(self.tc)), L.mhe_mano_workspace_bytes(R, 0))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.side = torch.cuda.Stream(self.dev)
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None
@@ -65,8 +66,15 @@ class TrainStep:
         theta, beta = z.data_ptr(), z.data_ptr() + 48 * 4
         pk, cws, cwsb = ptr(self.packed), ptr(self.cws), self.cws_bytes
         # ---- forward
-        if self.tc:   # weights change between steps: refresh their split-bf16 planes inside the step
-            check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, s), 'pack_weights')
+        if self.tc:   # weights change between steps: refresh their split planes inside the step.  The bfloat16 copies are
+            # only read by the backward, so they are produced on a side stream while the forward runs.
+            main = torch.cuda.current_stream(self.dev)
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 2, _lib.stream_ptr(self.dev)), 'pack_weights')
+                self.dflat.zero_()
+                self.dcp.zero_()
+            check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 1, s), 'pack_weights')
         check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
         check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
                                   ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
@@ -77,8 +85,11 @@ class TrainStep:
                                     ptr(self.uv), ptr(self.row_lp), ptr(self.log_p), ptr(self.h), ptr(self.qlp), ptr(self.loss), s),
               'reproj_loss_fwd')
         # ---- backward (dloss = 1)
-        self.dflat.zero_()
-        self.dcp.zero_()
+        if self.tc:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+        else:
+            self.dflat.zero_()
+            self.dcp.zero_()
         check(L.mhe_reproj_loss_bwd(self.cfg, ptr(self.jtr), ptr(z), ptr(self.crop_uv), ptr(self.vis), R, B, None, None,
                                     ptr(self.djtr), ptr(self.dz), ptr(self.dlog_q), s), 'reproj_loss_bwd')
         dz = self.dz.data_ptr()

@@ -274,7 +274,7 @@ class RealNVP(nn.Module):
                 raise _lib.MheError('this flow shape is outside the tensor-core path; set precision="fp32"')
             if self._packed is None or self._packed.device != flat.device:
                 self._packed = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
-            check(lib().mhe_flow_pack_weights(self._shape, ptr(flat), ptr(self._packed), stream_ptr(flat.device)), 'mhe_flow_pack_weights')
+            check(lib().mhe_flow_pack_weights(self._shape, ptr(flat), ptr(self._packed), 3, stream_ptr(flat.device)), 'mhe_flow_pack_weights')
             self._packed_sig = sig
         return self._packed
 

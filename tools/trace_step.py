@@ -24,14 +24,16 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         eng.run()
     torch.cuda.synchronize()
-evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-rows = sorted(((e.time_range.start, e.time_range.end - e.time_range.start, e.name) for e in evs), key=lambda r: r[0])
+prof.export_chrome_trace('gpurun_out/trace_step.json')
+tr = json.load(open('gpurun_out/trace_step.json'))
+evs = [e for e in tr['traceEvents'] if e.get('cat') in ('kernel', 'gpu_memset', 'gpu_memcpy')]
+evs.sort(key=lambda e: e['ts'])
 os.makedirs('gpurun_out', exist_ok=True)
 with open('gpurun_out/trace_step.csv', 'w') as fh:
-    fh.write('start_us,dur_us,name\n')
-    for st, du, nm in rows:
-        fh.write(f'{st:.3f},{du:.3f},"{nm[:120]}"\n')
-if rows:
-    t0, t1 = rows[0][0], max(r[0] + r[1] for r in rows)
-    busy = sum(r[1] for r in rows)
-    print(f'kernels {len(rows)} span {(t1 - t0) / 3:.1f} us/step, sum of kernel durations {busy / 3:.1f} us/step')
+    fh.write('start_us,dur_us,stream,name\n')
+    for e in evs:
+        fh.write(f"{e['ts']:.3f},{e['dur']:.3f},{e['args'].get('stream', -1)},\"{e['name'][:110]}\"\n")
+os.remove('gpurun_out/trace_step.json')
+if evs:
+    t0, t1 = evs[0]['ts'], max(e['ts'] + e['dur'] for e in evs)
+    print(f'kernels {len(evs)} span {(t1 - t0) / 3:.1f} us/step')
