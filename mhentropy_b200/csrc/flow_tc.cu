@@ -189,7 +189,9 @@ __global__ void coupling_fwd_kernel(const float* __restrict__ x, const float* __
 }
 
 // coupling backward (see flow.cu) + split planes of the head gradients [2 nets][2 planes][R][64] + the bias
-// gradient db2 += colsum(dpre).  Block = 4 row slots x 64 columns, 32 rows per block.
+// gradient db2 += colsum(dpre).  Block = 4 row slots x 64 columns, kCbRows rows per block (few rows per thread: the loop
+// is a chain of dependent memory round trips).
+constexpr int kCbRows = 8;
 __global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restrict__ x, const float* __restrict__ st, const float* __restrict__ mask,
                                     const float* g, const float* __restrict__ gl, float gl_scale, int R, int D, int direction,
                                     bf16* __restrict__ dprep, float* gx, float* __restrict__ db2, long db2_stride) {
@@ -200,8 +202,8 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restri
     const long ps = (long)R * kDp;
     const float m = d < D ? mask[d] : 1.f;
     float sds = 0.f, sdt = 0.f;
-    for (int rr = slot; rr < 32; rr += 4) {
-        const int r = blockIdx.x * 32 + rr;
+    for (int rr = slot; rr < kCbRows; rr += 4) {
+        const int r = blockIdx.x * kCbRows + rr;
         if (r >= R) break;
         float ds = 0.f, dt = 0.f;
         if (d < D) {
@@ -447,7 +449,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
             MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0][step + 2], 0), "wait wgrad"));
             MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[1][step + 2], 0), "wait wgrad"));
         }
-        MHE_TRY(cuda_ok(launch_chain(coupling_bwd_kernel, dim3(cdiv(R, 32)), dim3(256), 0, stream, (const float*)S.x(step), (const float*)S.st(step), mrow,
+        MHE_TRY(cuda_ok(launch_chain(coupling_bwd_kernel, dim3(cdiv(R, kCbRows)), dim3(256), 0, stream, (const float*)S.x(step), (const float*)S.st(step), mrow,
                                      g, dlogdet, dlogdet_scale, R, L.D, direction, ws.dprep[pb], gx, dblk + L.ob2, (long)L.blk), "tc coupling bwd"));
         MHE_TRY(check_launch("tc coupling bwd"));
         PlaneTensor dpreK = pt(ws.dprep[pb], kDp, R, kDp, RD, 2, 2 * RD);

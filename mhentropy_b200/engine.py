@@ -54,6 +54,10 @@ class TrainStep:
         self.ws_bytes = max(L.mhe_flow_workspace_bytes(self.shape, R, int(self.tc)), L.mhe_mano_workspace_bytes(R, 0))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.side = torch.cuda.Stream(self.dev)
+        self.side2 = torch.cuda.Stream(self.dev)
+        self.jtr_mesh = f(R, 21, 3)
+        self.mws_bytes = L.mhe_mano_workspace_bytes(R, 0)
+        self.mws = torch.empty(self.mws_bytes, dtype=torch.uint8, device=dev)
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None
@@ -80,7 +84,15 @@ class TrainStep:
                                   ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
         check(L.mhe_std_normal_logp_fwd(ptr(self.z0), ptr(self.logdet), -1.0, R, shape.dim, ptr(self.log_q), s), 'log_q')
         check(L.mhe_combine_z_fwd(ptr(self.x), ptr(self.z_det), R, B, ptr(z), s), 'combine_z')
-        check(L.mhe_mano_fwd(self.consts, theta, 61, beta, 61, R, 1, ptr(self.verts), ptr(self.jtr), None, ws, wsb, s), 'mano_fwd')
+        # joints (chain + the five tip vertices) feed the loss: one kernel on the main stream.  The 778-vertex mesh is an
+        # output nothing downstream reads, so it is skinned on the side stream while the loss and the backward run.
+        check(L.mhe_mano_fwd(self.consts, theta, 61, beta, 61, R, 1, None, ptr(self.jtr), None, ws, wsb, s), 'mano_fwd')
+        if self.verts is not None:
+            main = torch.cuda.current_stream(self.dev)
+            self.side2.wait_stream(main)
+            with torch.cuda.stream(self.side2):
+                check(L.mhe_mano_fwd(self.consts, theta, 61, beta, 61, R, 1, ptr(self.verts), ptr(self.jtr_mesh), None, ptr(self.mws),
+                                     self.mws_bytes, _lib.stream_ptr(self.dev)), 'mano_fwd mesh')
         check(L.mhe_reproj_loss_fwd(self.cfg, ptr(self.jtr), ptr(z), ptr(self.crop_uv), ptr(self.vis), ptr(self.log_q), R, B,
                                     ptr(self.uv), ptr(self.row_lp), ptr(self.log_p), ptr(self.h), ptr(self.qlp), ptr(self.loss), s),
               'reproj_loss_fwd')
@@ -101,6 +113,7 @@ class TrainStep:
                                   ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
         check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), pk, ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat),
                                   cws, cwsb, s), 'cond_bwd')
+        torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
 
     def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
         """Copy one batch (host or device tensors) into the static input buffers."""
