@@ -6,6 +6,7 @@
 // The backward recomputes a0/a1 from the saved layer input instead of storing them.
 #include "gemm_simt.cuh"
 #include "flow_tc.cuh"
+#include "flow_fused.cuh"
 
 namespace mhe {
 
@@ -253,7 +254,12 @@ size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s) { return (size_t)s.layers 
 size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core) {
     if (!valid_shape(s) || R < 0) return 0;
     FlowLayout L(s);
-    if (tensor_core) return tcflow::supported(L) ? tcflow::Ws::bytes(L, R) : 0;
+    if (tensor_core) {
+        if (!tcflow::supported(L)) return 0;
+        size_t n = tcflow::Ws::bytes(L, R);
+        if (fused::supported(L, R)) n = n > fused::FWs::bytes(L, R) ? n : fused::FWs::bytes(L, R);
+        return n;
+    }
     return FlowWs::floats(L, R) * sizeof(float);
 }
 
@@ -347,7 +353,9 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed,
     cudaStream_t stream = (cudaStream_t)stream_;
     if (packed) {
         if (!tcflow::supported(L)) { set_error("pass_fwd: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
-        if (workspace_bytes < tcflow::Ws::bytes(L, R)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 1)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        if (!saved && fused::supported(L, R))
+            return fused::pass_fwd(L, params, packed, mask, cp, in, R, B, direction, out, logdet, saved, workspace, stream);
         return tcflow::pass_fwd(L, params, packed, mask, cp, in, R, B, direction, out, logdet, saved, workspace, stream);
     }
     if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 0)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
