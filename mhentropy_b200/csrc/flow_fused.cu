@@ -7,15 +7,20 @@ namespace fused {
 using namespace tc;
 typedef __nv_bfloat16 bf16;
 
-constexpr int kThreadsF = 192;                 // warps 0-3: workers (epilogues, coupling), warp 4: TMA producer, warp 5: MMA issuer
-constexpr int kSlots = 3;
-constexpr int kSlotA = 16384;                  // one plane of an A block: [128][64] 16-bit
-constexpr int kSlotB = 8192;                   // one plane of a B block: [64][64] 16-bit
-constexpr int kSlotBytes = 2 * kSlotA + 2 * kSlotB;   // 48 KB
-constexpr int kXaBytes = 32768;                // xm planes (2 x 8 KB) or a1 planes (2 x 16 KB)
-constexpr int kXs = 65;                        // row stride of the fp32 x tile (odd: conflict-free column walks)
-constexpr int kSmemBytes = kSlots * kSlotBytes + kXaBytes + NT * kXs * 4 + 1024 /*align*/ + 512 /*barriers, logdet*/;
-constexpr int kTmemCols = 256;                 // acc0 [0,64) acc1 [64,128) acc2 [128,192)
+constexpr int kWorkers = 256;                  // warps 0-7: epilogues + coupling (warp w: TMEM lane quadrant w % 4, column half w / 4)
+constexpr int kThreadsF = kWorkers + 96;       // warp 8: weight (A) producer, warp 9: activation (B) producer, warp 10: MMA issuer
+constexpr int kASlots = 4;
+constexpr int kABytes = 32768;                 // A block, both planes: 2 x [128][64] 16-bit
+constexpr int kAPlane = 16384;
+constexpr int kBSlots = 3;
+constexpr int kBBytes = 16384;                 // B block, both planes: 2 x [64][64] 16-bit
+constexpr int kBPlane = 8192;
+constexpr int kXaBytes = 32768;                // xm planes (2 x 8 KB) / a0, a1 slice planes (2 x 16 KB) / partial staging
+constexpr int kXs = 49;                        // row stride of the fp32 x tile (odd: conflict-free column walks)
+constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + kXaBytes + NT * kXs * 4 + 1024 /*align*/;
+constexpr int kTmemCols = 512;                 // three accumulators of 128 columns: [0,64) = Ah.Bh + Al.Bh, [64,128) = Ah.Bl (summed in the epilogue)
+constexpr int kAcc0 = 0, kAcc1 = 128, kAcc2 = 256;
+constexpr int kPartRows = 24;                  // active dims per layer (<= 23), padded
 
 bool supported(const FlowLayout& L, int R) {
     static int max_rows = -1;
@@ -23,7 +28,7 @@ bool supported(const FlowLayout& L, int R) {
         const char* e = getenv("MHE_FUSED_MAX_ROWS");
         max_rows = e ? atoi(e) : 4096;
     }
-    return L.D <= 64 && L.H == 512 && L.C % 8 == 0 && R <= max_rows;
+    return L.D <= 46 && L.D >= 4 && L.H == 512 && L.C % 8 == 0 && R <= max_rows;
 }
 
 // ---- cluster / barrier primitives -----------------------------------------------------------------------------
@@ -50,7 +55,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {   // 64 consecutive columns of this thread's lane
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -92,36 +106,55 @@ __device__ __forceinline__ float fast_tanh_f(float x) {   // 1 - 2/(e^{2x}+1); s
     return 1.f - __fdividef(2.f, e + 1.f);
 }
 
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define MHE_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[step * 64 + (slot)] = clock64(); } while (0)
+
 struct FwdArgs {
     const float* params; const float* mask; const float* cp; const float* in;
     float* out; float* logdet;
     float* saved_x; float* saved_st;           // NULL when nothing is saved
     bf16* a0T; bf16* a1T;                        // a0T: [(L or 1)][2][2][H][Rp]; a1T: saved only
     float* partial;
-    int R, Rp, B, D, H, L, direction, save, tiles;
+    long long* dbg;                               // optional phase timestamps of CTA 0 (MHE_FUSED_DEBUG)
+    int R, Rp, B, D, H, L, direction, save, tiles, two_mma;
     long cp_ld;
     size_t blk, ob2;
 };
 
-// MMA issue helpers: one 64-deep k-block = 4 UMMA_K steps x 3 plane pairs
+// MMA issue helper: one 64-deep k-block = 4 UMMA_K steps.  Split precision in TWO instructions per step instead of three:
+//   acc[:, 0:128] += A_hi . [B_hi | B_lo]   (N = 128: the two B planes are one operand, the planes b_plane bytes apart)
+//   acc[:, 0:64]  += A_lo . B_hi            (N = 64)
+// so A_hi is read from shared memory once, not twice (the MMAs are shared-memory-bandwidth bound at N = 64).
 //   K-major operand: +32 B per step; MN-major operand: +2048 B per step (descriptor units of 16 B)
 template <bool B_MN>
 __device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
-                                             uint32_t idesc, uint32_t& accumulate) {
+                                             uint32_t& accumulate, int two_mma) {
+    constexpr uint32_t idesc128 = instr_desc(2 * NT, false, B_MN, true, true), idesc64 = instr_desc(NT, false, B_MN, true, true);
     constexpr uint32_t kHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));   // SBO = 1024 | version 1 | SWIZZLE_128B
     constexpr uint32_t kLoA = (16u >> 4) << 16;                                    // K-major: LBO unused
-    constexpr uint32_t kLoB = B_MN ? ((8192u >> 4) << 16) : ((16u >> 4) << 16);
     constexpr uint32_t kStepB = B_MN ? (2048u >> 4) : (32u >> 4);
-    const uint32_t a0 = kLoA | (a_addr >> 4), b0 = kLoB | (b_addr >> 4);
-#pragma unroll
-    for (int pr = 0; pr < 3; ++pr) {   // (hi,hi) (hi,lo) (lo,hi)
-        const uint32_t a = a0 + (pr == 2 ? (a_plane >> 4) : 0u);
-        const uint32_t b = b0 + (pr == 1 ? (b_plane >> 4) : 0u);
+    // MN-major B: LBO = distance between the 64-column groups = between the hi and lo planes.  K-major B (xm): rows 64..127 of the
+    // N = 128 operand are the lo plane, which must sit 8 * 1024 B after the hi plane (b_plane == 8192).
+    const uint32_t kLoB = B_MN ? ((b_plane >> 4) << 16) : ((16u >> 4) << 16);
+    // In a cluster launch the 32-bit shared address carries the CTA rank in its high bits (shared::cluster window): keep only the
+    // 14-bit start-address field, or the rank lands in the LBO field of the descriptor.
+    const uint32_t a0 = kLoA | ((a_addr >> 4) & 0x3FFFu), a1 = a0 + (a_plane >> 4), b0 = kLoB | ((b_addr >> 4) & 0x3FFFu);
+    if (!two_mma) {   // reference schedule: three N = 64 passes (hi,hi) (hi,lo) (lo,hi) into columns [0,64)
+        const uint32_t b1 = b0 + (b_plane >> 4);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            umma_bf16_lohi(tmem_d, a + ks * 2u, b + ks * kStepB, kHi, idesc, accumulate);
+            umma_bf16_lohi(tmem_d, a0 + ks * 2u, b0 + ks * kStepB, kHi, idesc64, accumulate);
+            umma_bf16_lohi(tmem_d, a0 + ks * 2u, b1 + ks * kStepB, kHi, idesc64, 1u);
+            umma_bf16_lohi(tmem_d, a1 + ks * 2u, b0 + ks * kStepB, kHi, idesc64, 1u);
             accumulate = 1;
         }
+        return;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        umma_bf16_lohi(tmem_d, a0 + ks * 2u, b0 + ks * kStepB, kHi, idesc128, accumulate);
+        umma_bf16_lohi(tmem_d, a1 + ks * 2u, b0 + ks * kStepB, kHi, idesc64, 1u);
+        accumulate = 1;
     }
 }
 
@@ -129,24 +162,29 @@ __global__ void __launch_bounds__(kThreadsF, 1)
 flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
                       const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapA0, FwdArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc[3], bar_xm, bar_a1, bar_a0, bar_part;
+    __shared__ __align__(8) uint64_t bar_fullA[kASlots], bar_emptyA[kASlots], bar_fullB[kBSlots], bar_emptyB[kBSlots], bar_acc[3];
+    __shared__ __align__(8) uint64_t bar_xm, bar_own, bar_a1, bar_a0, bar_part;
     __shared__ uint32_t tmem_slot;
     __shared__ float lds[NT];
+    __shared__ uint64_t mbits[64];
 
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t ring = smem0, xa = smem0 + kSlots * kSlotBytes;
-    float* xs = reinterpret_cast<float*>(smem_raw + (smem0 - smem_u32(smem_raw)) + kSlots * kSlotBytes + kXaBytes);   // [NT][kXs]
+    const uint32_t ringA = smem0, ringB = ringA + kASlots * kABytes, xa = ringB + kBSlots * kBBytes;
+    float* xs = reinterpret_cast<float*>(smem_raw + (xa - smem_u32(smem_raw)) + kXaBytes);   // [NT][kXs]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int net = rank >> 2, j = rank & 3;
     const int tile = blockIdx.x / kCluster;
     const int r0 = tile * NT;
+    const int nkb = p.H / 64;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSlots; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < kASlots; ++s) { mbar_init(smem_u32(&bar_fullA[s]), 1); mbar_init(smem_u32(&bar_emptyA[s]), 1); }
+        for (int s = 0; s < kBSlots; ++s) { mbar_init(smem_u32(&bar_fullB[s]), 1); mbar_init(smem_u32(&bar_emptyB[s]), 1); }
         for (int s = 0; s < 3; ++s) mbar_init(smem_u32(&bar_acc[s]), 1);
-        mbar_init(smem_u32(&bar_xm), 128);
-        mbar_init(smem_u32(&bar_a1), 128);
+        mbar_init(smem_u32(&bar_xm), kWorkers);
+        mbar_init(smem_u32(&bar_a1), kWorkers);
+        mbar_init(smem_u32(&bar_own), 1);
         mbar_init(smem_u32(&bar_a0), 4);
         mbar_init(smem_u32(&bar_part), kCluster);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,7 +193,7 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     }
-    if (warp == 5) {
+    if (warp == 10) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -165,122 +203,164 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
     cluster_sync_all();            // every CTA's barriers are initialised before any remote arrival
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 4) {
-        // ===================== TMA producer =====================
+    if (warp == 8) {
+        // ===================== weight (A) producer: W0, W1 k-blocks (own two first), W2 — runs ahead by kASlots blocks
         if (lane == 0) {
-            uint32_t q = 0;        // job counter: slot = q % kSlots, use = q / kSlots
-            auto acquire = [&](uint32_t bytes) -> uint32_t {   // wait for the slot, arm its full barrier
-                const uint32_t s = q % kSlots, use = q / kSlots;
-                mbar_wait(smem_u32(&bar_empty[s]), (use & 1) ^ 1);
-                mbar_expect_tx(smem_u32(&bar_full[s]), bytes);
+            uint32_t q = 0;
+            auto acquire = [&]() -> uint32_t {
+                const uint32_t s = q % kASlots, use = q / kASlots;
+                mbar_wait(smem_u32(&bar_emptyA[s]), (use & 1) ^ 1);
+                mbar_expect_tx(smem_u32(&bar_fullA[s]), kABytes);
                 ++q;
                 return s;
             };
             for (int step = 0; step < p.L; ++step) {
                 const int layer = p.direction == 0 ? step : p.L - 1 - step;
-                const int wb = layer * 2 + net;                       // batch index into the packed weights
-                const int ab = (p.save ? step * 2 : 0) + net;         // batch index into a0T
-                {   // W0 slice [128][64], both planes
-                    const uint32_t s = acquire(2 * kSlotA), full = smem_u32(&bar_full[s]), base = ring + s * kSlotBytes;
+                const int wb = layer * 2 + net;
+                {   // W0 slice [128 features][64 dims]
+                    const uint32_t s = acquire(), full = smem_u32(&bar_fullA[s]), base = ringA + s * kABytes;
+                    MHE_STAMP(56);
                     tma_load_4d(base, &mapW0, full, 0, j * FS, 0, wb);
-                    tma_load_4d(base + kSlotA, &mapW0, full, 0, j * FS, 1, wb);
+                    tma_load_4d(base + kAPlane, &mapW0, full, 0, j * FS, 1, wb);
                 }
-                uint32_t slot_kb[2];
-                for (int kb = 0; kb < 2; ++kb) {   // weights of the first two k-blocks do not wait for the activations
-                    const uint32_t s = acquire(kSlotBytes), full = smem_u32(&bar_full[s]), base = ring + s * kSlotBytes;
-                    slot_kb[kb] = s;
+                for (int i = 0; i < nkb; ++i) {   // W1 [128 out features][64 in features], k-blocks starting at the CTA's own
+                    const int kb = (2 * j + i) % nkb;
+                    const uint32_t s = acquire(), full = smem_u32(&bar_fullA[s]), base = ringA + s * kABytes;
+                    MHE_STAMP(48 + i);
                     tma_load_4d(base, &mapW1, full, kb * 64, j * FS, 0, wb);
-                    tma_load_4d(base + kSlotA, &mapW1, full, kb * 64, j * FS, 1, wb);
+                    tma_load_4d(base + kAPlane, &mapW1, full, kb * 64, j * FS, 1, wb);
                 }
-                mbar_wait_cluster(smem_u32(&bar_a0), step & 1);       // the 4 slices of a0T are in global memory
-                fence_proxy_async();
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint32_t s = slot_kb[kb], full = smem_u32(&bar_full[s]), base = ring + s * kSlotBytes + 2 * kSlotA;
-                    tma_load_4d(base, &mapA0, full, r0, kb * 64, 0, ab);
-                    tma_load_4d(base + kSlotB, &mapA0, full, r0, kb * 64, 1, ab);
-                }
-                for (int kb = 2; kb < p.H / 64; ++kb) {
-                    const uint32_t s = acquire(kSlotBytes), full = smem_u32(&bar_full[s]), base = ring + s * kSlotBytes;
-                    tma_load_4d(base, &mapW1, full, kb * 64, j * FS, 0, wb);
-                    tma_load_4d(base + kSlotA, &mapW1, full, kb * 64, j * FS, 1, wb);
-                    tma_load_4d(base + 2 * kSlotA, &mapA0, full, r0, kb * 64, 0, ab);
-                    tma_load_4d(base + 2 * kSlotA + kSlotB, &mapA0, full, r0, kb * 64, 1, ab);
-                }
-                {   // W2 [64 d][128 feature slice] as two k-blocks per plane
-                    const uint32_t s = acquire(2 * kSlotA), full = smem_u32(&bar_full[s]), base = ring + s * kSlotBytes;
+                {   // W2 [64 dims][128 feature slice] as two k-blocks per plane
+                    const uint32_t s = acquire(), full = smem_u32(&bar_fullA[s]), base = ringA + s * kABytes;
+                    MHE_STAMP(57);
 #pragma unroll
                     for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk)
-                            tma_load_4d(base + pl * kSlotA + kk * 8192, &mapW2, full, j * FS + kk * 64, 0, pl, wb);
+                            tma_load_4d(base + pl * kAPlane + kk * 8192, &mapW2, full, j * FS + kk * 64, 0, pl, wb);
                 }
             }
         }
-    } else if (warp == 5) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 9) {
+        // ===================== activation (B) producer: the three peers' a0T k-blocks from the exchange buffer in global memory
         if (lane == 0) {
-            constexpr uint32_t idescK = instr_desc(NT, false, false, true, true);    // B K-major (xm)
-            constexpr uint32_t idescMN = instr_desc(NT, false, true, true, true);    // B MN-major (a0T blocks, a1T)
             uint32_t q = 0;
-            auto wait_full = [&]() -> uint32_t {
-                const uint32_t s = q % kSlots, use = q / kSlots;
-                mbar_wait(smem_u32(&bar_full[s]), use & 1);
-                ++q;
+            for (int step = 0; step < p.L; ++step) {
+                const int ab = (p.save ? step * 2 : 0) + net;
+                MHE_STAMP(16);
+                mbar_wait_cluster(smem_u32(&bar_a0), step & 1);       // all four slices of this net's a0T are in global memory
+                fence_proxy_async();
+                MHE_STAMP(17);
+                for (int i = 2; i < nkb; ++i) {
+                    const int kb = (2 * j + i) % nkb;
+                    const uint32_t s = q % kBSlots, use = q / kBSlots;
+                    ++q;
+                    mbar_wait(smem_u32(&bar_emptyB[s]), (use & 1) ^ 1);
+                    const uint32_t full = smem_u32(&bar_fullB[s]), base = ringB + s * kBBytes;
+                    mbar_expect_tx(full, kBBytes);
+                    tma_load_4d(base, &mapA0, full, r0, kb * 64, 0, ab);
+                    tma_load_4d(base + kBPlane, &mapA0, full, r0, kb * 64, 1, ab);
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            uint32_t qa = 0, qb = 0;
+            auto wait_a = [&]() -> uint32_t {
+                const uint32_t s = qa % kASlots, use = qa / kASlots;
+                mbar_wait(smem_u32(&bar_fullA[s]), use & 1);
+                ++qa;
                 return s;
             };
             for (int step = 0; step < p.L; ++step) {
                 const uint32_t par = step & 1;
-                {   // G0
-                    const uint32_t s = wait_full();
+                {   // G0: acc0 = W0 slice . xm^T
+                    const uint32_t s = wait_a();
+                    MHE_STAMP(20);
                     mbar_wait(smem_u32(&bar_xm), par);
                     tcgen05_fence_after();
+                    MHE_STAMP(21);
                     uint32_t acc = 0;
-                    issue_kblock<false>(tmem + 0, ring + s * kSlotBytes, kSlotA, xa, 8192, idescK, acc);
-                    tcgen05_commit(smem_u32(&bar_empty[s]));
+                    issue_kblock<false>(tmem + kAcc0, ringA + s * kABytes, kAPlane, xa, 8192, acc, p.two_mma & 1);
+                    tcgen05_commit(smem_u32(&bar_emptyA[s]));
                     tcgen05_commit(smem_u32(&bar_acc[0]));
                 }
-                {   // G1
+                {   // G1: acc1 = W1 slice . a0T — own two k-blocks straight from shared memory, the peers' through the B ring
                     uint32_t acc = 0;
-                    for (int kb = 0; kb < p.H / 64; ++kb) {
-                        const uint32_t s = wait_full();
-                        tcgen05_fence_after();
-                        const uint32_t base = ring + s * kSlotBytes;
-                        issue_kblock<true>(tmem + 64, base, kSlotA, base + 2 * kSlotA, kSlotB, idescMN, acc);
-                        tcgen05_commit(smem_u32(&bar_empty[s]));
+                    for (int i = 0; i < nkb; ++i) {
+                        const uint32_t s = wait_a();
+                        MHE_STAMP(32 + i);
+                        const uint32_t abase = ringA + s * kABytes;
+                        if (i < 2) {
+                            if (i == 0) { mbar_wait(smem_u32(&bar_own), par); MHE_STAMP(22); }
+                            tcgen05_fence_after();
+                            issue_kblock<true>(tmem + kAcc1, abase, kAPlane, xa + i * 16384, 8192, acc, p.two_mma & 2);
+                        } else {
+                            const uint32_t sb = qb % kBSlots, useb = qb / kBSlots;
+                            ++qb;
+                            mbar_wait(smem_u32(&bar_fullB[sb]), useb & 1);
+                            tcgen05_fence_after();
+                            MHE_STAMP(40 + i);
+                            issue_kblock<true>(tmem + kAcc1, abase, kAPlane, ringB + sb * kBBytes, kBPlane, acc, p.two_mma & 2);
+                            tcgen05_commit(smem_u32(&bar_emptyB[sb]));
+                        }
+                        tcgen05_commit(smem_u32(&bar_emptyA[s]));
                     }
                     tcgen05_commit(smem_u32(&bar_acc[1]));
                 }
-                {   // G2
-                    const uint32_t s = wait_full();
+                {   // G2: acc2 = W2[:, slice] . a1T slice (partial head outputs)
+                    const uint32_t s = wait_a();
+                    MHE_STAMP(24);
                     mbar_wait(smem_u32(&bar_a1), par);
                     tcgen05_fence_after();
+                    MHE_STAMP(25);
                     uint32_t acc = 0;
-                    const uint32_t base = ring + s * kSlotBytes;
-                    issue_kblock<true>(tmem + 128, base, kSlotA, xa, 16384, idescMN, acc);
-                    issue_kblock<true>(tmem + 128, base + 8192, kSlotA, xa + 8192, 16384, idescMN, acc);
-                    tcgen05_commit(smem_u32(&bar_empty[s]));
+                    const uint32_t base = ringA + s * kABytes;
+                    issue_kblock<true>(tmem + kAcc2, base, kAPlane, xa, 8192, acc, p.two_mma & 8);
+                    issue_kblock<true>(tmem + kAcc2, base + 8192, kAPlane, xa + 16384, 8192, acc, p.two_mma & 8);
+                    tcgen05_commit(smem_u32(&bar_emptyA[s]));
                     tcgen05_commit(smem_u32(&bar_acc[2]));
                 }
             }
         }
     } else {
-        // ===================== workers (128 threads) =====================
+        // ===================== workers (256 threads)
         const int t = threadIdx.x;
-        const int f = j * FS + t;                                  // feature inside the net (TMEM lane = t)
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const int lq = warp & 3, ch = warp >> 2;                   // TMEM lane quadrant, column half
+        const int fl = lq * 32 + lane;                             // feature inside the slice = TMEM lane
+        const int f = j * FS + fl;                                 // feature inside the net
+        const uint32_t tm_lane = (uint32_t)(lq * 32) << 16;
         const int D = p.D;
-        const int xn = t & 63, xh = t >> 6;                        // xm writer: row, half of the 64 padded dims
-        const int uq = t & 15, ug = t >> 4;                        // coupling: rows 4*uq.., dims ug + 8 i
+        const int xn = t & 63, xq = t >> 6;                        // xm writer: row, quarter of the 64 padded dims
+        const int uq = t & 15, ug = t >> 4;                        // coupling: rows 4*uq.., dims ug + 16 i
+        const uint32_t rowoff = (uint32_t)(fl >> 6) * 16384u + (uint32_t)(fl & 63) * 128u;  // k-row fl of the slice: [k-block][hi | lo][64 k-rows][128 B]
 
-        auto write_xm = [&](const float* mrow) {   // xm = mask * x as K-major split planes [64 rows][64 dims]
+        // one thread polls the mbarrier, the others block on the named barrier: 256 spinning threads would fight the tensor core for the
+        // shared-memory pipe while it streams MMA operands
+        auto worker_wait = [&](uint64_t* bar, uint32_t parity, bool cluster_scope) {
+            if (t == 0) { if (cluster_scope) mbar_wait_cluster(smem_u32(bar), parity); else mbar_wait(smem_u32(bar), parity); }
+            worker_sync();
+        };
+        // accumulator columns [col, col+32) of both halves (Ah.Bh + Al.Bh | Ah.Bl), summed
+        auto load_acc = [&](uint32_t acc_col, float* v, int both) {
+            float w[32];
+            tmem_ld32(tmem + tm_lane + acc_col + 32 * ch, v);
+            if (both) {
+                tmem_ld32(tmem + tm_lane + acc_col + 64 + 32 * ch, w);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int cc = xh * 4 + c;
+                for (int n = 0; n < 32; ++n) v[n] += w[n];
+            }
+        };
+        auto write_xm = [&](uint64_t mb) {   // xm = mask * x as K-major split planes [64 rows][64 dims]; lo plane 8 KB after hi
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int cc = xq * 2 + c;
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int d = cc * 8 + e;
-                    v[e] = (d < D && mrow) ? xs[xn * kXs + d] * __ldg(mrow + d) : 0.f;
+                    v[e] = (d < D && ((mb >> d) & 1)) ? xs[xn * kXs + d] : 0.f;
                 }
                 uint4 hi, lo;
                 split8<true>(v, hi, lo);
@@ -291,9 +371,35 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(smem_u32(&bar_xm));
         };
+        auto load_cp = [&](float* c, int which, int layer) {   // cp[image of row][layer, net, which][f] for this thread's 32 rows
+            const float* cpb = p.cp + (size_t)(layer * 4 + net * 2 + which) * p.H + f;
+            int img = (r0 + 32 * ch) % p.B;
+#pragma unroll
+            for (int n = 0; n < 32; ++n) { c[n] = __ldg(cpb + (size_t)img * p.cp_ld); if (++img == p.B) img = 0; }
+        };
+        // this thread's 32 activations -> its half of k-row fl of the MN-major slice planes in xa (and of the global planes)
+        auto store_slice = [&](const float* v, uint4* ghi, uint4* glo) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = ch * 4 + i;
+                uint4 hi, lo;
+                split8<true>(v + 8 * i, hi, lo);
+                const uint32_t off = rowoff + (uint32_t)((cc ^ (fl & 7)) << 4);
+                st_shared_v4(xa + off, hi);
+                st_shared_v4(xa + 8192 + off, lo);
+                if (ghi) { ghi[cc] = hi; glo[cc] = lo; }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        };
 
+        // coupling masks as bit sets (bit d = mask[layer][d] != 0)
+        if (t < p.L) {
+            uint64_t mb = 0;
+            for (int d = 0; d < D; ++d) mb |= (uint64_t)(p.mask[(size_t)t * D + d] != 0.f) << d;
+            mbits[t] = mb;
+        }
         // load the row tile
-        for (int i = t; i < NT * D; i += 128) {
+        for (int i = t; i < NT * D; i += kWorkers) {
             const int n = i / D, d = i - n * D;
             xs[n * kXs + d] = (r0 + n < p.R) ? p.in[(size_t)(r0 + n) * D + d] : 0.f;
         }
@@ -301,108 +407,109 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         worker_sync();
         if (p.save && rank == 0) {
             const int nvalid = min(NT, p.R - r0) * D;
-            for (int i = t; i < nvalid; i += 128) { const int n = i / D, d = i - n * D; p.saved_x[(size_t)r0 * D + i] = xs[n * kXs + d]; }
+            for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; p.saved_x[(size_t)r0 * D + i] = xs[n * kXs + d]; }
         }
-        write_xm(p.mask + (size_t)(p.direction == 0 ? 0 : p.L - 1) * D);
+        float v[32], c[32];
+        load_cp(c, 0, p.direction == 0 ? 0 : p.L - 1);
+        write_xm(mbits[p.direction == 0 ? 0 : p.L - 1]);
 
         for (int step = 0; step < p.L; ++step) {
             const int layer = p.direction == 0 ? step : p.L - 1 - step;
             const uint32_t par = step & 1;
-            const float* mrow = p.mask + (size_t)layer * D;
-            const size_t abatch = (size_t)((p.save ? step * 2 : 0) + net) * 2;   // plane index base into a0T / a1T
-            float v[64], c[64];
-            // ---------------- E0: a0 = lrelu(acc0 + cp0) -> global a0T (gathered by the net's CTAs)
+            const uint64_t mb = mbits[layer];
+            const int ab = (p.save ? step * 2 : 0) + net;           // batch index into a0T / a1T
+            // head biases of this thread's coupling dims (used in U; loaded now, off the critical path)
+            float bs3[3], bt3[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int d = min(ug + 16 * i, D - 1);
+                bs3[i] = __ldg(p.params + (size_t)(layer * 2 + 0) * p.blk + p.ob2 + d);
+                bt3[i] = __ldg(p.params + (size_t)(layer * 2 + 1) * p.blk + p.ob2 + d);
+            }
+            if (t == 0) { MHE_STAMP(0); if (p.dbg && blockIdx.x == 0) p.dbg[step * 64 + 60] = gtime(); }
+            // ---------------- E0: a0 = lrelu(acc0 + cp0) -> shared slice (own k-blocks of G1) + global exchange buffer (peers' k-blocks)
             {
-                const float* cpb = p.cp + (size_t)(layer * 4 + net * 2 + 0) * p.H + f;
-                int img = r0 % p.B;
-#pragma unroll
-                for (int n = 0; n < NT; ++n) { c[n] = __ldg(cpb + (size_t)img * p.cp_ld); if (++img == p.B) img = 0; }
-                mbar_wait(smem_u32(&bar_acc[0]), par);
+                worker_wait(&bar_acc[0], par, false);
                 tcgen05_fence_after();
-                tmem_ld64(tmem + lane_base + 0, v);
+                if (t == 0) MHE_STAMP(2);
+                load_acc(kAcc0, v, p.two_mma & 1);
 #pragma unroll
-                for (int n = 0; n < NT; ++n) v[n] = lrelu(v[n] + c[n]);
-                uint4* ghi = reinterpret_cast<uint4*>(p.a0T + ((abatch + 0) * p.H + f) * p.Rp + r0);
-                uint4* glo = reinterpret_cast<uint4*>(p.a0T + ((abatch + 1) * p.H + f) * p.Rp + r0);
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    uint4 hi, lo;
-                    split8<true>(v + 8 * cc, hi, lo);
-                    ghi[cc] = hi;
-                    glo[cc] = lo;
-                }
-                fence_proxy_async();
-                fence_cluster();
+                for (int n = 0; n < 32; ++n) v[n] = lrelu(v[n] + c[n]);
+                uint4* ghi = reinterpret_cast<uint4*>(p.a0T + (((size_t)ab * 2 + 0) * p.H + f) * p.Rp + r0);
+                uint4* glo = reinterpret_cast<uint4*>(p.a0T + (((size_t)ab * 2 + 1) * p.H + f) * p.Rp + r0);
+                store_slice(v, ghi, glo);
+                tcgen05_fence_before();
                 worker_sync();
-                if (t < 4) mbar_arrive_remote(smem_u32(&bar_a0), net * 4 + t);
+                if (t == 0) { MHE_STAMP(3); mbar_arrive(smem_u32(&bar_own)); }   // the MMA warp may consume the own slice
+                if (t < 4) {   // publish the slice: the CTA barrier ordered every thread's stores before this cumulative fence
+                    fence_proxy_async();
+                    fence_cluster();
+                    mbar_arrive_remote(smem_u32(&bar_a0), net * 4 + t);
+                    if (t == 0) MHE_STAMP(4);
+                }
+                load_cp(c, 1, layer);                                 // in flight while G1 runs
             }
             // ---------------- E1: a1 = lrelu(acc1 + cp1) -> shared (B operand of G2, MN-major) [+ global when saving]
             {
-                const float* cpb = p.cp + (size_t)(layer * 4 + net * 2 + 1) * p.H + f;
-                int img = r0 % p.B;
-#pragma unroll
-                for (int n = 0; n < NT; ++n) { c[n] = __ldg(cpb + (size_t)img * p.cp_ld); if (++img == p.B) img = 0; }
-                mbar_wait(smem_u32(&bar_acc[1]), par);
+                worker_wait(&bar_acc[1], par, false);
                 tcgen05_fence_after();
-                tmem_ld64(tmem + lane_base + 64, v);
+                if (t == 0) MHE_STAMP(6);
+                load_acc(kAcc1, v, p.two_mma & 2);
 #pragma unroll
-                for (int n = 0; n < NT; ++n) v[n] = lrelu(v[n] + c[n]);
-                uint4* ghi = p.save ? reinterpret_cast<uint4*>(p.a1T + ((abatch + 0) * p.H + f) * p.Rp + r0) : nullptr;
-                uint4* glo = p.save ? reinterpret_cast<uint4*>(p.a1T + ((abatch + 1) * p.H + f) * p.Rp + r0) : nullptr;
-                const uint32_t rowoff = (uint32_t)(t >> 6) * 8192u + (uint32_t)(t & 63) * 128u;   // k-row t of the MN-major tile
-#pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
-                    uint4 hi, lo;
-                    split8<true>(v + 8 * cc, hi, lo);
-                    const uint32_t off = rowoff + (uint32_t)((cc ^ (t & 7)) << 4);
-                    st_shared_v4(xa + off, hi);
-                    st_shared_v4(xa + 16384 + off, lo);
-                    if (ghi) { ghi[cc] = hi; glo[cc] = lo; }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                for (int n = 0; n < 32; ++n) v[n] = lrelu(v[n] + c[n]);
+                uint4* ghi = p.save ? reinterpret_cast<uint4*>(p.a1T + (((size_t)ab * 2 + 0) * p.H + f) * p.Rp + r0) : nullptr;
+                uint4* glo = p.save ? reinterpret_cast<uint4*>(p.a1T + (((size_t)ab * 2 + 1) * p.H + f) * p.Rp + r0) : nullptr;
+                store_slice(v, ghi, glo);
                 tcgen05_fence_before();
                 mbar_arrive(smem_u32(&bar_a1));
+                if (t == 0) MHE_STAMP(7);
             }
             // ---------------- E2: partial head outputs of this CTA's feature slice -> global exchange buffer
             {
-                mbar_wait(smem_u32(&bar_acc[2]), par);
+                worker_wait(&bar_acc[2], par, false);
                 tcgen05_fence_after();
-                if (warp < 2) {
-                    tmem_ld64(tmem + lane_base + 128, v);
-                    if (t < D && __ldg(mrow + t) == 0.f) {
-                        float4* dst = reinterpret_cast<float4*>(p.partial + ((((size_t)par * p.tiles + tile) * kCluster + rank) * kDp + t) * NT);
+                if (t == 0) MHE_STAMP(8);
+                if (lq < 2) {   // accumulator rows = flow dims: lanes 0..63
+                    load_acc(kAcc2, v, p.two_mma & 8);
+                    if (fl < D && !((mb >> fl) & 1)) {
+                        float4* dst = reinterpret_cast<float4*>(p.partial + ((((size_t)par * p.tiles + tile) * kCluster + rank) * kDp + fl) * NT + 32 * ch);
 #pragma unroll
-                        for (int i = 0; i < NT / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
                 }
-                fence_cluster();
                 tcgen05_fence_before();
                 worker_sync();
-                if (t < kCluster) mbar_arrive_remote(smem_u32(&bar_part), t);
+                if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
+                if (t == 0) MHE_STAMP(9);
             }
             // ---------------- U: sum the partials, affine coupling, next layer's masked input
             {
-                mbar_wait_cluster(smem_u32(&bar_part), par);
+                const bool last = step == p.L - 1;
+                const int next_layer = p.direction == 0 ? layer + 1 : layer - 1;
+                worker_wait(&bar_part, par, true);
+                if (t == 0) MHE_STAMP(10);
                 const float* pbase = p.partial + (((size_t)par * p.tiles + tile) * kCluster) * kDp * NT + uq * 4;
-                const float* b2s = p.params + (size_t)(layer * 2 + 0) * p.blk + p.ob2;
-                const float* b2t = p.params + (size_t)(layer * 2 + 1) * p.blk + p.ob2;
+                float4 pv[3][8];
+                bool act[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int d = ug + 16 * i;
+                    act[i] = d < D && !((mb >> d) & 1);
+#pragma unroll
+                    for (int cta = 0; cta < 8; ++cta)
+                        pv[i][cta] = act[i] ? __ldcg(reinterpret_cast<const float4*>(pbase + ((size_t)cta * kDp + d) * NT)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (!last) load_cp(c, 0, next_layer);                 // next layer's conditioning, in flight during the coupling
                 float ld4[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int d = ug; d < D; d += 8) {
-                    if (__ldg(mrow + d) != 0.f) continue;
-                    float4 acc[2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int cta = 0; cta < 4; ++cta) {
-                            const float4 q4 = __ldcg(reinterpret_cast<const float4*>(pbase + ((size_t)(h * 4 + cta) * kDp + d) * NT));
-                            s4.x += q4.x; s4.y += q4.y; s4.z += q4.z; s4.w += q4.w;
-                        }
-                        acc[h] = s4;
-                    }
-                    const float bs = __ldg(b2s + d), bt = __ldg(b2t + d);
-                    const float sv[4] = {acc[0].x + bs, acc[0].y + bs, acc[0].z + bs, acc[0].w + bs};
-                    const float tv[4] = {acc[1].x + bt, acc[1].y + bt, acc[1].z + bt, acc[1].w + bt};
+                for (int i = 0; i < 3; ++i) {
+                    if (!act[i]) continue;
+                    const int d = ug + 16 * i;
+                    const float bs = bs3[i], bt = bt3[i];
+                    const float sv[4] = {pv[i][0].x + pv[i][1].x + pv[i][2].x + pv[i][3].x + bs, pv[i][0].y + pv[i][1].y + pv[i][2].y + pv[i][3].y + bs,
+                                         pv[i][0].z + pv[i][1].z + pv[i][2].z + pv[i][3].z + bs, pv[i][0].w + pv[i][1].w + pv[i][2].w + pv[i][3].w + bs};
+                    const float tv[4] = {pv[i][4].x + pv[i][5].x + pv[i][6].x + pv[i][7].x + bt, pv[i][4].y + pv[i][5].y + pv[i][6].y + pv[i][7].y + bt,
+                                         pv[i][4].z + pv[i][5].z + pv[i][6].z + pv[i][7].z + bt, pv[i][4].w + pv[i][5].w + pv[i][6].w + pv[i][7].w + bt};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int n = uq * 4 + k;
@@ -412,27 +519,25 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                         if (p.direction == 0) { y = fmaf(xv, expf(s), tv[k]); ld4[k] += s; }
                         else { y = (xv - tv[k]) * expf(-s); ld4[k] -= s; }
                         xs[n * kXs + d] = y;
-                        if (p.save && (int)rank == ug && r0 + n < p.R) {
+                        if (p.save && (int)rank == (ug & 7) && r0 + n < p.R) {
                             p.saved_st[((size_t)(step * 2 + 0) * p.R + r0 + n) * D + d] = s;
                             p.saved_st[((size_t)(step * 2 + 1) * p.R + r0 + n) * D + d] = tv[k];
                         }
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) atomicAdd(&lds[uq * 4 + k], ld4[k]);
+                for (int k = 0; k < 4; ++k) if (ld4[k] != 0.f) atomicAdd(&lds[uq * 4 + k], ld4[k]);
                 worker_sync();
-                const bool last = step == p.L - 1;
+                if (t == 0) MHE_STAMP(11);
+                if (!last) write_xm(mbits[next_layer]);
                 if (p.save && (int)rank == ((step + 1) & 7)) {
                     const int nvalid = min(NT, p.R - r0) * D;
                     float* dst = p.saved_x + (size_t)(step + 1) * p.R * D + (size_t)r0 * D;
-                    for (int i = t; i < nvalid; i += 128) { const int n = i / D, d = i - n * D; dst[i] = xs[n * kXs + d]; }
+                    for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; dst[i] = xs[n * kXs + d]; }
                 }
-                if (!last) {
-                    const int next_layer = p.direction == 0 ? layer + 1 : layer - 1;
-                    write_xm(p.mask + (size_t)next_layer * D);
-                } else if (rank == 0) {
+                if (last && rank == 0) {
                     const int nvalid = min(NT, p.R - r0) * D;
-                    for (int i = t; i < nvalid; i += 128) { const int n = i / D, d = i - n * D; p.out[(size_t)r0 * D + i] = xs[n * kXs + d]; }
+                    for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; p.out[(size_t)r0 * D + i] = xs[n * kXs + d]; }
                     if (p.logdet && t < NT && r0 + t < p.R) p.logdet[r0 + t] = lds[t];
                 }
             }
@@ -442,10 +547,25 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
+long long* debug_buffer();
+
 // ---- host -----------------------------------------------------------------------------------------------------
+// MHE_FUSED_DEBUG=1: a small device buffer receives %globaltimer stamps of CTA 0's phases; read it with mhe_fused_debug_read
+static long long* g_dbg = nullptr;
+long long* debug_buffer() {
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* e = getenv("MHE_FUSED_DEBUG");
+        if (e && atoi(e) && cudaMalloc(&g_dbg, 64 * 64 * sizeof(long long)) == cudaSuccess) cudaMemset(g_dbg, 0, 64 * 64 * sizeof(long long));
+        else g_dbg = nullptr;
+    }
+    return g_dbg;
+}
+
 static PlaneTensor pt4(const bf16* base, int cols, int rows, int batches) {
     PlaneTensor t;
     t.base = base; t.cols = cols; t.rows = rows; t.planes = 2; t.batches = batches;
@@ -461,6 +581,8 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
     FwdArgs a{};
     a.params = params; a.mask = mask; a.cp = cp; a.in = in; a.out = out; a.logdet = logdet;
     a.partial = ws.partial;
+    { const char* e = getenv("MHE_FUSED_TWO_MMA"); a.two_mma = e ? atoi(e) : 15; }
+    a.dbg = debug_buffer();
     a.R = R; a.Rp = Rp; a.B = B; a.D = L.D; a.H = L.H; a.L = L.L; a.direction = direction; a.save = saved ? 1 : 0; a.tiles = tiles;
     a.cp_ld = (long)L.L * 4 * L.H; a.blk = L.blk; a.ob2 = L.ob2;
     if (saved) {
@@ -503,3 +625,9 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
 
 }  // namespace fused
 }  // namespace mhe
+
+extern "C" int mhe_fused_debug_read(long long* host, int n) {
+    if (!mhe::fused::g_dbg) return MHE_ERR_UNSUPPORTED;
+    if (n > 64 * 64) n = 64 * 64;
+    return cudaMemcpy(host, mhe::fused::g_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? MHE_OK : MHE_ERR_CUDA;
+}
