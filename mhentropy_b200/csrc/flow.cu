@@ -257,7 +257,10 @@ size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core) {
     if (tensor_core) {
         if (!tcflow::supported(L)) return 0;
         size_t n = tcflow::Ws::bytes(L, R);
-        if (fused::supported(L, R)) n = n > fused::FWs::bytes(L, R) ? n : fused::FWs::bytes(L, R);
+        if (fused::supported(L, R)) {
+            n = n > fused::FWs::bytes(L, R) ? n : fused::FWs::bytes(L, R);
+            n = n > fused::BWs::bytes(L, R) ? n : fused::BWs::bytes(L, R);
+        }
         return n;
     }
     return FlowWs::floats(L, R) * sizeof(float);
@@ -266,7 +269,10 @@ size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core) {
 size_t mhe_flow_saved_bytes(mhe_flow_shape s, int R, int tensor_core) {
     if (!valid_shape(s) || R < 0) return 0;
     FlowLayout L(s);
-    if (tensor_core) return tcflow::supported(L) ? tcflow::Saved::bytes(L, R) : 0;
+    if (tensor_core) {
+        if (!tcflow::supported(L)) return 0;
+        return fused::supported(L, R) ? fused::FSaved::bytes(L, R) : tcflow::Saved::bytes(L, R);
+    }
     return (size_t)(L.L + 1) * R * L.D * sizeof(float);
 }
 
@@ -354,7 +360,7 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed,
     if (packed) {
         if (!tcflow::supported(L)) { set_error("pass_fwd: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
         if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 1)) { set_error("pass_fwd: workspace too small"); return MHE_ERR_WORKSPACE; }
-        if (!saved && fused::supported(L, R))
+        if (fused::supported(L, R))
             return fused::pass_fwd(L, params, packed, mask, cp, in, R, B, direction, out, logdet, saved, workspace, stream);
         return tcflow::pass_fwd(L, params, packed, mask, cp, in, R, B, direction, out, logdet, saved, workspace, stream);
     }
@@ -396,7 +402,9 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
     cudaStream_t stream = (cudaStream_t)stream_;
     if (packed) {
         if (!tcflow::supported(L)) { set_error("pass_bwd: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
-        if (workspace_bytes < tcflow::Ws::bytes(L, R)) { set_error("pass_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 1)) { set_error("pass_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        if (fused::supported(L, R))
+            return fused::pass_bwd(L, params, packed, mask, saved, R, B, direction, dout, dlogdet, dlogdet_scale, din, dparams, dcp, workspace, stream);
         return tcflow::pass_bwd(L, params, packed, mask, cp, saved, R, B, direction, dout, dlogdet, dlogdet_scale, din, dparams, dcp, workspace, stream);
     }
     if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 0)) { set_error("pass_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }

@@ -126,14 +126,16 @@ struct FwdArgs {
 //   acc[:, 0:64]  += A_lo . B_hi            (N = 64)
 // so A_hi is read from shared memory once, not twice (the MMAs are shared-memory-bandwidth bound at N = 64).
 //   K-major operand: +32 B per step; MN-major operand: +2048 B per step (descriptor units of 16 B)
-template <bool B_MN>
+template <bool A_MN, bool B_MN, bool F16>
 __device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t a_plane, uint32_t b_addr, uint32_t b_plane,
                                              uint32_t& accumulate, int two_mma) {
-    constexpr uint32_t idesc128 = instr_desc(2 * NT, false, B_MN, true, true), idesc64 = instr_desc(NT, false, B_MN, true, true);
+    constexpr uint32_t idesc128 = instr_desc(2 * NT, A_MN, B_MN, F16, F16), idesc64 = instr_desc(NT, A_MN, B_MN, F16, F16);
     constexpr uint32_t kHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));   // SBO = 1024 | version 1 | SWIZZLE_128B
-    constexpr uint32_t kLoA = (16u >> 4) << 16;                                    // K-major: LBO unused
+    // MN-major A: two 64-row groups 8192 B apart (LBO), +2048 B per k-step; K-major A: LBO unused, +32 B per k-step
+    constexpr uint32_t kLoA = A_MN ? ((8192u >> 4) << 16) : ((16u >> 4) << 16);
+    constexpr uint32_t kStepA = A_MN ? (2048u >> 4) : (32u >> 4);
     constexpr uint32_t kStepB = B_MN ? (2048u >> 4) : (32u >> 4);
-    // MN-major B: LBO = distance between the 64-column groups = between the hi and lo planes.  K-major B (xm): rows 64..127 of the
+    // MN-major B: LBO = distance between the 64-column groups = between the hi and lo planes.  K-major B: rows 64..127 of the
     // N = 128 operand are the lo plane, which must sit 8 * 1024 B after the hi plane (b_plane == 8192).
     const uint32_t kLoB = B_MN ? ((b_plane >> 4) << 16) : ((16u >> 4) << 16);
     // In a cluster launch the 32-bit shared address carries the CTA rank in its high bits (shared::cluster window): keep only the
@@ -143,17 +145,17 @@ __device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_addr, u
         const uint32_t b1 = b0 + (b_plane >> 4);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            umma_bf16_lohi(tmem_d, a0 + ks * 2u, b0 + ks * kStepB, kHi, idesc64, accumulate);
-            umma_bf16_lohi(tmem_d, a0 + ks * 2u, b1 + ks * kStepB, kHi, idesc64, 1u);
-            umma_bf16_lohi(tmem_d, a1 + ks * 2u, b0 + ks * kStepB, kHi, idesc64, 1u);
+            umma_bf16_lohi(tmem_d, a0 + ks * kStepA, b0 + ks * kStepB, kHi, idesc64, accumulate);
+            umma_bf16_lohi(tmem_d, a0 + ks * kStepA, b1 + ks * kStepB, kHi, idesc64, 1u);
+            umma_bf16_lohi(tmem_d, a1 + ks * kStepA, b0 + ks * kStepB, kHi, idesc64, 1u);
             accumulate = 1;
         }
         return;
     }
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-        umma_bf16_lohi(tmem_d, a0 + ks * 2u, b0 + ks * kStepB, kHi, idesc128, accumulate);
-        umma_bf16_lohi(tmem_d, a1 + ks * 2u, b0 + ks * kStepB, kHi, idesc64, 1u);
+        umma_bf16_lohi(tmem_d, a0 + ks * kStepA, b0 + ks * kStepB, kHi, idesc128, accumulate);
+        umma_bf16_lohi(tmem_d, a1 + ks * kStepA, b0 + ks * kStepB, kHi, idesc64, 1u);
         accumulate = 1;
     }
 }
@@ -282,7 +284,7 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                     tcgen05_fence_after();
                     MHE_STAMP(21);
                     uint32_t acc = 0;
-                    issue_kblock<false>(tmem + kAcc0, ringA + s * kABytes, kAPlane, xa, 8192, acc, p.two_mma & 1);
+                    issue_kblock<false, false, true>(tmem + kAcc0, ringA + s * kABytes, kAPlane, xa, 8192, acc, p.two_mma & 1);
                     tcgen05_commit(smem_u32(&bar_emptyA[s]));
                     tcgen05_commit(smem_u32(&bar_acc[0]));
                 }
@@ -295,14 +297,14 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                         if (i < 2) {
                             if (i == 0) { mbar_wait(smem_u32(&bar_own), par); MHE_STAMP(22); }
                             tcgen05_fence_after();
-                            issue_kblock<true>(tmem + kAcc1, abase, kAPlane, xa + i * 16384, 8192, acc, p.two_mma & 2);
+                            issue_kblock<false, true, true>(tmem + kAcc1, abase, kAPlane, xa + i * 16384, 8192, acc, p.two_mma & 2);
                         } else {
                             const uint32_t sb = qb % kBSlots, useb = qb / kBSlots;
                             ++qb;
                             mbar_wait(smem_u32(&bar_fullB[sb]), useb & 1);
                             tcgen05_fence_after();
                             MHE_STAMP(40 + i);
-                            issue_kblock<true>(tmem + kAcc1, abase, kAPlane, ringB + sb * kBBytes, kBPlane, acc, p.two_mma & 2);
+                            issue_kblock<false, true, true>(tmem + kAcc1, abase, kAPlane, ringB + sb * kBBytes, kBPlane, acc, p.two_mma & 2);
                             tcgen05_commit(smem_u32(&bar_emptyB[sb]));
                         }
                         tcgen05_commit(smem_u32(&bar_emptyA[s]));
@@ -317,8 +319,8 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                     MHE_STAMP(25);
                     uint32_t acc = 0;
                     const uint32_t base = ringA + s * kABytes;
-                    issue_kblock<true>(tmem + kAcc2, base, kAPlane, xa, 8192, acc, p.two_mma & 8);
-                    issue_kblock<true>(tmem + kAcc2, base + 8192, kAPlane, xa + 16384, 8192, acc, p.two_mma & 8);
+                    issue_kblock<false, true, true>(tmem + kAcc2, base, kAPlane, xa, 8192, acc, p.two_mma & 8);
+                    issue_kblock<false, true, true>(tmem + kAcc2, base + 8192, kAPlane, xa + 16384, 8192, acc, p.two_mma & 8);
                     tcgen05_commit(smem_u32(&bar_emptyA[s]));
                     tcgen05_commit(smem_u32(&bar_acc[2]));
                 }
@@ -550,6 +552,390 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
     if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
+// =====================================================================================================================
+// Backward pass (data gradients) of all L layers for one row tile; same cluster mapping and exchange scheme as the forward.
+// Per layer (reverse order), with g = dL/d(layer output) held in shared memory:
+//   bU  coupling backward (reference flows.py:213-216 / 222-226 differentiated): dpre (head pre-activation gradient of the CTA's
+//       net) -> shared, K-major; direct path of dL/dx -> g in place
+//   bG2 dh1T[slice] = W2^T[slice, :] . dpre^T         then  * lrelu'(a1)   -> shared slice + global (exchange, weight gradients)
+//   bG1 dh0T[slice] = W1^T[slice, :] . dh1T           then  * lrelu'(a0)   -> shared slice + global (weight gradients)
+//   bG0 part[d]     = W0^T[:, slice] . dh0T[slice]    partial input gradients, summed by every CTA after the exchange
+//   g[n][d] += mask[d] * sum_c part_c[d][n]
+// Gradients travel as bfloat16 split planes (full fp32 range); the weights are read from their bfloat16 planes, MN-major.
+struct BwdArgs {
+    const float* mask; const float* saved_x; const float* saved_st;
+    const bf16* a0T; const bf16* a1T;           // saved half planes: only their signs are read here
+    const float* dout; const float* dlogdet; float dlogdet_scale;
+    float* din; float* dparams;
+    bf16* dh1T; bf16* dh0T; bf16* dpreT;        // [L][2 nets][2 planes][H][Rp] x2, [L][2][2][64][Rp]
+    float* partial;
+    long long* dbg;
+    int R, Rp, D, H, L, direction, tiles, two_mma;
+    size_t blk, ob2;
+};
+
+__global__ void __launch_bounds__(kThreadsF, 1)
+flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
+                      const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapDh1, BwdArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_fullA[kASlots], bar_emptyA[kASlots], bar_fullB[kBSlots], bar_emptyB[kBSlots], bar_acc[3];
+    __shared__ __align__(8) uint64_t bar_xm, bar_own, bar_a1, bar_a0, bar_part;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float gls[NT], db2s[kDp];
+    __shared__ uint64_t mbits[64];
+
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ringA = smem0, ringB = ringA + kASlots * kABytes, xa = ringB + kBSlots * kBBytes;
+    float* gs = reinterpret_cast<float*>(smem_raw + (xa - smem_u32(smem_raw)) + kXaBytes);   // [NT][kXs] gradient tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int net = rank >> 2, j = rank & 3;
+    const int tile = blockIdx.x / kCluster;
+    const int r0 = tile * NT;
+    const int nkb = p.H / 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kASlots; ++s) { mbar_init(smem_u32(&bar_fullA[s]), 1); mbar_init(smem_u32(&bar_emptyA[s]), 1); }
+        for (int s = 0; s < kBSlots; ++s) { mbar_init(smem_u32(&bar_fullB[s]), 1); mbar_init(smem_u32(&bar_emptyB[s]), 1); }
+        for (int s = 0; s < 3; ++s) mbar_init(smem_u32(&bar_acc[s]), 1);
+        mbar_init(smem_u32(&bar_xm), kWorkers);
+        mbar_init(smem_u32(&bar_a1), kWorkers);
+        mbar_init(smem_u32(&bar_own), 1);
+        mbar_init(smem_u32(&bar_a0), 4);
+        mbar_init(smem_u32(&bar_part), kCluster);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapDh1) : "memory");
+    }
+    if (warp == 10) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    cluster_sync_all();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 8) {
+        // ===================== weight (A) producer, all blocks MN-major: [64 k-rows][64 m-cols] boxes, two per plane
+        if (lane == 0) {
+            uint32_t q = 0;
+            auto acquire = [&]() -> uint32_t {
+                const uint32_t s = q % kASlots, use = q / kASlots;
+                mbar_wait(smem_u32(&bar_emptyA[s]), (use & 1) ^ 1);
+                mbar_expect_tx(smem_u32(&bar_fullA[s]), kABytes);
+                ++q;
+                return s;
+            };
+            for (int step = p.L - 1; step >= 0; --step) {
+                const int layer = p.direction == 0 ? step : p.L - 1 - step;
+                const int wb = layer * 2 + net;
+                {   // W2^T slice: k = flow dim (64 rows of W2), m = feature slice (two 64-column groups)
+                    const uint32_t s = acquire(), full = smem_u32(&bar_fullA[s]), base = ringA + s * kABytes;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) tma_load_4d(base + pl * kAPlane + g * 8192, &mapW2, full, j * FS + g * 64, 0, pl, wb);
+                }
+                for (int i = 0; i < nkb; ++i) {   // W1^T: k = out-feature block (rows of W1), m = in-feature slice
+                    const int kb = (2 * j + i) % nkb;
+                    const uint32_t s = acquire(), full = smem_u32(&bar_fullA[s]), base = ringA + s * kABytes;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) tma_load_4d(base + pl * kAPlane + g * 8192, &mapW1, full, j * FS + g * 64, kb * 64, pl, wb);
+                }
+                {   // W0^T: k = feature slice (two 64-row blocks of W0), m = flow dim (one 64-column group)
+                    const uint32_t s = acquire(), full = smem_u32(&bar_fullA[s]), base = ringA + s * kABytes;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) tma_load_4d(base + pl * kAPlane + kk * 8192, &mapW0, full, 0, j * FS + kk * 64, pl, wb);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== gradient (B) producer: the three peers' dh1T k-blocks from global memory
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int step = p.L - 1; step >= 0; --step) {
+                const int it = p.L - 1 - step;
+                const int ab = (p.direction == 0 ? step : p.L - 1 - step) * 2 + net;
+                mbar_wait_cluster(smem_u32(&bar_a0), it & 1);
+                fence_proxy_async();
+                for (int i = 2; i < nkb; ++i) {
+                    const int kb = (2 * j + i) % nkb;
+                    const uint32_t s = q % kBSlots, use = q / kBSlots;
+                    ++q;
+                    mbar_wait(smem_u32(&bar_emptyB[s]), (use & 1) ^ 1);
+                    const uint32_t full = smem_u32(&bar_fullB[s]), base = ringB + s * kBBytes;
+                    mbar_expect_tx(full, kBBytes);
+                    tma_load_4d(base, &mapDh1, full, r0, kb * 64, 0, ab);
+                    tma_load_4d(base + kBPlane, &mapDh1, full, r0, kb * 64, 1, ab);
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            uint32_t qa = 0, qb = 0;
+            auto wait_a = [&]() -> uint32_t {
+                const uint32_t s = qa % kASlots, use = qa / kASlots;
+                mbar_wait(smem_u32(&bar_fullA[s]), use & 1);
+                ++qa;
+                return s;
+            };
+            for (int step = p.L - 1; step >= 0; --step) {
+                const uint32_t par = (p.L - 1 - step) & 1;
+                {   // bG2: acc0 = W2^T slice . dpre^T   (B K-major in xa)
+                    const uint32_t s = wait_a();
+                    mbar_wait(smem_u32(&bar_xm), par);
+                    tcgen05_fence_after();
+                    uint32_t acc = 0;
+                    issue_kblock<true, false, false>(tmem + kAcc0, ringA + s * kABytes, kAPlane, xa, 8192, acc, p.two_mma);
+                    tcgen05_commit(smem_u32(&bar_emptyA[s]));
+                    tcgen05_commit(smem_u32(&bar_acc[0]));
+                }
+                {   // bG1: acc1 = W1^T slice . dh1T
+                    uint32_t acc = 0;
+                    for (int i = 0; i < nkb; ++i) {
+                        const uint32_t s = wait_a();
+                        const uint32_t abase = ringA + s * kABytes;
+                        if (i < 2) {
+                            if (i == 0) mbar_wait(smem_u32(&bar_own), par);
+                            tcgen05_fence_after();
+                            issue_kblock<true, true, false>(tmem + kAcc1, abase, kAPlane, xa + i * 16384, 8192, acc, p.two_mma);
+                        } else {
+                            const uint32_t sb = qb % kBSlots, useb = qb / kBSlots;
+                            ++qb;
+                            mbar_wait(smem_u32(&bar_fullB[sb]), useb & 1);
+                            tcgen05_fence_after();
+                            issue_kblock<true, true, false>(tmem + kAcc1, abase, kAPlane, ringB + sb * kBBytes, kBPlane, acc, p.two_mma);
+                            tcgen05_commit(smem_u32(&bar_emptyB[sb]));
+                        }
+                        tcgen05_commit(smem_u32(&bar_emptyA[s]));
+                    }
+                    tcgen05_commit(smem_u32(&bar_acc[1]));
+                }
+                {   // bG0: acc2 = W0^T[:, slice] . dh0T slice
+                    const uint32_t s = wait_a();
+                    mbar_wait(smem_u32(&bar_a1), par);
+                    tcgen05_fence_after();
+                    uint32_t acc = 0;
+                    const uint32_t base = ringA + s * kABytes;
+                    issue_kblock<true, true, false>(tmem + kAcc2, base, kAPlane, xa, 8192, acc, p.two_mma);
+                    issue_kblock<true, true, false>(tmem + kAcc2, base + 8192, kAPlane, xa + 16384, 8192, acc, p.two_mma);
+                    tcgen05_commit(smem_u32(&bar_emptyA[s]));
+                    tcgen05_commit(smem_u32(&bar_acc[2]));
+                }
+            }
+        }
+    } else {
+        // ===================== workers (256 threads)
+        const int t = threadIdx.x;
+        const int lq = warp & 3, ch = warp >> 2;
+        const int fl = lq * 32 + lane;
+        const int f = j * FS + fl;
+        const uint32_t tm_lane = (uint32_t)(lq * 32) << 16;
+        const int D = p.D;
+        const int uq = t & 15, ug = t >> 4;                        // coupling: rows 4*uq.., dims ug + 16 i
+        const uint32_t rowoff = (uint32_t)(fl >> 6) * 16384u + (uint32_t)(fl & 63) * 128u;
+
+        auto worker_wait = [&](uint64_t* bar, uint32_t parity, bool cluster_scope) {
+            if (t == 0) { if (cluster_scope) mbar_wait_cluster(smem_u32(bar), parity); else mbar_wait(smem_u32(bar), parity); }
+            worker_sync();
+        };
+        auto load_acc = [&](uint32_t acc_col, float* v) {
+            tmem_ld32(tmem + tm_lane + acc_col + 32 * ch, v);
+            if (p.two_mma) {
+                float w[32];
+                tmem_ld32(tmem + tm_lane + acc_col + 64 + 32 * ch, w);
+#pragma unroll
+                for (int n = 0; n < 32; ++n) v[n] += w[n];
+            }
+        };
+        // 32 gradients of feature fl (rows 32 ch ..) masked by lrelu'(saved activation), as bfloat16 planes -> xa slice + global planes
+        auto store_grad_slice = [&](float* v, const uint4* sg, bf16* gplanes) {
+            uint32_t sw[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sw[4 * i] = sg[i].x; sw[4 * i + 1] = sg[i].y; sw[4 * i + 2] = sg[i].z; sw[4 * i + 3] = sg[i].w; }
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+                const uint32_t e = (sw[n >> 1] >> ((n & 1) * 16)) & 0xFFFFu;      // saved half activation: > 0 <=> sign clear and non-zero
+                v[n] *= ((e & 0x8000u) == 0 && (e & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
+            }
+            uint4* ghi = reinterpret_cast<uint4*>(gplanes + ((size_t)0 * p.H + f) * p.Rp + r0);
+            uint4* glo = reinterpret_cast<uint4*>(gplanes + ((size_t)1 * p.H + f) * p.Rp + r0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = ch * 4 + i;
+                uint4 hi, lo;
+                split8<false>(v + 8 * i, hi, lo);
+                const uint32_t off = rowoff + (uint32_t)((cc ^ (fl & 7)) << 4);
+                st_shared_v4(xa + off, hi);
+                st_shared_v4(xa + 8192 + off, lo);
+                ghi[cc] = hi;
+                glo[cc] = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        };
+
+        if (t < p.L) {
+            uint64_t mb = 0;
+            for (int d = 0; d < D; ++d) mb |= (uint64_t)(p.mask[(size_t)t * D + d] != 0.f) << d;
+            mbits[t] = mb;
+        }
+        for (int i = t; i < NT * D; i += kWorkers) {
+            const int n = i / D, d = i - n * D;
+            gs[n * kXs + d] = (r0 + n < p.R) ? p.dout[(size_t)(r0 + n) * D + d] : 0.f;
+        }
+        if (t < NT) gls[t] = (p.dlogdet && r0 + t < p.R) ? p.dlogdet_scale * p.dlogdet[r0 + t] : 0.f;
+        if (t < kDp) db2s[t] = 0.f;
+        worker_sync();
+
+        float v[32];
+        for (int step = p.L - 1; step >= 0; --step) {
+            const int layer = p.direction == 0 ? step : p.L - 1 - step;
+            const int it = p.L - 1 - step;
+            const uint32_t par = it & 1;
+            const uint64_t mb = mbits[layer];
+            const size_t sbatch = (size_t)(step * 2 + net) * 2;    // plane index base of the saved activations (indexed by step)
+            const size_t gbatch = (size_t)(layer * 2 + net) * 2;   // ... of the gradient planes (indexed by layer, like the parameters)
+            // ---------------- bU: coupling backward on the tile (every CTA, redundantly), dpre of the CTA's net -> xa (K-major planes)
+            {
+                // zero the K-major dpre tile (both planes, 16 KB): passive and padded dims stay zero
+                {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) st_shared_v4(xa + (uint32_t)(t * 4 + i) * 16u, z);
+                }
+                worker_sync();
+                float dsum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int d = ug + 16 * i;
+                    if (d >= D) continue;
+                    if ((mb >> d) & 1) continue;                      // passive dim: g passes through unchanged, no head gradient
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = uq * 4 + k, r = r0 + n;
+                        float dpre = 0.f;
+                        if (r < p.R) {
+                            const float g = gs[n * kXs + d];
+                            const float xv = __ldg(p.saved_x + ((size_t)step * p.R + r) * D + d);
+                            const float s = __ldg(p.saved_st + ((size_t)(step * 2 + 0) * p.R + r) * D + d);
+                            const float tt = __ldg(p.saved_st + ((size_t)(step * 2 + 1) * p.R + r) * D + d);
+                            const float gl = gls[n];
+                            float dx, ds, dt;
+                            if (p.direction == 0) { const float e = expf(s); dx = g * e; dt = g; ds = g * xv * e + gl; }
+                            else { const float e = expf(-s); dx = g * e; dt = -g * e; ds = -g * (xv - tt) * e - gl; }
+                            ds *= (1.f - s * s);
+                            gs[n * kXs + d] = dx;
+                            dpre = net == 0 ? ds : dt;
+                        }
+                        dsum[i] += dpre;
+                        // K-major [64 rows][64 dims] planes: element (n, d)
+                        const uint16_t h = to16<false>(dpre), l = to16<false>(dpre - from16<false>(h));
+                        const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u + (uint32_t)(((d >> 3) ^ (n & 7)) << 4) + (uint32_t)(d & 7) * 2u;
+                        asm volatile("st.shared.b16 [%0], %1;" ::"r"(xa + off), "h"(h) : "memory");
+                        asm volatile("st.shared.b16 [%0], %1;" ::"r"(xa + 8192 + off), "h"(l) : "memory");
+                        if (j == 0) {   // one CTA per net keeps dpre^T for the W2 weight gradient: [d][row] planes
+                            uint16_t* gp = reinterpret_cast<uint16_t*>(p.dpreT) + ((gbatch + 0) * kDp + d) * p.Rp + r0 + n;
+                            gp[0] = h;
+                            gp[(size_t)kDp * p.Rp] = l;
+                        }
+                    }
+                    if (j == 0) atomicAdd(&db2s[d], dsum[i]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(smem_u32(&bar_xm));
+            }
+            // ---------------- bE2: dh1 = acc0 * lrelu'(a1) -> xa slice + global dh1T (exchange, weight gradients)
+            {
+                uint4 sg[4];
+                const uint4* sp = reinterpret_cast<const uint4*>(p.a1T + ((sbatch + 0) * p.H + f) * p.Rp + r0 + 32 * ch);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sg[i] = __ldg(sp + i);
+                worker_wait(&bar_acc[0], par, false);
+                tcgen05_fence_after();
+                if (j == 0 && t < D && !((mb >> t) & 1)) {   // db2 += column sums of dpre (bU finished: every worker passed the barrier)
+                    atomicAdd(p.dparams + (size_t)(layer * 2 + net) * p.blk + p.ob2 + t, db2s[t]);
+                    db2s[t] = 0.f;
+                }
+                load_acc(kAcc0, v);
+                store_grad_slice(v, sg, p.dh1T + gbatch * p.H * p.Rp);
+                tcgen05_fence_before();
+                worker_sync();
+                if (t == 0) mbar_arrive(smem_u32(&bar_own));
+                if (t < 4) {
+                    fence_proxy_async();
+                    fence_cluster();
+                    mbar_arrive_remote(smem_u32(&bar_a0), net * 4 + t);
+                }
+            }
+            // ---------------- bE1: dh0 = acc1 * lrelu'(a0) -> xa slice (B operand of bG0) + global dh0T (weight gradients)
+            {
+                uint4 sg[4];
+                const uint4* sp = reinterpret_cast<const uint4*>(p.a0T + ((sbatch + 0) * p.H + f) * p.Rp + r0 + 32 * ch);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sg[i] = __ldg(sp + i);
+                worker_wait(&bar_acc[1], par, false);
+                tcgen05_fence_after();
+                load_acc(kAcc1, v);
+                store_grad_slice(v, sg, p.dh0T + gbatch * p.H * p.Rp);
+                tcgen05_fence_before();
+                mbar_arrive(smem_u32(&bar_a1));
+            }
+            // ---------------- bE0: partial input gradients of this CTA's feature slice -> global exchange buffer
+            {
+                worker_wait(&bar_acc[2], par, false);
+                tcgen05_fence_after();
+                if (lq < 2) {   // accumulator rows = flow dims
+                    load_acc(kAcc2, v);
+                    if (fl < D && ((mb >> fl) & 1)) {   // only the dims the nets read (mask = 1) receive this gradient
+                        float4* dst = reinterpret_cast<float4*>(p.partial + ((((size_t)par * p.tiles + tile) * kCluster + rank) * kDp + fl) * NT + 32 * ch);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+                tcgen05_fence_before();
+                worker_sync();
+                if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
+            }
+            // ---------------- combine: g[n][d] += sum over the 8 CTAs of the partials (conditioning dims), g becomes dL/d(layer input)
+            {
+                worker_wait(&bar_part, par, true);
+                const float* pbase = p.partial + (((size_t)par * p.tiles + tile) * kCluster) * kDp * NT + uq * 4;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int d = ug + 16 * i;
+                    if (d >= D || !((mb >> d) & 1)) continue;
+                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int cta = 0; cta < 8; ++cta) {
+                        const float4 q4 = __ldcg(reinterpret_cast<const float4*>(pbase + ((size_t)cta * kDp + d) * NT));
+                        a4.x += q4.x; a4.y += q4.y; a4.z += q4.z; a4.w += q4.w;
+                    }
+                    gs[(uq * 4 + 0) * kXs + d] += a4.x; gs[(uq * 4 + 1) * kXs + d] += a4.y;
+                    gs[(uq * 4 + 2) * kXs + d] += a4.z; gs[(uq * 4 + 3) * kXs + d] += a4.w;
+                }
+                worker_sync();
+            }
+        }
+        if (rank == 0) {
+            const int nvalid = min(NT, p.R - r0) * D;
+            for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; p.din[(size_t)r0 * D + i] = gs[n * kXs + d]; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
 long long* debug_buffer();
 
 // ---- host -----------------------------------------------------------------------------------------------------
@@ -621,6 +1007,164 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
         return MHE_ERR_CUDA;
     }
     return check_launch("fused flow fwd");
+}
+
+
+// ---- small kernels around the backward ---------------------------------------------------------------------------------
+// saved half planes [step][net][2][n] -> bfloat16 planes [layer][net][2][n] of the same values (operands of the weight-gradient GEMMs)
+__global__ void replane_by_layer_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long n, int L, int direction) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int sb = blockIdx.y;                    // step * 2 + net
+    const int step = sb >> 1, net = sb & 1;
+    const int layer = direction == 0 ? step : L - 1 - step;
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + (long)sb * 2 * n;
+    uint16_t* d16 = reinterpret_cast<uint16_t*>(dst) + (long)(layer * 2 + net) * 2 * n;
+    const float v = from16<true>(s16[i]) + from16<true>(s16[n + i]);
+    const uint16_t h = to16<false>(v);
+    d16[i] = h;
+    d16[n + i] = to16<false>(v - from16<false>(h));
+}
+// xmT[layer][net][plane][d][r] = bfloat16 planes of mask[layer][d] * x_step[r][d]  (zero for d >= D, r >= R)
+__global__ void xm_transposed_kernel(const float* __restrict__ saved_x, const float* __restrict__ mask, int R, int Rp, int D, int L, int direction,
+                                     bf16* __restrict__ xmT) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.y, layer = blockIdx.z;
+    if (r >= Rp) return;
+    const int step = direction == 0 ? layer : L - 1 - layer;
+    float v = 0.f;
+    if (r < R && d < D) v = saved_x[((size_t)step * R + r) * D + d] * mask[(size_t)layer * D + d];
+    const uint16_t h = to16<false>(v), l = to16<false>(v - from16<false>(h));
+    uint16_t* o = reinterpret_cast<uint16_t*>(xmT);
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+        const size_t base = ((size_t)(layer * 2 + net) * 2) * kDp * Rp + (size_t)d * Rp + r;
+        o[base] = h;
+        o[base + (size_t)kDp * Rp] = l;
+    }
+}
+// dcp[b][(layer*4 + net*2 + jj)*H + f] += sum_s dh_jj[layer][net][f][s*B + b]   (jj = 0: dh0, 1: dh1; planes hi + lo)
+__global__ void __launch_bounds__(256) dcp_from_planes_kernel(const bf16* __restrict__ dh0T, const bf16* __restrict__ dh1T, int R, int Rp, int B, int H,
+                                                               float* __restrict__ dcp, long cp_ld) {
+    __shared__ float tile[32][33];
+    const int f0 = blockIdx.x * 32, ln = blockIdx.y, jj = blockIdx.z;       // ln = layer * 2 + net
+    const uint16_t* src = reinterpret_cast<const uint16_t*>(jj == 0 ? dh0T : dh1T) + (size_t)ln * 2 * H * Rp;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int layer = ln >> 1, net = ln & 1;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int b = b0 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {       // warp w sums features f0 + 4 w + q over the hypotheses of image b
+            const int fl = 4 * w + q;
+            const uint16_t* hi = src + (size_t)(f0 + fl) * Rp, *lo = hi + (size_t)H * Rp;
+            float acc = 0.f;
+            if (b < B)
+                for (int r = b; r < R; r += B) acc += from16<false>(hi[r]) + from16<false>(lo[r]);
+            tile[fl][lane] = acc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {       // rows of dcp: 32 consecutive features per image
+            const int bl = 4 * w + q;
+            if (b0 + bl < B) dcp[(size_t)(b0 + bl) * cp_ld + (size_t)(layer * 4 + net * 2 + jj) * H + f0 + lane] += tile[lane][bl];
+        }
+        __syncthreads();
+    }
+}
+
+static PlaneTensor ptk(const bf16* base, int cols, int rows, int batches) {   // [batches][2 planes][rows][cols]
+    PlaneTensor t;
+    t.base = base; t.cols = cols; t.rows = rows; t.planes = 2; t.batches = batches;
+    t.row_pitch = cols; t.plane_stride = (long)rows * cols; t.batch_stride = (long)2 * rows * cols;
+    return t;
+}
+
+static int cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return MHE_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MHE_ERR_CUDA;
+}
+
+int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* saved, int R, int B, int direction,
+             const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp, void* workspace,
+             cudaStream_t stream) {
+    (void)params;
+    tcflow::Packed P(L, (bf16*)packed);
+    BWs ws(workspace, L, R);
+    FSaved S(const_cast<float*>(saved), L, R);
+    const int Rp = padded_rows(R), tiles = tiles_of(R);
+    const long nact = (long)L.H * Rp;
+    BwdArgs a{};
+    a.mask = mask; a.saved_x = S.x_; a.saved_st = S.st_; a.a0T = S.a0_; a.a1T = S.a1_;
+    a.dout = dout; a.dlogdet = dlogdet; a.dlogdet_scale = dlogdet_scale; a.din = din; a.dparams = dparams;
+    a.dh1T = ws.dh1T; a.dh0T = ws.dh0T; a.dpreT = ws.dpreT; a.partial = ws.partial; a.dbg = nullptr;
+    a.R = R; a.Rp = Rp; a.D = L.D; a.H = L.H; a.L = L.L; a.direction = direction; a.tiles = tiles;
+    { const char* e = getenv("MHE_FUSED_TWO_MMA"); a.two_mma = e ? (atoi(e) != 0) : 1; }
+    a.blk = L.blk; a.ob2 = L.ob2;
+    int st = MHE_OK;
+    const CUtensorMap* mW0 = cached_map(pt4(P.w0b, tcflow::kDp, L.H, L.L * 2), 64, &st);
+    if (st != MHE_OK) return st;
+    const CUtensorMap* mW1 = cached_map(pt4(P.w1b, L.H, L.H, L.L * 2), 64, &st);
+    if (st != MHE_OK) return st;
+    const CUtensorMap* mW2 = cached_map(pt4(P.w2b, L.H, tcflow::kDp, L.L * 2), 64, &st);
+    if (st != MHE_OK) return st;
+    const CUtensorMap* mDh1 = cached_map(pt4(ws.dh1T, Rp, L.H, L.L * 2), 64, &st);
+    if (st != MHE_OK) return st;
+    // only the active dims of dpreT are written by the kernel
+    MHE_TRY(cuda_ok(cudaMemsetAsync(ws.dpreT, 0, (size_t)L.L * 4 * kDp * Rp * 2, stream), "memset dpreT"));
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(flow_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+            set_error("fused flow bwd: cannot raise dynamic shared memory to %d", kSmemBytes);
+            return MHE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    {
+        ProbeScope probe("fused flow bwd", stream);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(tiles * kCluster); cfg.blockDim = dim3(kThreadsF); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, flow_bwd_fused_kernel, *mW0, *mW1, *mW2, *mDh1, a) != cudaSuccess) {
+            set_error("fused flow bwd: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return MHE_ERR_CUDA;
+        }
+        MHE_TRY(check_launch("fused flow bwd"));
+    }
+    // operands of the weight gradients: bfloat16 planes of the saved activations (by layer) and of the masked inputs
+    {
+        dim3 grid(cdiv((int)nact, 256), L.L * 2);
+        replane_by_layer_kernel<<<grid, 256, 0, stream>>>(S.a0_, ws.a0b, nact, L.L, direction);
+        MHE_TRY(check_launch("replane a0"));
+        replane_by_layer_kernel<<<grid, 256, 0, stream>>>(S.a1_, ws.a1b, nact, L.L, direction);
+        MHE_TRY(check_launch("replane a1"));
+        dim3 gx(cdiv(Rp, 128), kDp, L.L);
+        xm_transposed_kernel<<<gx, 128, 0, stream>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT);
+        MHE_TRY(check_launch("xm transposed"));
+    }
+    const int nb = L.L * 2;
+    {   // dW1 [out][in] += dh1T . a0T^T  (contraction over the rows)
+        GemmShape g{L.H, L.H, Rp, nb, 1, 1, 1};
+        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh1T, Rp, L.H, nb), ptk(ws.a0b, Rp, L.H, nb), g, dparams + L.oW1, L.H, (long)L.blk, L.H, 0, stream, "fused wgrad W1"));
+    }
+    {   // dW0 [feat][d] += dh0T . xmT^T
+        GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
+        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh0T, Rp, L.H, nb), ptk(ws.xmT, Rp, kDp, nb), g, dparams + L.oW0, L.D, (long)L.blk, L.D, 0, stream, "fused wgrad W0"));
+    }
+    {   // dW2 [d][feat] += dpreT . a1T^T, computed as (a1T . dpreT^T)[feat][d] and stored transposed
+        GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
+        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.a1b, Rp, L.H, nb), ptk(ws.dpreT, Rp, kDp, nb), g, dparams + L.oW2, L.H, (long)L.blk, L.D, 1, stream, "fused wgrad W2"));
+    }
+    {   // dcp += sums over the hypotheses of dh0 / dh1
+        dim3 grid(L.H / 32, nb, 2);
+        dcp_from_planes_kernel<<<grid, 256, 0, stream>>>(ws.dh0T, ws.dh1T, R, Rp, B, L.H, dcp, (long)L.L * 4 * L.H);
+        MHE_TRY(check_launch("dcp from planes"));
+    }
+    return MHE_OK;
 }
 
 }  // namespace fused

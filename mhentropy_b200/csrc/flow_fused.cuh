@@ -61,6 +61,33 @@ struct FWs {
     }
 };
 
+// backward scratch: gradient planes of every layer (consumed by the batched weight-gradient GEMMs), bfloat16 re-planes of the saved
+// activations and of the masked layer inputs, the exchange buffer
+struct BWs {
+    __nv_bfloat16 *dh1T, *dh0T;   // [L][2 nets][2 planes][H][Rp]   (indexed by layer)
+    __nv_bfloat16 *dpreT;         // [L][2][2][64][Rp]
+    __nv_bfloat16 *a0b, *a1b;     // [L][2][2][H][Rp]  bfloat16 planes of the saved half activations, re-indexed by layer
+    __nv_bfloat16 *xmT;           // [L][2][2][64][Rp] masked layer inputs, transposed, one copy per net
+    float* partial;
+    static size_t bytes(const FlowLayout& L, int R) {
+        const size_t act = (size_t)L.L * 4 * L.H * padded_rows(R) * 2, small = (size_t)L.L * 4 * kDp * padded_rows(R) * 2;
+        return 4 * act + 2 * small + (size_t)2 * tiles_of(R) * kCluster * kDp * NT * 4 + 16 * 1024;
+    }
+    BWs(void* base_, const FlowLayout& L, int R) {
+        uint8_t* base = (uint8_t*)base_;
+        auto take = [&](size_t n) { uint8_t* p = base; base += (n + 1023) / 1024 * 1024; return p; };
+        const size_t act = (size_t)L.L * 4 * L.H * padded_rows(R) * 2, small = (size_t)L.L * 4 * kDp * padded_rows(R) * 2;
+        dh1T = (__nv_bfloat16*)take(act); dh0T = (__nv_bfloat16*)take(act);
+        a0b = (__nv_bfloat16*)take(act); a1b = (__nv_bfloat16*)take(act);
+        dpreT = (__nv_bfloat16*)take(small); xmT = (__nv_bfloat16*)take(small);
+        partial = (float*)take((size_t)2 * tiles_of(R) * kCluster * kDp * NT * 4);
+    }
+};
+
+int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* saved, int R, int B, int direction,
+             const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp, void* workspace,
+             cudaStream_t stream);
+
 int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,
              int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream);
 

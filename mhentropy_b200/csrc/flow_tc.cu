@@ -276,6 +276,16 @@ static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const E
     return launch_tc_gemm<64, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
 }
 
+int wgrad_kmajor(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, float* dW, long ld, long batch_stride, int ncols, int transposed,
+                 cudaStream_t stream, const char* what) {
+    if (transposed) {
+        EpiWgradT e{dW, ld, batch_stride, ncols, g.ksplit > 1};
+        return gemm<false, false, false>(A, B, g, e, stream, what);
+    }
+    EpiWgrad e{dW, ld, batch_stride, ncols, g.ksplit > 1};
+    return gemm<false, false, false>(A, B, g, e, stream, what);
+}
+
 // ---- side stream for the weight-gradient GEMMs ---------------------------------------------------------
 // dW GEMMs are off the critical path of the backward (nothing downstream in the pass reads them), so they are
 // forked onto an internal stream, layer by layer, and joined at the end of the pass.  Fork/join uses events, which

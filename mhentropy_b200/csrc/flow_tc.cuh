@@ -82,6 +82,11 @@ inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
     return ((size_t)2 * B * L.C + 512 + (size_t)2 * B * L.L * 4 * L.H) * 2 + 4096;
 }
 
+// dW[batch] (+)= A[batch] . B[batch]^T for K-major bfloat16 plane operands (A: [M rows][K], B: [N rows][K]); rows of dW have pitch ld.
+// transposed != 0 stores element (m, n) at dW[n][m] instead.
+int wgrad_kmajor(const tc::PlaneTensor& A, const tc::PlaneTensor& B, tc::GemmShape g, float* dW, long ld, long batch_stride, int ncols,
+                 int transposed, cudaStream_t stream, const char* what);
+
 int pack_weights(const FlowLayout& L, const float* params, void* packed, int which, cudaStream_t stream);
 int cond_fwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, int B, float* cp, void* ws, cudaStream_t stream);
 int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, const float* dcp, int B, float* dparams,

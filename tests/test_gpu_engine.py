@@ -36,7 +36,7 @@ def test_engine_matches_autograd_path_and_oracle(use_graph, B, S, precision):
     for _ in range(2):           # replay twice: the graph must be re-runnable (gradient buffers are re-zeroed inside)
         loss = eng.run()
     torch.cuda.synchronize()
-    assert eng.launches_per_step > 100
+    assert eng.launches_per_step > 10
 
     feat = devb['feat'].clone().requires_grad_(True)
     z_det = devb['z_det'].clone().requires_grad_(True)
