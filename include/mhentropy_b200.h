@@ -116,6 +116,13 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
                       float* din, float* dparams, float* dcp,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Asynchronous weight gradients (optional).  After mhe_flow_set_async(1), mhe_flow_pass_bwd may return while its weight-gradient
+ * GEMMs (the dparams W0/W1/W2 slots) still run on internal streams, so that the caller can enqueue independent work (the
+ * conditioning backward only needs dcp); mhe_flow_join(stream) makes `stream` wait for them and must be called before dparams
+ * is read or the captured graph ends.  Default: off (pass_bwd joins before returning).                                      */
+int mhe_flow_set_async(int on);
+int mhe_flow_join(void* stream);
+
 /* log N(z; 0, I) + logdet per row (flows.py:320) and its gradient seeds:
  *   fwd: logp[r] = -0.5|z_r|^2 - 0.5 D ln(2 pi) + logdet_sign*logdet[r]   (logdet may be NULL)
  *   bwd: dz[r][:] = -z[r][:] * dlogp[r]                                                          */

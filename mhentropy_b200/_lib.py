@@ -53,6 +53,8 @@ _SIGNATURES = {
     'mhe_flow_cond_bwd': (c_int, [FlowShape, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     'mhe_flow_pass_fwd': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     'mhe_flow_pass_bwd': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    'mhe_flow_set_async': (c_int, [c_int]),
+    'mhe_flow_join': (c_int, [_P]),
     'mhe_std_normal_logp_fwd': (c_int, [_P, _P, c_float, c_int, c_int, _P, _P]),
     'mhe_std_normal_logp_bwd': (c_int, [_P, _P, c_int, c_int, _P, _P]),
     'mhe_mano_workspace_bytes': (c_size_t, [c_int, c_int]),

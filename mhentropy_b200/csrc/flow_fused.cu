@@ -20,7 +20,6 @@ constexpr int kXs = 49;                        // row stride of the fp32 x tile 
 constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + kXaBytes + NT * kXs * 4 + 1024 /*align*/;
 constexpr int kTmemCols = 512;                 // three accumulators of 128 columns: [0,64) = Ah.Bh + Al.Bh, [64,128) = Ah.Bl (summed in the epilogue)
 constexpr int kAcc0 = 0, kAcc1 = 128, kAcc2 = 256;
-constexpr int kPartRows = 24;                  // active dims per layer (<= 23), padded
 
 bool supported(const FlowLayout& L, int R) {
     static int max_rows = -1;
@@ -1044,31 +1043,41 @@ __global__ void xm_transposed_kernel(const float* __restrict__ saved_x, const fl
     }
 }
 // dcp[b][(layer*4 + net*2 + jj)*H + f] += sum_s dh_jj[layer][net][f][s*B + b]   (jj = 0: dh0, 1: dh1; planes hi + lo)
+// block: 32 features x 64 images; thread = (feature, 8 consecutive images), 16-byte plane loads; transposed through shared memory
+// so that the rows of dcp receive 32 consecutive features (128 B) per store
 __global__ void __launch_bounds__(256) dcp_from_planes_kernel(const bf16* __restrict__ dh0T, const bf16* __restrict__ dh1T, int R, int Rp, int B, int H,
                                                                float* __restrict__ dcp, long cp_ld) {
-    __shared__ float tile[32][33];
-    const int f0 = blockIdx.x * 32, ln = blockIdx.y, jj = blockIdx.z;       // ln = layer * 2 + net
+    __shared__ float tile[32][65];
+    const int f0 = blockIdx.x * 32, ln = blockIdx.y, jj = blockIdx.z & 1, b0 = (blockIdx.z >> 1) * 64;       // ln = layer * 2 + net
     const uint16_t* src = reinterpret_cast<const uint16_t*>(jj == 0 ? dh0T : dh1T) + (size_t)ln * 2 * H * Rp;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int layer = ln >> 1, net = ln & 1;
-    for (int b0 = 0; b0 < B; b0 += 32) {
-        const int b = b0 + lane;
+    const int fl = threadIdx.x >> 3, bg = threadIdx.x & 7;
+    const uint16_t* hi = src + (size_t)(f0 + fl) * Rp, *lo = hi + (size_t)H * Rp;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int b = b0 + bg * 8;
+    if ((B & 7) == 0) {
+        if (b < B)
+            for (int r = b; r < R; r += B) {
+                const uint4 h4 = *reinterpret_cast<const uint4*>(hi + r), l4 = *reinterpret_cast<const uint4*>(lo + r);
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {       // warp w sums features f0 + 4 w + q over the hypotheses of image b
-            const int fl = 4 * w + q;
-            const uint16_t* hi = src + (size_t)(f0 + fl) * Rp, *lo = hi + (size_t)H * Rp;
-            float acc = 0.f;
-            if (b < B)
-                for (int r = b; r < R; r += B) acc += from16<false>(hi[r]) + from16<false>(lo[r]);
-            tile[fl][lane] = acc;
-        }
-        __syncthreads();
+                for (int k = 0; k < 8; ++k)
+                    acc[k] += from16<false>((uint16_t)(hw[k >> 1] >> ((k & 1) * 16))) + from16<false>((uint16_t)(lw[k >> 1] >> ((k & 1) * 16)));
+            }
+    } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {       // rows of dcp: 32 consecutive features per image
-            const int bl = 4 * w + q;
-            if (b0 + bl < B) dcp[(size_t)(b0 + bl) * cp_ld + (size_t)(layer * 4 + net * 2 + jj) * H + f0 + lane] += tile[lane][bl];
-        }
-        __syncthreads();
+        for (int k = 0; k < 8; ++k)
+            if (b + k < B)
+                for (int r = b + k; r < R; r += B) acc[k] += from16<false>(hi[r]) + from16<false>(lo[r]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[fl][bg * 8 + k] = acc[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int bl = w * 8 + q;
+        if (b0 + bl < B) dcp[(size_t)(b0 + bl) * cp_ld + (size_t)(layer * 4 + net * 2 + jj) * H + f0 + lane] += tile[lane][bl];
     }
 }
 
@@ -1083,6 +1092,44 @@ static int cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return MHE_OK;
     set_error("%s: %s", what, cudaGetErrorString(e));
     return MHE_ERR_CUDA;
+}
+
+struct BwdAux {
+    cudaStream_t stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t start = nullptr, replaned = nullptr, bwd_done = nullptr, wgrad_done[3] = {nullptr, nullptr, nullptr};
+    bool has_pending = false;
+    bool ok = false;
+};
+static BwdAux& bwd_aux() {
+    static BwdAux a;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        bool ok = true;
+        for (int i = 0; i < 3 && ok; ++i)
+            ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&a.wgrad_done[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&a.start, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&a.replaned, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&a.bwd_done, cudaEventDisableTiming) == cudaSuccess;
+        a.ok = ok;
+    }
+    return a;
+}
+static int g_async_wgrad = 0;
+void set_async_wgrad(int on) { g_async_wgrad = on; }
+static bool async_wgrad() { return g_async_wgrad != 0; }
+static int join_pending_on(cudaStream_t stream) {
+    BwdAux& ax = bwd_aux();
+    for (int i = 0; i < 3; ++i)
+        if (cudaStreamWaitEvent(stream, ax.wgrad_done[i], 0) != cudaSuccess) { set_error("join weight gradients: %s", cudaGetErrorString(cudaGetLastError())); return MHE_ERR_CUDA; }
+    ax.has_pending = false;
+    return MHE_OK;
+}
+int join(cudaStream_t stream) {
+    BwdAux& ax = bwd_aux();
+    if (!ax.ok || !ax.has_pending) return MHE_OK;
+    return join_pending_on(stream);
 }
 
 int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* saved, int R, int B, int direction,
@@ -1121,6 +1168,23 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         }
         attr_set = true;
     }
+    {   // operands of the weight gradients (bfloat16 planes of the saved activations by layer, masked inputs): side stream, concurrent
+        BwdAux& ax0 = bwd_aux();
+        cudaStream_t sr = ax0.ok ? ax0.stream[0] : stream;
+        if (ax0.ok) {
+            MHE_TRY(cuda_ok(cudaEventRecord(ax0.start, stream), "fork replane"));
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax0.start, 0), "fork replane"));
+        }
+        dim3 grid(cdiv((int)nact, 256), L.L * 2);
+        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a0_, ws.a0b, nact, L.L, direction);
+        MHE_TRY(check_launch("replane a0"));
+        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a1_, ws.a1b, nact, L.L, direction);
+        MHE_TRY(check_launch("replane a1"));
+        dim3 gx(cdiv(Rp, 128), kDp, L.L);
+        xm_transposed_kernel<<<gx, 128, 0, sr>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT);
+        MHE_TRY(check_launch("xm transposed"));
+        if (ax0.ok) MHE_TRY(cuda_ok(cudaEventRecord(ax0.replaned, sr), "replaned"));
+    }
     {
         ProbeScope probe("fused flow bwd", stream);
         cudaLaunchConfig_t cfg = {};
@@ -1135,34 +1199,40 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         }
         MHE_TRY(check_launch("fused flow bwd"));
     }
-    // operands of the weight gradients: bfloat16 planes of the saved activations (by layer) and of the masked inputs
-    {
-        dim3 grid(cdiv((int)nact, 256), L.L * 2);
-        replane_by_layer_kernel<<<grid, 256, 0, stream>>>(S.a0_, ws.a0b, nact, L.L, direction);
-        MHE_TRY(check_launch("replane a0"));
-        replane_by_layer_kernel<<<grid, 256, 0, stream>>>(S.a1_, ws.a1b, nact, L.L, direction);
-        MHE_TRY(check_launch("replane a1"));
-        dim3 gx(cdiv(Rp, 128), kDp, L.L);
-        xm_transposed_kernel<<<gx, 128, 0, stream>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT);
-        MHE_TRY(check_launch("xm transposed"));
-    }
+    // Everything after the data-gradient kernel is off its critical path and mutually independent: the re-planes run on a side
+    // stream while the kernel runs (it fills 80 of the 148 SMs), the three weight-gradient GEMMs on three streams, the dcp sums on
+    // the caller's stream.  Fork / join with events (graph-capture safe).
+    BwdAux& ax = bwd_aux();
+    const bool par = ax.ok;
+    cudaStream_t s0 = par ? ax.stream[0] : stream, s1 = par ? ax.stream[1] : stream, s2 = par ? ax.stream[2] : stream;
     const int nb = L.L * 2;
+    if (par) {
+        MHE_TRY(cuda_ok(cudaEventRecord(ax.bwd_done, stream), "fork"));
+        for (int i = 0; i < 3; ++i) MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[i], ax.bwd_done, 0), "fork"));
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(s1, ax.replaned, 0), "fork"));
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(s2, ax.replaned, 0), "fork"));
+    }
     {   // dW1 [out][in] += dh1T . a0T^T  (contraction over the rows)
         GemmShape g{L.H, L.H, Rp, nb, 1, 1, 1};
-        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh1T, Rp, L.H, nb), ptk(ws.a0b, Rp, L.H, nb), g, dparams + L.oW1, L.H, (long)L.blk, L.H, 0, stream, "fused wgrad W1"));
+        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh1T, Rp, L.H, nb), ptk(ws.a0b, Rp, L.H, nb), g, dparams + L.oW1, L.H, (long)L.blk, L.H, 0, s0, "fused wgrad W1"));
     }
     {   // dW0 [feat][d] += dh0T . xmT^T
         GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
-        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh0T, Rp, L.H, nb), ptk(ws.xmT, Rp, kDp, nb), g, dparams + L.oW0, L.D, (long)L.blk, L.D, 0, stream, "fused wgrad W0"));
+        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh0T, Rp, L.H, nb), ptk(ws.xmT, Rp, kDp, nb), g, dparams + L.oW0, L.D, (long)L.blk, L.D, 0, s1, "fused wgrad W0"));
     }
     {   // dW2 [d][feat] += dpreT . a1T^T, computed as (a1T . dpreT^T)[feat][d] and stored transposed
         GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
-        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.a1b, Rp, L.H, nb), ptk(ws.dpreT, Rp, kDp, nb), g, dparams + L.oW2, L.H, (long)L.blk, L.D, 1, stream, "fused wgrad W2"));
+        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.a1b, Rp, L.H, nb), ptk(ws.dpreT, Rp, kDp, nb), g, dparams + L.oW2, L.H, (long)L.blk, L.D, 1, s2, "fused wgrad W2"));
     }
     {   // dcp += sums over the hypotheses of dh0 / dh1
-        dim3 grid(L.H / 32, nb, 2);
+        dim3 grid(L.H / 32, nb, 2 * cdiv(B, 64));
         dcp_from_planes_kernel<<<grid, 256, 0, stream>>>(ws.dh0T, ws.dh1T, R, Rp, B, L.H, dcp, (long)L.L * 4 * L.H);
         MHE_TRY(check_launch("dcp from planes"));
+    }
+    if (par) {
+        for (int i = 0; i < 3; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.wgrad_done[i], ax.stream[i]), "join"));
+        if (async_wgrad()) ax.has_pending = true;    // the caller joins with mhe_flow_join() before reading dparams
+        else MHE_TRY(join_pending_on(stream));
     }
     return MHE_OK;
 }

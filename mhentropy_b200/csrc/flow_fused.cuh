@@ -88,6 +88,11 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
              const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp, void* workspace,
              cudaStream_t stream);
 
+// Asynchronous weight gradients: with set_async_wgrad(1) pass_bwd returns with its weight-gradient GEMMs still running on internal
+// streams; join(stream) makes `stream` wait for them (mhe_flow_set_async / mhe_flow_join in the C ABI).
+void set_async_wgrad(int on);
+int join(cudaStream_t stream);
+
 int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,
              int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream);
 

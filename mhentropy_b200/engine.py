@@ -109,10 +109,17 @@ class TrainStep:
                              ws, wsb, s), 'mano_bwd')
         check(L.mhe_combine_z_bwd(ptr(self.dz), R, B, ptr(self.dx), ptr(self.dz_det), s), 'combine_z_bwd')
         # log_q = log N(z0) - logdet  ->  dL/dlogdet = -dL/dlog_q
-        check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
-                                  ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
+        # the weight-gradient GEMMs of the pass keep running on the library's streams while the conditioning backward (which only
+        # needs dcp) is enqueued; mhe_flow_join() brings them back before the step ends
+        check(L.mhe_flow_set_async(1), 'set_async')
+        try:
+            check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
+                                      ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
+        finally:
+            check(L.mhe_flow_set_async(0), 'set_async')
         check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), pk, ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat),
                                   cws, cwsb, s), 'cond_bwd')
+        check(L.mhe_flow_join(s), 'flow_join')
         torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
 
     def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
