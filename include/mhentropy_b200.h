@@ -80,7 +80,8 @@ size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s);
  *                    whenever the parameters change.  Needs dim <= 64, hidden % 64 == 0, cond % 8 == 0
  *                    (mhe_flow_packed_bytes() returns 0 otherwise).                                   */
 size_t mhe_flow_packed_bytes(mhe_flow_shape s);
-/* which: 1 = the half planes the forward GEMMs read, 2 = the bfloat16 planes the backward GEMMs read, 3 = both */
+/* which (bit set): 1 = the half planes the forward GEMMs read, 2 = the bfloat16 planes the backward GEMMs read; 4 / 8 = only the
+ * conditioning / only the coupling part of the half planes (so the conditioning GEMM can start while the rest is converted) */
 int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, int which, void* stream);
 /* bytes of scratch needed by the flow passes over R rows (forward and backward) on the chosen path */
 size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core);

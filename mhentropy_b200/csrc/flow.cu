@@ -289,7 +289,7 @@ size_t mhe_flow_packed_bytes(mhe_flow_shape s) {
 }
 
 int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, int which, void* stream) {
-    MHE_REQUIRE(valid_shape(s) && params && packed && which >= 1 && which <= 3, "pack_weights: bad args");
+    MHE_REQUIRE(valid_shape(s) && params && packed && which >= 1 && which <= 15, "pack_weights: bad args");
     FlowLayout L(s);
     if (!tcflow::supported(L)) { set_error("pack_weights: shape outside the tensor-core path (dim <= 64, hidden %% 64 == 0, cond %% 8 == 0)"); return MHE_ERR_UNSUPPORTED; }
     return tcflow::pack_weights(L, params, packed, which, (cudaStream_t)stream);

@@ -1168,23 +1168,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         }
         attr_set = true;
     }
-    {   // operands of the weight gradients (bfloat16 planes of the saved activations by layer, masked inputs): side stream, concurrent
-        BwdAux& ax0 = bwd_aux();
-        cudaStream_t sr = ax0.ok ? ax0.stream[0] : stream;
-        if (ax0.ok) {
-            MHE_TRY(cuda_ok(cudaEventRecord(ax0.start, stream), "fork replane"));
-            MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax0.start, 0), "fork replane"));
-        }
-        dim3 grid(cdiv((int)nact, 256), L.L * 2);
-        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a0_, ws.a0b, nact, L.L, direction);
-        MHE_TRY(check_launch("replane a0"));
-        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a1_, ws.a1b, nact, L.L, direction);
-        MHE_TRY(check_launch("replane a1"));
-        dim3 gx(cdiv(Rp, 128), kDp, L.L);
-        xm_transposed_kernel<<<gx, 128, 0, sr>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT);
-        MHE_TRY(check_launch("xm transposed"));
-        if (ax0.ok) MHE_TRY(cuda_ok(cudaEventRecord(ax0.replaned, sr), "replaned"));
-    }
+    if (bwd_aux().ok) MHE_TRY(cuda_ok(cudaEventRecord(bwd_aux().start, stream), "fork replane"));
     {
         ProbeScope probe("fused flow bwd", stream);
         cudaLaunchConfig_t cfg = {};
@@ -1198,6 +1182,23 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
             return MHE_ERR_CUDA;
         }
         MHE_TRY(check_launch("fused flow bwd"));
+    }
+    // (launched after the kernel so that its 80 clusters' CTAs get their SMs first; the re-planes fill the remaining ones)
+    {   // operands of the weight gradients (bfloat16 planes of the saved activations by layer, masked inputs): side stream, concurrent
+        BwdAux& ax0 = bwd_aux();
+        cudaStream_t sr = ax0.ok ? ax0.stream[0] : stream;
+        if (ax0.ok) {
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax0.start, 0), "fork replane"));
+        }
+        dim3 grid(cdiv((int)nact, 256), L.L * 2);
+        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a0_, ws.a0b, nact, L.L, direction);
+        MHE_TRY(check_launch("replane a0"));
+        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a1_, ws.a1b, nact, L.L, direction);
+        MHE_TRY(check_launch("replane a1"));
+        dim3 gx(cdiv(Rp, 128), kDp, L.L);
+        xm_transposed_kernel<<<gx, 128, 0, sr>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT);
+        MHE_TRY(check_launch("xm transposed"));
+        if (ax0.ok) MHE_TRY(cuda_ok(cudaEventRecord(ax0.replaned, sr), "replaned"));
     }
     // Everything after the data-gradient kernel is off its critical path and mutually independent: the re-planes run on a side
     // stream while the kernel runs (it fills 80 of the 148 SMs), the three weight-gradient GEMMs on three streams, the dcp sums on

@@ -315,8 +315,10 @@ static Aux& aux_ctx() {
 int pack_weights(const FlowLayout& L, const float* params, void* packed, int which, cudaStream_t stream) {
     Packed P(L, (bf16*)packed);
     // W0 [H][D] -> [H][64]; W1 [H][H]; W2 [D][H] -> [64][H]; Cw [H][C]
-    if (which & 1) {   // half planes: forward GEMMs
+    // half planes (forward GEMMs): bit 0 = all of them, bit 2 = only the conditioning weights, bit 3 = only the coupling weights
+    if (which & (1 | 4))
         MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cw, L.H, L.C, 2, L.L * 4, true, stream));
+    if (which & (1 | 8)) {
         MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0, L.H, kDp, 2, L.L * 2, true, stream));
         MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, true, stream));
         MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, true, stream));

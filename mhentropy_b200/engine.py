@@ -55,6 +55,7 @@ class TrainStep:
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.side = torch.cuda.Stream(self.dev)
         self.side2 = torch.cuda.Stream(self.dev)
+        self.side3 = torch.cuda.Stream(self.dev)
         self.jtr_mesh = f(R, 21, 3)
         self.mws_bytes = L.mhe_mano_workspace_bytes(R, 0)
         self.mws = torch.empty(self.mws_bytes, dtype=torch.uint8, device=dev)
@@ -70,16 +71,23 @@ class TrainStep:
         theta, beta = z.data_ptr(), z.data_ptr() + 48 * 4
         pk, cws, cwsb = ptr(self.packed), ptr(self.cws), self.cws_bytes
         # ---- forward
-        if self.tc:   # weights change between steps: refresh their split planes inside the step.  The bfloat16 copies are
-            # only read by the backward, so they are produced on a side stream while the forward runs.
+        if self.tc:   # weights change between steps: refresh their split planes inside the step.  Only the conditioning planes gate
+            # the first GEMM; the coupling planes are converted on a side stream meanwhile, and the bfloat16 copies (read by the
+            # backward only) on another one while the forward runs.
             main = torch.cuda.current_stream(self.dev)
             self.side.wait_stream(main)
+            self.side3.wait_stream(main)
+            check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 4, s), 'pack_weights')
+            with torch.cuda.stream(self.side3):
+                check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 8, _lib.stream_ptr(self.dev)), 'pack_weights')
             with torch.cuda.stream(self.side):
+                self.side.wait_stream(self.side3)      # the forward-critical conversions get the memory system first
                 check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 2, _lib.stream_ptr(self.dev)), 'pack_weights')
                 self.dflat.zero_()
                 self.dcp.zero_()
-            check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 1, s), 'pack_weights')
         check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
+        if self.tc:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side3)
         check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
                                   ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
         check(L.mhe_std_normal_logp_fwd(ptr(self.z0), ptr(self.logdet), -1.0, R, shape.dim, ptr(self.log_q), s), 'log_q')
