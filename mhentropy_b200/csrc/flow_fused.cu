@@ -12,12 +12,14 @@ constexpr int kThreadsF = kWorkers + 96;       // warp 8: weight (A) producer, w
 constexpr int kASlots = 4;
 constexpr int kABytes = 32768;                 // A block, both planes: 2 x [128][64] 16-bit
 constexpr int kAPlane = 16384;
-constexpr int kBSlots = 3;
+constexpr int kBSlots = 2;
 constexpr int kBBytes = 16384;                 // B block, both planes: 2 x [64][64] 16-bit
 constexpr int kBPlane = 8192;
 constexpr int kXaBytes = 32768;                // xm planes (2 x 8 KB) / a0, a1 slice planes (2 x 16 KB) / partial staging
 constexpr int kXs = 49;                        // row stride of the fp32 x tile (odd: conflict-free column walks)
-constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + kXaBytes + NT * kXs * 4 + 1024 /*align*/;
+constexpr int kActMax = 24;                    // active (transformed) dims per layer the in-cluster exchange is sized for
+constexpr int kRecvBytes = 2 * kCluster * kActMax * 8 * 4;   // [parity][source CTA][active dim][8 rows] fp32
+constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + kXaBytes + NT * kXs * 4 + kRecvBytes + 1024 /*align*/;
 constexpr int kTmemCols = 512;                 // three accumulators of 128 columns: [0,64) = Ah.Bh + Al.Bh, [64,128) = Ah.Bl (summed in the epilogue)
 constexpr int kAcc0 = 0, kAcc1 = 128, kAcc2 = 256;
 
@@ -27,7 +29,7 @@ bool supported(const FlowLayout& L, int R) {
         const char* e = getenv("MHE_FUSED_MAX_ROWS");
         max_rows = e ? atoi(e) : 4096;
     }
-    return L.D <= 46 && L.D >= 4 && L.H == 512 && L.C % 8 == 0 && R <= max_rows;
+    return L.D <= 46 && L.D >= 4 && L.H == 512 && L.C % 8 == 0 && L.L <= 16 && R <= max_rows;
 }
 
 // ---- cluster / barrier primitives -----------------------------------------------------------------------------
@@ -39,6 +41,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
     uint32_t raddr;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_bar), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float a) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(a) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {        // acquire at cluster scope
@@ -83,16 +96,26 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {   // 64 co
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// 8 fp32 -> 8 hi + 8 lo 16-bit values packed as two uint4
+// 8 fp32 -> 8 hi + 8 lo 16-bit values packed as two uint4 (packed two-at-a-time conversions: this runs in every epilogue thread)
 template <bool F16>
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint16_t h0 = to16<F16>(v[2 * j]), h1 = to16<F16>(v[2 * j + 1]);
-        const uint16_t l0 = to16<F16>(v[2 * j] - from16<F16>(h0)), l1 = to16<F16>(v[2 * j + 1] - from16<F16>(h1));
-        h[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-        l[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        const float a = v[2 * j], b = v[2 * j + 1];
+        if (F16) {
+            const __half2 hh = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        } else {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -107,6 +130,20 @@ __device__ __forceinline__ float fast_tanh_f(float x) {   // 1 - 2/(e^{2x}+1); s
 
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define MHE_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[step * 64 + (slot)] = clock64(); } while (0)
+
+// Copy the CTA's slice (128 features x 64 rows, split planes, in xa: [k-block][hi | lo][64 k-rows][128 B], 16-byte chunks swizzled)
+// to the transposed global planes [plane][H][Rp]: 8 lanes write one 128-byte feature row, a warp four of them per instruction.
+__device__ __forceinline__ void copy_slice_to_global(uint32_t xa, bf16* gplanes, int H, int Rp, int f0, int r0, int t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = i * kWorkers + t;
+        const int pl = idx >> 10, row = (idx >> 3) & 127, cc = idx & 7;
+        const uint32_t sa = xa + (uint32_t)(row >> 6) * 16384u + (uint32_t)pl * 8192u + (uint32_t)(row & 63) * 128u + (uint32_t)((cc ^ (row & 7)) << 4);
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
+        *reinterpret_cast<uint4*>(gplanes + ((size_t)pl * H + f0 + row) * Rp + r0 + cc * 8) = v;
+    }
+}
 
 struct FwdArgs {
     const float* params; const float* mask; const float* cp; const float* in;
@@ -164,7 +201,9 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                       const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapA0, FwdArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_fullA[kASlots], bar_emptyA[kASlots], bar_fullB[kBSlots], bar_emptyB[kBSlots], bar_acc[3];
-    __shared__ __align__(8) uint64_t bar_xm, bar_own, bar_a1, bar_a0, bar_part;
+    __shared__ __align__(8) uint64_t bar_xm, bar_own, bar_a1, bar_a0, bar_part, bar_x;
+    __shared__ uint8_t actd[16][kActMax];       // per layer: the active (transformed) dims in ascending order
+    __shared__ int nact_s[16];
     __shared__ uint32_t tmem_slot;
     __shared__ float lds[NT];
     __shared__ uint64_t mbits[64];
@@ -172,6 +211,7 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ringA = smem0, ringB = ringA + kASlots * kABytes, xa = ringB + kBSlots * kBBytes;
     float* xs = reinterpret_cast<float*>(smem_raw + (xa - smem_u32(smem_raw)) + kXaBytes);   // [NT][kXs]
+    float* recv = xs + NT * kXs;                // [2 parities][8 source CTAs][kActMax][8 rows]: partial head outputs of this CTA's 8 rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int net = rank >> 2, j = rank & 3;
@@ -188,6 +228,7 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         mbar_init(smem_u32(&bar_own), 1);
         mbar_init(smem_u32(&bar_a0), 4);
         mbar_init(smem_u32(&bar_part), kCluster);
+        mbar_init(smem_u32(&bar_x), kCluster);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW1) : "memory");
@@ -334,7 +375,6 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         const uint32_t tm_lane = (uint32_t)(lq * 32) << 16;
         const int D = p.D;
         const int xn = t & 63, xq = t >> 6;                        // xm writer: row, quarter of the 64 padded dims
-        const int uq = t & 15, ug = t >> 4;                        // coupling: rows 4*uq.., dims ug + 16 i
         const uint32_t rowoff = (uint32_t)(fl >> 6) * 16384u + (uint32_t)(fl & 63) * 128u;  // k-row fl of the slice: [k-block][hi | lo][64 k-rows][128 B]
 
         // one thread polls the mbarrier, the others block on the named barrier: 256 spinning threads would fight the tensor core for the
@@ -398,6 +438,9 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             uint64_t mb = 0;
             for (int d = 0; d < D; ++d) mb |= (uint64_t)(p.mask[(size_t)t * D + d] != 0.f) << d;
             mbits[t] = mb;
+            int na = 0;
+            for (int d = 0; d < D; ++d) if (!((mb >> d) & 1) && na < kActMax) actd[t][na++] = (uint8_t)d;
+            nact_s[t] = na;
         }
         // load the row tile
         for (int i = t; i < NT * D; i += kWorkers) {
@@ -419,13 +462,12 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             const uint32_t par = step & 1;
             const uint64_t mb = mbits[layer];
             const int ab = (p.save ? step * 2 : 0) + net;           // batch index into a0T / a1T
-            // head biases of this thread's coupling dims (used in U; loaded now, off the critical path)
-            float bs3[3], bt3[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int d = min(ug + 16 * i, D - 1);
-                bs3[i] = __ldg(p.params + (size_t)(layer * 2 + 0) * p.blk + p.ob2 + d);
-                bt3[i] = __ldg(p.params + (size_t)(layer * 2 + 1) * p.blk + p.ob2 + d);
+            // head biases of this thread's coupling element (used in U; loaded now, off the critical path)
+            float b2s_pre = 0.f, b2t_pre = 0.f;
+            if ((t >> 3) < nact_s[layer]) {
+                const int d = actd[layer][t >> 3];
+                b2s_pre = __ldg(p.params + (size_t)(layer * 2 + 0) * p.blk + p.ob2 + d);
+                b2t_pre = __ldg(p.params + (size_t)(layer * 2 + 1) * p.blk + p.ob2 + d);
             }
             if (t == 0) { MHE_STAMP(0); if (p.dbg && blockIdx.x == 0) p.dbg[step * 64 + 60] = gtime(); }
             // ---------------- E0: a0 = lrelu(acc0 + cp0) -> shared slice (own k-blocks of G1) + global exchange buffer (peers' k-blocks)
@@ -436,12 +478,12 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 load_acc(kAcc0, v, p.two_mma & 1);
 #pragma unroll
                 for (int n = 0; n < 32; ++n) v[n] = lrelu(v[n] + c[n]);
-                uint4* ghi = reinterpret_cast<uint4*>(p.a0T + (((size_t)ab * 2 + 0) * p.H + f) * p.Rp + r0);
-                uint4* glo = reinterpret_cast<uint4*>(p.a0T + (((size_t)ab * 2 + 1) * p.H + f) * p.Rp + r0);
-                store_slice(v, ghi, glo);
+                store_slice(v, nullptr, nullptr);
                 tcgen05_fence_before();
                 worker_sync();
                 if (t == 0) { MHE_STAMP(3); mbar_arrive(smem_u32(&bar_own)); }   // the MMA warp may consume the own slice
+                copy_slice_to_global(xa, p.a0T + (size_t)ab * 2 * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
+                worker_sync();
                 if (t < 4) {   // publish the slice: the CTA barrier ordered every thread's stores before this cumulative fence
                     fence_proxy_async();
                     fence_cluster();
@@ -458,14 +500,18 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 load_acc(kAcc1, v, p.two_mma & 2);
 #pragma unroll
                 for (int n = 0; n < 32; ++n) v[n] = lrelu(v[n] + c[n]);
-                uint4* ghi = p.save ? reinterpret_cast<uint4*>(p.a1T + (((size_t)ab * 2 + 0) * p.H + f) * p.Rp + r0) : nullptr;
-                uint4* glo = p.save ? reinterpret_cast<uint4*>(p.a1T + (((size_t)ab * 2 + 1) * p.H + f) * p.Rp + r0) : nullptr;
-                store_slice(v, ghi, glo);
+                store_slice(v, nullptr, nullptr);
                 tcgen05_fence_before();
                 mbar_arrive(smem_u32(&bar_a1));
+                if (p.save) {   // saved for the backward; off the critical path (G2 only reads xa)
+                    worker_sync();
+                    copy_slice_to_global(xa, p.a1T + (size_t)ab * 2 * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
+                }
                 if (t == 0) MHE_STAMP(7);
             }
-            // ---------------- E2: partial head outputs of this CTA's feature slice -> global exchange buffer
+            // ---------------- E2: partial head outputs of this CTA's feature slice -> the CTA that owns the rows (DSMEM)
+            // Row ownership for the coupling: CTA c updates rows [8c, 8c+8) of the tile.  Thread (dim d, column half ch) holds rows
+            // 32 ch .. 32 ch + 31 of partial[d]: four 8-row groups for CTAs 4 ch .. 4 ch + 3.
             {
                 worker_wait(&bar_acc[2], par, false);
                 tcgen05_fence_after();
@@ -473,9 +519,16 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 if (lq < 2) {   // accumulator rows = flow dims: lanes 0..63
                     load_acc(kAcc2, v, p.two_mma & 8);
                     if (fl < D && !((mb >> fl) & 1)) {
-                        float4* dst = reinterpret_cast<float4*>(p.partial + ((((size_t)par * p.tiles + tile) * kCluster + rank) * kDp + fl) * NT + 32 * ch);
+                        const int ai = __popcll(~mb & ((1ull << fl) - 1ull));                 // index of this dim among the active ones
+                        if (ai < kActMax) {
+                            const uint32_t slot = smem_u32(recv) + (uint32_t)((((par * kCluster + rank) * kActMax + ai) * 8) * 4);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t ra = map_to_cta(slot, 4 * ch + q);
+                                st_cluster_v4(ra, v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]);
+                                st_cluster_v4(ra + 16, v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]);
+                            }
+                        }
                     }
                 }
                 tcgen05_fence_before();
@@ -483,63 +536,53 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
                 if (t == 0) MHE_STAMP(9);
             }
-            // ---------------- U: sum the partials, affine coupling, next layer's masked input
+            // ---------------- U: affine coupling of this CTA's 8 rows, results broadcast to every CTA's x tile (DSMEM)
             {
                 const bool last = step == p.L - 1;
                 const int next_layer = p.direction == 0 ? layer + 1 : layer - 1;
                 worker_wait(&bar_part, par, true);
                 if (t == 0) MHE_STAMP(10);
-                const float* pbase = p.partial + (((size_t)par * p.tiles + tile) * kCluster) * kDp * NT + uq * 4;
-                float4 pv[3][8];
-                bool act[3];
+                const int urow = t & 7, uai = t >> 3;          // row inside the CTA's group, active-dim index
+                if (uai < nact_s[layer]) {
+                    const int d = actd[layer][uai];
+                    const int n = 8 * (int)rank + urow;
+                    const float* rv = recv + ((size_t)(par * kCluster) * kActMax + uai) * 8 + urow;
+                    float sp = b2s_pre, tp = b2t_pre;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int d = ug + 16 * i;
-                    act[i] = d < D && !((mb >> d) & 1);
+                    for (int c4 = 0; c4 < 4; ++c4) { sp += rv[(size_t)c4 * kActMax * 8]; tp += rv[(size_t)(4 + c4) * kActMax * 8]; }
+                    const float sv = fast_tanh_f(sp);
+                    const float xv = xs[n * kXs + d];
+                    float y;
+                    if (p.direction == 0) { y = fmaf(xv, expf(sv), tp); atomicAdd(&lds[n], sv); }
+                    else { y = (xv - tp) * expf(-sv); atomicAdd(&lds[n], -sv); }
+                    const uint32_t xaddr = smem_u32(xs + n * kXs + d);
 #pragma unroll
-                    for (int cta = 0; cta < 8; ++cta)
-                        pv[i][cta] = act[i] ? __ldcg(reinterpret_cast<const float4*>(pbase + ((size_t)cta * kDp + d) * NT)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (!last) load_cp(c, 0, next_layer);                 // next layer's conditioning, in flight during the coupling
-                float ld4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    if (!act[i]) continue;
-                    const int d = ug + 16 * i;
-                    const float bs = bs3[i], bt = bt3[i];
-                    const float sv[4] = {pv[i][0].x + pv[i][1].x + pv[i][2].x + pv[i][3].x + bs, pv[i][0].y + pv[i][1].y + pv[i][2].y + pv[i][3].y + bs,
-                                         pv[i][0].z + pv[i][1].z + pv[i][2].z + pv[i][3].z + bs, pv[i][0].w + pv[i][1].w + pv[i][2].w + pv[i][3].w + bs};
-                    const float tv[4] = {pv[i][4].x + pv[i][5].x + pv[i][6].x + pv[i][7].x + bt, pv[i][4].y + pv[i][5].y + pv[i][6].y + pv[i][7].y + bt,
-                                         pv[i][4].z + pv[i][5].z + pv[i][6].z + pv[i][7].z + bt, pv[i][4].w + pv[i][5].w + pv[i][6].w + pv[i][7].w + bt};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = uq * 4 + k;
-                        const float s = fast_tanh_f(sv[k]);
-                        const float xv = xs[n * kXs + d];
-                        float y;
-                        if (p.direction == 0) { y = fmaf(xv, expf(s), tv[k]); ld4[k] += s; }
-                        else { y = (xv - tv[k]) * expf(-s); ld4[k] -= s; }
-                        xs[n * kXs + d] = y;
-                        if (p.save && (int)rank == (ug & 7) && r0 + n < p.R) {
-                            p.saved_st[((size_t)(step * 2 + 0) * p.R + r0 + n) * D + d] = s;
-                            p.saved_st[((size_t)(step * 2 + 1) * p.R + r0 + n) * D + d] = tv[k];
-                        }
+                    for (int c8 = 0; c8 < kCluster; ++c8) st_cluster_f32(map_to_cta(xaddr, c8), y);
+                    if (p.save && r0 + n < p.R) {
+                        p.saved_st[((size_t)(step * 2 + 0) * p.R + r0 + n) * D + d] = sv;
+                        p.saved_st[((size_t)(step * 2 + 1) * p.R + r0 + n) * D + d] = tp;
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (ld4[k] != 0.f) atomicAdd(&lds[uq * 4 + k], ld4[k]);
                 worker_sync();
+                if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_x), t); }
+                worker_wait(&bar_x, par, true);                // every CTA's rows of the new x have landed in this CTA's tile
                 if (t == 0) MHE_STAMP(11);
-                if (!last) write_xm(mbits[next_layer]);
+                if (!last) {
+                    write_xm(mbits[next_layer]);
+                    load_cp(c, 0, next_layer);                 // next layer's conditioning, in flight during G0
+                }
                 if (p.save && (int)rank == ((step + 1) & 7)) {
                     const int nvalid = min(NT, p.R - r0) * D;
                     float* dst = p.saved_x + (size_t)(step + 1) * p.R * D + (size_t)r0 * D;
                     for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; dst[i] = xs[n * kXs + d]; }
                 }
-                if (last && rank == 0) {
-                    const int nvalid = min(NT, p.R - r0) * D;
-                    for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; p.out[(size_t)r0 * D + i] = xs[n * kXs + d]; }
-                    if (p.logdet && t < NT && r0 + t < p.R) p.logdet[r0 + t] = lds[t];
+                if (last) {
+                    if (rank == 0) {
+                        const int nvalid = min(NT, p.R - r0) * D;
+                        for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; p.out[(size_t)r0 * D + i] = xs[n * kXs + d]; }
+                    }
+                    // every CTA holds the log-determinant of its own 8 rows
+                    if (p.logdet && t < 8 && r0 + 8 * (int)rank + t < p.R) p.logdet[r0 + 8 * rank + t] = lds[8 * rank + t];
                 }
             }
         }
@@ -757,7 +800,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             }
         };
         // 32 gradients of feature fl (rows 32 ch ..) masked by lrelu'(saved activation), as bfloat16 planes -> xa slice + global planes
-        auto store_grad_slice = [&](float* v, const uint4* sg, bf16* gplanes) {
+        auto store_grad_slice = [&](float* v, const uint4* sg) {
             uint32_t sw[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { sw[4 * i] = sg[i].x; sw[4 * i + 1] = sg[i].y; sw[4 * i + 2] = sg[i].z; sw[4 * i + 3] = sg[i].w; }
@@ -766,8 +809,6 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 const uint32_t e = (sw[n >> 1] >> ((n & 1) * 16)) & 0xFFFFu;      // saved half activation: > 0 <=> sign clear and non-zero
                 v[n] *= ((e & 0x8000u) == 0 && (e & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
             }
-            uint4* ghi = reinterpret_cast<uint4*>(gplanes + ((size_t)0 * p.H + f) * p.Rp + r0);
-            uint4* glo = reinterpret_cast<uint4*>(gplanes + ((size_t)1 * p.H + f) * p.Rp + r0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int cc = ch * 4 + i;
@@ -776,8 +817,6 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 const uint32_t off = rowoff + (uint32_t)((cc ^ (fl & 7)) << 4);
                 st_shared_v4(xa + off, hi);
                 st_shared_v4(xa + 8192 + off, lo);
-                ghi[cc] = hi;
-                glo[cc] = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         };
@@ -865,10 +904,12 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                     db2s[t] = 0.f;
                 }
                 load_acc(kAcc0, v);
-                store_grad_slice(v, sg, p.dh1T + gbatch * p.H * p.Rp);
+                store_grad_slice(v, sg);
                 tcgen05_fence_before();
                 worker_sync();
                 if (t == 0) mbar_arrive(smem_u32(&bar_own));
+                copy_slice_to_global(xa, p.dh1T + gbatch * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
+                worker_sync();
                 if (t < 4) {
                     fence_proxy_async();
                     fence_cluster();
@@ -884,9 +925,11 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 worker_wait(&bar_acc[1], par, false);
                 tcgen05_fence_after();
                 load_acc(kAcc1, v);
-                store_grad_slice(v, sg, p.dh0T + gbatch * p.H * p.Rp);
+                store_grad_slice(v, sg);
                 tcgen05_fence_before();
                 mbar_arrive(smem_u32(&bar_a1));
+                worker_sync();      // kept for the weight gradients; off the critical path (bG0 only reads xa)
+                copy_slice_to_global(xa, p.dh0T + gbatch * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
             }
             // ---------------- bE0: partial input gradients of this CTA's feature slice -> global exchange buffer
             {
