@@ -621,14 +621,17 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                       const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapDh1, BwdArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_fullA[kASlots], bar_emptyA[kASlots], bar_fullB[kBSlots], bar_emptyB[kBSlots], bar_acc[3];
-    __shared__ __align__(8) uint64_t bar_xm, bar_own, bar_a1, bar_a0, bar_part;
+    __shared__ __align__(8) uint64_t bar_xm, bar_own, bar_a1, bar_a0, bar_part, bar_dpre;
     __shared__ uint32_t tmem_slot;
-    __shared__ float gls[NT], db2s[kDp];
+    __shared__ float gls[8];
     __shared__ uint64_t mbits[64];
+    __shared__ uint8_t actd[16][kActMax], pasd[16][kActMax];   // per layer: transformed / conditioning dims, ascending
+    __shared__ int nact_s[16], npas_s[16];
 
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ringA = smem0, ringB = ringA + kASlots * kABytes, xa = ringB + kBSlots * kBBytes;
-    float* gs = reinterpret_cast<float*>(smem_raw + (xa - smem_u32(smem_raw)) + kXaBytes);   // [NT][kXs] gradient tile
+    float* gs = reinterpret_cast<float*>(smem_raw + (xa - smem_u32(smem_raw)) + kXaBytes);   // [8][kXs]: gradient rows this CTA owns (rows 8 rank ..)
+    float* recv = gs + NT * kXs;                // [2 parities][8 source CTAs][kActMax][8 rows]: partial input gradients of the owned rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int net = rank >> 2, j = rank & 3;
@@ -640,11 +643,12 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         for (int s = 0; s < kASlots; ++s) { mbar_init(smem_u32(&bar_fullA[s]), 1); mbar_init(smem_u32(&bar_emptyA[s]), 1); }
         for (int s = 0; s < kBSlots; ++s) { mbar_init(smem_u32(&bar_fullB[s]), 1); mbar_init(smem_u32(&bar_emptyB[s]), 1); }
         for (int s = 0; s < 3; ++s) mbar_init(smem_u32(&bar_acc[s]), 1);
-        mbar_init(smem_u32(&bar_xm), kWorkers);
+        mbar_init(smem_u32(&bar_xm), 1);
         mbar_init(smem_u32(&bar_a1), kWorkers);
         mbar_init(smem_u32(&bar_own), 1);
         mbar_init(smem_u32(&bar_a0), 4);
         mbar_init(smem_u32(&bar_part), kCluster);
+        mbar_init(smem_u32(&bar_dpre), kCluster);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW1) : "memory");
@@ -777,13 +781,17 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         }
     } else {
         // ===================== workers (256 threads)
+        // Row ownership: CTA c owns rows [8c, 8c+8) of the tile.  The owner keeps their gradient g, sums the partial input gradients the
+        // eight CTAs send it (DSMEM), runs the coupling backward for them and writes the head gradients straight into the shared-memory
+        // B tiles of the CTAs of each net (DSMEM), so no CTA repeats the elementwise work and nothing goes through global memory.
         const int t = threadIdx.x;
         const int lq = warp & 3, ch = warp >> 2;
         const int fl = lq * 32 + lane;
         const int f = j * FS + fl;
         const uint32_t tm_lane = (uint32_t)(lq * 32) << 16;
         const int D = p.D;
-        const int uq = t & 15, ug = t >> 4;                        // coupling: rows 4*uq.., dims ug + 16 i
+        const int urow = t & 7, uk = t >> 3;                       // owned row, index into the active / passive dim lists
+        const int own_n = 8 * (int)rank + urow, own_r = r0 + own_n;
         const uint32_t rowoff = (uint32_t)(fl >> 6) * 16384u + (uint32_t)(fl & 63) * 128u;
 
         auto worker_wait = [&](uint64_t* bar, uint32_t parity, bool cluster_scope) {
@@ -799,7 +807,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 for (int n = 0; n < 32; ++n) v[n] += w[n];
             }
         };
-        // 32 gradients of feature fl (rows 32 ch ..) masked by lrelu'(saved activation), as bfloat16 planes -> xa slice + global planes
+        // 32 gradients of feature fl (rows 32 ch ..) masked by lrelu'(saved activation), as bfloat16 planes -> xa slice
         auto store_grad_slice = [&](float* v, const uint4* sg) {
             uint32_t sw[16];
 #pragma unroll
@@ -820,19 +828,80 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         };
+        auto zero_dpre_tile = [&]() {   // K-major dpre tile (both planes, 16 KB): dims / rows nobody writes stay zero
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st_shared_v4(xa + (uint32_t)(t * 4 + i) * 16u, z);
+        };
+        // coupling backward of the owned row for the `step` about to run: g -> direct path in place, head gradients -> the nets' CTAs
+        auto owner_coupling = [&](int step, int layer) {
+            const bool on = uk < nact_s[layer];
+            const int d = on ? actd[layer][uk] : 0;
+            float ds = 0.f, dt = 0.f;
+            if (on && own_r < p.R) {
+                const float g = gs[urow * kXs + d];
+                const float xv = __ldg(p.saved_x + ((size_t)step * p.R + own_r) * D + d);
+                const float s = __ldg(p.saved_st + ((size_t)(step * 2 + 0) * p.R + own_r) * D + d);
+                const float tt = __ldg(p.saved_st + ((size_t)(step * 2 + 1) * p.R + own_r) * D + d);
+                const float gl = gls[urow];
+                float dx;
+                if (p.direction == 0) { const float e = expf(s); dx = g * e; dt = g; ds = g * xv * e + gl; }
+                else { const float e = expf(-s); dx = g * e; dt = -g * e; ds = -g * (xv - tt) * e - gl; }
+                ds *= (1.f - s * s);
+                gs[urow * kXs + d] = dx;
+            }
+            // element (row own_n, dim d) of the K-major [64 rows][64 dims] bfloat16 planes of every CTA of the net
+            const uint32_t off = (uint32_t)(own_n >> 3) * 1024u + (uint32_t)(own_n & 7) * 128u + (uint32_t)(((d >> 3) ^ (own_n & 7)) << 4) + (uint32_t)(d & 7) * 2u;
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn) {
+                const float dv = nn == 0 ? ds : dt;
+                const uint16_t h = to16<false>(dv), l = to16<false>(dv - from16<false>(h));
+                if (on) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const uint32_t ra = map_to_cta(xa + off, nn * 4 + c4);
+                        asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(ra), "h"(h) : "memory");
+                        asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(ra + 8192), "h"(l) : "memory");
+                    }
+                    // dpre^T planes for the W2 weight gradient
+                    uint16_t* gp = reinterpret_cast<uint16_t*>(p.dpreT) + ((size_t)((layer * 2 + nn) * 2) * kDp + d) * p.Rp + own_r;
+                    gp[0] = h;
+                    gp[(size_t)kDp * p.Rp] = l;
+                }
+                // bias gradient: sum over the 8 owned rows = 8 adjacent lanes (all lanes take part in the shuffles)
+                float sum = dv;
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                if (on && urow == 0) atomicAdd(p.dparams + (size_t)(layer * 2 + nn) * p.blk + p.ob2 + d, sum);
+            }
+            worker_sync();
+            if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_dpre), t); }
+        };
 
         if (t < p.L) {
             uint64_t mb = 0;
             for (int d = 0; d < D; ++d) mb |= (uint64_t)(p.mask[(size_t)t * D + d] != 0.f) << d;
             mbits[t] = mb;
+            int na = 0, np = 0;
+            for (int d = 0; d < D; ++d) {
+                if ((mb >> d) & 1) { if (np < kActMax) pasd[t][np++] = (uint8_t)d; }
+                else if (na < kActMax) actd[t][na++] = (uint8_t)d;
+            }
+            nact_s[t] = na; npas_s[t] = np;
         }
-        for (int i = t; i < NT * D; i += kWorkers) {
+        for (int i = t; i < 8 * D; i += kWorkers) {
             const int n = i / D, d = i - n * D;
-            gs[n * kXs + d] = (r0 + n < p.R) ? p.dout[(size_t)(r0 + n) * D + d] : 0.f;
+            const int r = r0 + 8 * (int)rank + n;
+            gs[n * kXs + d] = r < p.R ? p.dout[(size_t)r * D + d] : 0.f;
         }
-        if (t < NT) gls[t] = (p.dlogdet && r0 + t < p.R) ? p.dlogdet_scale * p.dlogdet[r0 + t] : 0.f;
-        if (t < kDp) db2s[t] = 0.f;
+        if (t < 8) { const int r = r0 + 8 * (int)rank + t; gls[t] = (p.dlogdet && r < p.R) ? p.dlogdet_scale * p.dlogdet[r] : 0.f; }
+        zero_dpre_tile();
         worker_sync();
+        // every CTA's dpre tile is zeroed before any owner writes into it: cluster-wide rendezvous of the worker warps via bar_part
+        if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
+        worker_wait(&bar_part, 0, true);
+        owner_coupling(p.L - 1, p.direction == 0 ? p.L - 1 : 0);
 
         float v[32];
         for (int step = p.L - 1; step >= 0; --step) {
@@ -842,67 +911,20 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             const uint64_t mb = mbits[layer];
             const size_t sbatch = (size_t)(step * 2 + net) * 2;    // plane index base of the saved activations (indexed by step)
             const size_t gbatch = (size_t)(layer * 2 + net) * 2;   // ... of the gradient planes (indexed by layer, like the parameters)
-            // ---------------- bU: coupling backward on the tile (every CTA, redundantly), dpre of the CTA's net -> xa (K-major planes)
-            {
-                // zero the K-major dpre tile (both planes, 16 KB): passive and padded dims stay zero
-                {
-                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) st_shared_v4(xa + (uint32_t)(t * 4 + i) * 16u, z);
-                }
-                worker_sync();
-                float dsum[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int d = ug + 16 * i;
-                    if (d >= D) continue;
-                    if ((mb >> d) & 1) continue;                      // passive dim: g passes through unchanged, no head gradient
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = uq * 4 + k, r = r0 + n;
-                        float dpre = 0.f;
-                        if (r < p.R) {
-                            const float g = gs[n * kXs + d];
-                            const float xv = __ldg(p.saved_x + ((size_t)step * p.R + r) * D + d);
-                            const float s = __ldg(p.saved_st + ((size_t)(step * 2 + 0) * p.R + r) * D + d);
-                            const float tt = __ldg(p.saved_st + ((size_t)(step * 2 + 1) * p.R + r) * D + d);
-                            const float gl = gls[n];
-                            float dx, ds, dt;
-                            if (p.direction == 0) { const float e = expf(s); dx = g * e; dt = g; ds = g * xv * e + gl; }
-                            else { const float e = expf(-s); dx = g * e; dt = -g * e; ds = -g * (xv - tt) * e - gl; }
-                            ds *= (1.f - s * s);
-                            gs[n * kXs + d] = dx;
-                            dpre = net == 0 ? ds : dt;
-                        }
-                        dsum[i] += dpre;
-                        // K-major [64 rows][64 dims] planes: element (n, d)
-                        const uint16_t h = to16<false>(dpre), l = to16<false>(dpre - from16<false>(h));
-                        const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u + (uint32_t)(((d >> 3) ^ (n & 7)) << 4) + (uint32_t)(d & 7) * 2u;
-                        asm volatile("st.shared.b16 [%0], %1;" ::"r"(xa + off), "h"(h) : "memory");
-                        asm volatile("st.shared.b16 [%0], %1;" ::"r"(xa + 8192 + off), "h"(l) : "memory");
-                        if (j == 0) {   // one CTA per net keeps dpre^T for the W2 weight gradient: [d][row] planes
-                            uint16_t* gp = reinterpret_cast<uint16_t*>(p.dpreT) + ((gbatch + 0) * kDp + d) * p.Rp + r0 + n;
-                            gp[0] = h;
-                            gp[(size_t)kDp * p.Rp] = l;
-                        }
-                    }
-                    if (j == 0) atomicAdd(&db2s[d], dsum[i]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(smem_u32(&bar_xm));
-            }
-            // ---------------- bE2: dh1 = acc0 * lrelu'(a1) -> xa slice + global dh1T (exchange, weight gradients)
+            // ---------------- the head gradients of all 64 rows have been written into xa by their owners
             {
                 uint4 sg[4];
                 const uint4* sp = reinterpret_cast<const uint4*>(p.a1T + ((sbatch + 0) * p.H + f) * p.Rp + r0 + 32 * ch);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) sg[i] = __ldg(sp + i);
+                if (t == 0) {
+                    mbar_wait_cluster(smem_u32(&bar_dpre), par);
+                    fence_proxy_async();                               // the tile was written through the generic proxy (by peers)
+                    mbar_arrive(smem_u32(&bar_xm));
+                }
+                // ---------------- bE2: dh1 = acc0 * lrelu'(a1) -> xa slice + global dh1T (exchange, weight gradients)
                 worker_wait(&bar_acc[0], par, false);
                 tcgen05_fence_after();
-                if (j == 0 && t < D && !((mb >> t) & 1)) {   // db2 += column sums of dpre (bU finished: every worker passed the barrier)
-                    atomicAdd(p.dparams + (size_t)(layer * 2 + net) * p.blk + p.ob2 + t, db2s[t]);
-                    db2s[t] = 0.f;
-                }
                 load_acc(kAcc0, v);
                 store_grad_slice(v, sg);
                 tcgen05_fence_before();
@@ -931,45 +953,49 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 worker_sync();      // kept for the weight gradients; off the critical path (bG0 only reads xa)
                 copy_slice_to_global(xa, p.dh0T + gbatch * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
             }
-            // ---------------- bE0: partial input gradients of this CTA's feature slice -> global exchange buffer
+            // ---------------- bE0: partial input gradients of this CTA's feature slice -> the CTAs that own the rows (DSMEM)
             {
                 worker_wait(&bar_acc[2], par, false);
                 tcgen05_fence_after();
                 if (lq < 2) {   // accumulator rows = flow dims
                     load_acc(kAcc2, v);
                     if (fl < D && ((mb >> fl) & 1)) {   // only the dims the nets read (mask = 1) receive this gradient
-                        float4* dst = reinterpret_cast<float4*>(p.partial + ((((size_t)par * p.tiles + tile) * kCluster + rank) * kDp + fl) * NT + 32 * ch);
+                        const int pi = __popcll(mb & ((1ull << fl) - 1ull));
+                        if (pi < kActMax) {
+                            const uint32_t slot = smem_u32(recv) + (uint32_t)(((((1 - (int)par) * kCluster + rank) * kActMax + pi) * 8) * 4);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t ra = map_to_cta(slot, 4 * ch + q);
+                                st_cluster_v4(ra, v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]);
+                                st_cluster_v4(ra + 16, v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]);
+                            }
+                        }
                     }
                 }
                 tcgen05_fence_before();
+                zero_dpre_tile();                                      // bG0 is done with xa; the owners refill the tile for the next layer
                 worker_sync();
                 if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
             }
-            // ---------------- combine: g[n][d] += sum over the 8 CTAs of the partials (conditioning dims), g becomes dL/d(layer input)
+            // ---------------- owner: g[row][d] += sum over the 8 CTAs of the partials (conditioning dims), then the next layer's coupling
             {
-                worker_wait(&bar_part, par, true);
-                const float* pbase = p.partial + (((size_t)par * p.tiles + tile) * kCluster) * kDp * NT + uq * 4;
+                worker_wait(&bar_part, 1 - par, true);                 // completion it + 1 of bar_part (completion 0 was the start rendezvous)
+                if (uk < npas_s[layer]) {
+                    const int d = pasd[layer][uk];
+                    const float* rv = recv + ((size_t)((1 - (int)par) * kCluster) * kActMax + uk) * 8 + urow;
+                    float a = 0.f;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int d = ug + 16 * i;
-                    if (d >= D || !((mb >> d) & 1)) continue;
-                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int cta = 0; cta < 8; ++cta) {
-                        const float4 q4 = __ldcg(reinterpret_cast<const float4*>(pbase + ((size_t)cta * kDp + d) * NT));
-                        a4.x += q4.x; a4.y += q4.y; a4.z += q4.z; a4.w += q4.w;
-                    }
-                    gs[(uq * 4 + 0) * kXs + d] += a4.x; gs[(uq * 4 + 1) * kXs + d] += a4.y;
-                    gs[(uq * 4 + 2) * kXs + d] += a4.z; gs[(uq * 4 + 3) * kXs + d] += a4.w;
+                    for (int c8 = 0; c8 < kCluster; ++c8) a += rv[(size_t)c8 * kActMax * 8];
+                    gs[urow * kXs + d] += a;
                 }
                 worker_sync();
+                if (step > 0) owner_coupling(step - 1, p.direction == 0 ? step - 1 : p.L - step);
             }
         }
-        if (rank == 0) {
-            const int nvalid = min(NT, p.R - r0) * D;
-            for (int i = t; i < nvalid; i += kWorkers) { const int n = i / D, d = i - n * D; p.din[(size_t)r0 * D + i] = gs[n * kXs + d]; }
+        for (int i = t; i < 8 * D; i += kWorkers) {   // every CTA writes the rows it owns
+            const int n = i / D, d = i - n * D;
+            const int r = r0 + 8 * (int)rank + n;
+            if (r < p.R) p.din[(size_t)r * D + d] = gs[n * kXs + d];
         }
     }
     tcgen05_fence_before();
