@@ -117,10 +117,13 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
                       float* din, float* dparams, float* dcp,
                       void* workspace, size_t workspace_bytes, void* stream);
 
-/* Asynchronous weight gradients (optional).  After mhe_flow_set_async(1), mhe_flow_pass_bwd may return while its weight-gradient
- * GEMMs (the dparams W0/W1/W2 slots) still run on internal streams, so that the caller can enqueue independent work (the
- * conditioning backward only needs dcp); mhe_flow_join(stream) makes `stream` wait for them and must be called before dparams
- * is read or the captured graph ends.  Default: off (pass_bwd joins before returning).                                      */
+/* Gradient-accumulation options (bit set; default 0).
+ *   bit 0  asynchronous weight gradients: mhe_flow_pass_bwd may return while its weight-gradient GEMMs (the dparams W0/W1/W2
+ *          slots) still run on internal streams, so that the caller can enqueue independent work (the conditioning backward only
+ *          needs dcp); mhe_flow_join(stream) makes `stream` wait for them and must be called before dparams is read or the
+ *          captured graph ends.
+ *   bit 1  the caller promises that the WEIGHT slots of dparams (W0, W1, W2, Cw) are zero when mhe_flow_pass_bwd /
+ *          mhe_flow_cond_bwd run: their epilogues then store instead of read-modify-write (bias slots always accumulate).      */
 int mhe_flow_set_async(int on);
 int mhe_flow_join(void* stream);
 

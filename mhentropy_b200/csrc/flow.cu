@@ -484,7 +484,11 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
     return MHE_OK;
 }
 
-int mhe_flow_set_async(int on) { fused::set_async_wgrad(on); return MHE_OK; }
+int mhe_flow_set_async(int on) {
+    fused::set_async_wgrad(on & 1);
+    tcflow::set_grads_are_zero((on >> 1) & 1);
+    return MHE_OK;
+}
 int mhe_flow_join(void* stream) { return fused::join((cudaStream_t)stream); }
 
 int mhe_std_normal_logp_fwd(const float* z, const float* logdet, float logdet_sign, int R, int D, float* logp, void* stream) {

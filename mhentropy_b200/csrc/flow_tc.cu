@@ -100,7 +100,7 @@ struct EpiMaskAtomicAdd {   // gx[row][col] += mask[col] * acc, col < D
 };
 struct EpiWgrad {   // dW[batch][row][col] += acc, col < ncols  (staged: lanes along the columns; loads batched before stores)
     static constexpr bool kDirect = false, kStaged = true, kRmw = true;
-    float* dW; long ld; long batch_stride; int ncols; int atomic;
+    float* dW; long ld; long batch_stride; int ncols; int atomic; int overwrite = 0;
     __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
     __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
     __device__ float* rmw_ptr(int b, int row0, int col, long& stride) const {
@@ -110,9 +110,14 @@ struct EpiWgrad {   // dW[batch][row][col] += acc, col < ncols  (staged: lanes a
 };
 struct EpiWgradT {   // element (row, col) goes to dW[batch][col][row]: lanes = rows are already contiguous in memory
     static constexpr bool kDirect = true, kStaged = false, kRmw = false;
-    float* dW; long ld; long batch_stride; int ncols; int atomic;
+    float* dW; long ld; long batch_stride; int ncols; int atomic; int overwrite = 0;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
         float* base = dW + (long)b * batch_stride + row;
+        if (overwrite && !atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (col0 + j < ncols) base[(long)(col0 + j) * ld] = v[j];
+            return;
+        }
         if (atomic) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (col0 + j < ncols) atomicAdd(base + (long)(col0 + j) * ld, v[j]);
@@ -276,13 +281,17 @@ static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const E
     return launch_tc_gemm<64, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
 }
 
+static int g_grads_zero = 0;
+void set_grads_are_zero(int on) { g_grads_zero = on; }
+bool grads_are_zero() { return g_grads_zero != 0; }
+
 int wgrad_kmajor(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, float* dW, long ld, long batch_stride, int ncols, int transposed,
                  cudaStream_t stream, const char* what) {
     if (transposed) {
-        EpiWgradT e{dW, ld, batch_stride, ncols, g.ksplit > 1};
+        EpiWgradT e{dW, ld, batch_stride, ncols, g.ksplit > 1, grads_are_zero() && g.ksplit == 1};
         return gemm<false, false, false>(A, B, g, e, stream, what);
     }
-    EpiWgrad e{dW, ld, batch_stride, ncols, g.ksplit > 1};
+    EpiWgrad e{dW, ld, batch_stride, ncols, g.ksplit > 1, grads_are_zero() && g.ksplit == 1};
     return gemm<false, false, false>(A, B, g, e, stream, what);
 }
 
@@ -356,7 +365,7 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
-        EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0};
+        EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
         MHE_TRY((gemm<true, true, false>(A, Bt, g, e, stream, "tc cond wgrad")));
     }
     cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, stream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);

@@ -84,6 +84,11 @@ inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
 
 // dW[batch] (+)= A[batch] . B[batch]^T for K-major bfloat16 plane operands (A: [M rows][K], B: [N rows][K]); rows of dW have pitch ld.
 // transposed != 0 stores element (m, n) at dW[n][m] instead.
+// The caller may promise that the weight slots of dparams are zero when the backward entry points run (mhe_flow_set_async bit 1):
+// the weight-gradient epilogues then store instead of read-modify-write.
+void set_grads_are_zero(int on);
+bool grads_are_zero();
+
 int wgrad_kmajor(const tc::PlaneTensor& A, const tc::PlaneTensor& B, tc::GemmShape g, float* dW, long ld, long batch_stride, int ncols,
                  int transposed, cudaStream_t stream, const char* what);
 

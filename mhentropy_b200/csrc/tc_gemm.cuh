@@ -285,6 +285,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (p0 && rows > 0) {
                         if (epi.atomic) {
                             for (int rr = 0; rr < rows; ++rr) atomicAdd(p0 + rr * stride, st[rr][lane]);
+                        } else if (epi.overwrite) {   // the destination is known to be zero: store, no read
+#pragma unroll
+                            for (int rr = 0; rr < 32; ++rr) if (rr < rows) p0[rr * stride] = st[rr][lane];
                         } else {
                             float old[32];
 #pragma unroll

@@ -119,14 +119,15 @@ class TrainStep:
         # log_q = log N(z0) - logdet  ->  dL/dlogdet = -dL/dlog_q
         # the weight-gradient GEMMs of the pass keep running on the library's streams while the conditioning backward (which only
         # needs dcp) is enqueued; mhe_flow_join() brings them back before the step ends
-        check(L.mhe_flow_set_async(1), 'set_async')
+        # (bit 1: dflat was zeroed at the start of the step, so the weight-gradient epilogues may store instead of accumulate)
+        check(L.mhe_flow_set_async(3), 'set_async')
         try:
             check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
                                       ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
+            check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), pk, ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat),
+                                      cws, cwsb, s), 'cond_bwd')
         finally:
             check(L.mhe_flow_set_async(0), 'set_async')
-        check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), pk, ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat),
-                                  cws, cwsb, s), 'cond_bwd')
         check(L.mhe_flow_join(s), 'flow_join')
         torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
 
@@ -146,7 +147,7 @@ class TrainStep:
             self.launches_per_step = lib().mhe_kernel_launch_count() - n0
             return self.loss
         if self.graph is None:
-            side = torch.cuda.Stream(self.dev)
+            side = torch.cuda.Stream(self.dev, priority=-1)   # the step's critical chain outranks the library's weight-gradient streams
             side.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(side):
                 self._enqueue()                      # warm-up outside capture
@@ -154,7 +155,7 @@ class TrainStep:
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
             n0 = lib().mhe_kernel_launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):
                 self._enqueue()
             self.launches_per_step = lib().mhe_kernel_launch_count() - n0
             self.graph = g
