@@ -54,20 +54,52 @@ struct WarpPose {
     float R[kJ][9], J[kJ][3], Gr[kJ][9], Gt[kJ][3], A[kJ][12];
     float dGr[kJ][9], dGt[kJ][3], dJ[kJ][3], dR[kJ][9], dpose[kPose];
     float dA[kJ][12], dpm[kWsPm], dGt_out[kJ * 3], T[12], red[8];
+    float th[48], be[12];
 };
 constexpr int kPoseWarps = 4;
 
-__device__ __forceinline__ void pose_fwd_warp(const mhe_mano_consts& c, const float* __restrict__ theta, const float* __restrict__ beta,
+// Small constants of the pose / tip path, staged once per block in shared memory: the per-row work is a long chain of short
+// dependent steps, and with a handful of warps per SM every global-memory round trip in it is exposed latency.
+struct PoseTables {
+    float comps[45 * 45], hands_mean[48], jt[kJ * 3], js[kJ * 3 * kShape];
+    float ptip[5][kPoseMap][3], stip[5][3][kShape], vtip[5][4], wtip[5][kJ];
+};
+__device__ __forceinline__ void stage_pose_tables(const mhe_mano_consts& c, PoseTables& T, bool tips) {
+    const int t = threadIdx.x, n = blockDim.x;
+    for (int i = t; i < 45 * 45; i += n) T.comps[i] = __ldg(c.comps + i);
+    for (int i = t; i < 45; i += n) T.hands_mean[i] = __ldg(c.hands_mean + i);
+    for (int i = t; i < kJ * 3; i += n) T.jt[i] = __ldg(c.jt + i);
+    for (int i = t; i < kJ * 3 * kShape; i += n) T.js[i] = __ldg(c.js + i);
+    if (tips) {
+        for (int i = t; i < 5 * kPoseMap * 3; i += n) {
+            const int tip = i / (kPoseMap * 3), k = (i / 3) % kPoseMap, cc = i % 3;
+            T.ptip[tip][k][cc] = __ldg(c.posedirs_t + (long)k * kVC + c_tip_vert[tip] * 3 + cc);
+        }
+        for (int i = t; i < 5 * 3 * kShape; i += n) {
+            const int tip = i / (3 * kShape), cc = (i / kShape) % 3, b = i % kShape;
+            T.stip[tip][cc][b] = __ldg(c.shapedirs + (c_tip_vert[tip] * 3 + cc) * kShape + b);
+        }
+        for (int i = t; i < 15; i += n) T.vtip[i / 3][i % 3] = __ldg(c.v_template + c_tip_vert[i / 3] * 3 + i % 3);
+        for (int i = t; i < 5 * kJ; i += n) T.wtip[i / kJ][i % kJ] = __ldg(c.weights + c_tip_vert[i / kJ] * kJ + i % kJ);
+    }
+}
+
+__device__ __forceinline__ void pose_fwd_warp(const PoseTables& T, const float* __restrict__ theta_g, const float* __restrict__ beta_g,
                                               WarpPose& W, int lane) {
+    for (int i = lane; i < 48; i += 32) W.th[i] = theta_g[i];
+    if (lane < kShape) W.be[lane] = beta_g[lane];
+    __syncwarp();
+    const float* theta = W.th;
+    const float* beta = W.be;
     for (int j = lane; j < 45; j += 32) {
-        float acc = __ldg(c.hands_mean + j);
-        for (int k = 0; k < 45; ++k) acc = fmaf(theta[3 + k], __ldg(c.comps + k * 45 + j), acc);
+        float acc = T.hands_mean[j];
+        for (int k = 0; k < 45; ++k) acc = fmaf(theta[3 + k], T.comps[k * 45 + j], acc);
         W.pose[3 + j] = acc;
     }
     if (lane < 3) W.pose[lane] = theta[lane];
     for (int i = lane; i < kJ * 3; i += 32) {
-        float acc = __ldg(c.jt + i);
-        for (int b = 0; b < kShape; ++b) acc = fmaf(__ldg(c.js + i * kShape + b), beta[b], acc);
+        float acc = T.jt[i];
+        for (int b = 0; b < kShape; ++b) acc = fmaf(T.js[i * kShape + b], beta[b], acc);
         W.J[i / 3][i % 3] = acc;
     }
     __syncwarp();
@@ -98,27 +130,27 @@ __device__ __forceinline__ void pose_fwd_warp(const mhe_mano_consts& c, const fl
     __syncwarp();
 }
 
-// blend shapes + LBS of tip vertex v by a whole warp: vp (3) and T (12, in W.T) are left in every lane / smem
-__device__ __forceinline__ void tip_skin_warp(const mhe_mano_consts& c, int v, const float* __restrict__ beta, WarpPose& W, int lane, float* vp) {
+// blend shapes + LBS of tip vertex `tip` by a whole warp: vp (3) and T (12, in W.T) are left in every lane / smem
+__device__ __forceinline__ void tip_skin_warp(const PoseTables& T, int tip, WarpPose& W, int lane, float* vp) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int k = lane; k < kPoseMap; k += 32) {
         const float p = W.R[1 + k / 9][k % 9] - ((k % 9) % 4 == 0 ? 1.f : 0.f);
-        a0 = fmaf(__ldg(c.posedirs_t + (long)k * kVC + v * 3 + 0), p, a0);
-        a1 = fmaf(__ldg(c.posedirs_t + (long)k * kVC + v * 3 + 1), p, a1);
-        a2 = fmaf(__ldg(c.posedirs_t + (long)k * kVC + v * 3 + 2), p, a2);
+        a0 = fmaf(T.ptip[tip][k][0], p, a0);
+        a1 = fmaf(T.ptip[tip][k][1], p, a1);
+        a2 = fmaf(T.ptip[tip][k][2], p, a2);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     float sh[3];
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) {
-        float acc = __ldg(c.v_template + v * 3 + cc);
-        for (int b = 0; b < kShape; ++b) acc = fmaf(__ldg(c.shapedirs + (v * 3 + cc) * kShape + b), beta[b], acc);
+        float acc = T.vtip[tip][cc];
+        for (int b = 0; b < kShape; ++b) acc = fmaf(T.stip[tip][cc][b], W.be[b], acc);
         sh[cc] = acc;
     }
     vp[0] = sh[0] + a0; vp[1] = sh[1] + a1; vp[2] = sh[2] + a2;
     if (lane < 12) {
         float t = 0.f;
-        for (int k = 0; k < kJ; ++k) t = fmaf(__ldg(c.weights + v * kJ + k), W.A[k][lane], t);
+        for (int k = 0; k < kJ; ++k) t = fmaf(T.wtip[tip][k], W.A[k][lane], t);
         W.T[lane] = t;
     }
     __syncwarp();
@@ -132,12 +164,15 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_fwd_kernel(mhe_mano
                                      float* __restrict__ pm, float* __restrict__ A, float* __restrict__ cen,
                                      float* __restrict__ jtr) {
     __shared__ WarpPose s_w[kPoseWarps];
+    __shared__ PoseTables s_t;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * kPoseWarps + warp;
+    stage_pose_tables(c, s_t, tips != 0);
+    __syncthreads();
     if (r >= R) return;
     WarpPose& W = s_w[warp];
     const float* be = beta + (long)r * ld_beta;
-    pose_fwd_warp(c, theta + (long)r * ld_theta, be, W, lane);
+    pose_fwd_warp(s_t, theta + (long)r * ld_theta, be, W, lane);
     if (pm) for (int k = lane; k < kPoseMap; k += 32) pm[(long)r * kWsPm + k] = W.R[1 + k / 9][k % 9] - ((k % 9) % 4 == 0 ? 1.f : 0.f);
     if (A) for (int i = lane; i < kWsA; i += 32) A[(long)r * kWsA + i] = W.A[i / 12][i % 12];
     if (cen && lane < 3) cen[(long)r * kWsCen + lane] = W.Gt[kCenterJoint][lane];
@@ -149,7 +184,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_fwd_kernel(mhe_mano
         if (tips) {
             for (int t = 0; t < 5; ++t) {
                 float vp[3];
-                tip_skin_warp(c, c_tip_vert[t], be, W, lane, vp);
+                tip_skin_warp(s_t, t, W, lane, vp);
                 if (lane < 3) {
                     const float o = (W.T[lane * 3 + 0] * vp[0] + W.T[lane * 3 + 1] * vp[1] + W.T[lane * 3 + 2] * vp[2] + W.T[9 + lane] - W.Gt[kCenterJoint][lane]) * kMM;
                     for (int i = 0; i < kNJ; ++i) if (c_jtr_src[order][i] == kJ + t) jtr[((long)r * kNJ + i) * 3 + lane] = o;
@@ -383,12 +418,15 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
                                      const float* __restrict__ dbv_g, const float* __restrict__ dcen_g,
                                      float* __restrict__ dtheta, int ld_dtheta, float* __restrict__ dbeta, int ld_dbeta, int accumulate) {
     __shared__ WarpPose s_w[kPoseWarps];
+    __shared__ PoseTables s_t;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * kPoseWarps + warp;
+    stage_pose_tables(c, s_t, tips_in_kernel != 0);
+    __syncthreads();
     if (r >= R) return;
     WarpPose& W = s_w[warp];
     const float* be = beta + (long)r * ld_beta;
-    pose_fwd_warp(c, theta + (long)r * ld_theta, be, W, lane);
+    pose_fwd_warp(s_t, theta + (long)r * ld_theta, be, W, lane);
 
     // vertex-side gradients -> W.dA, W.dpm, dbeta seed, centre gradient
     float db = 0.f;                       // lane b < 10 owns dbeta[b]
@@ -402,27 +440,24 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
     __syncwarp();
     if (tips_in_kernel && djtr) {
         for (int t = 0; t < 5; ++t) {
-            const int v = c_tip_vert[t];
             int slot = 0;
             for (int i = 0; i < kNJ; ++i) if (c_jtr_src[order][i] == kJ + t) slot = i;
             const float dv0 = djtr[((long)r * kNJ + slot) * 3 + 0] * kMM, dv1 = djtr[((long)r * kNJ + slot) * 3 + 1] * kMM,
                         dv2 = djtr[((long)r * kNJ + slot) * 3 + 2] * kMM;
             const float dv[3] = {dv0, dv1, dv2};
             float vp[3];
-            tip_skin_warp(c, v, be, W, lane, vp);
+            tip_skin_warp(s_t, t, W, lane, vp);
             for (int e = lane; e < kWsA; e += 32) {
                 const int k = e / 12, ee = e % 12;
-                const float w = __ldg(c.weights + v * kJ + k);
+                const float w = s_t.wtip[t][k];
                 W.dA[k][ee] += w * (ee < 9 ? dv[ee / 3] * vp[ee % 3] : dv[ee - 9]);
             }
             float dvp[3];
             mat3t_vec(W.T, dv, dvp);
             for (int k = lane; k < kPoseMap; k += 32)
-                W.dpm[k] += __ldg(c.posedirs_t + (long)k * kVC + v * 3) * dvp[0] + __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 1) * dvp[1] +
-                            __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 2) * dvp[2];
+                W.dpm[k] += s_t.ptip[t][k][0] * dvp[0] + s_t.ptip[t][k][1] * dvp[1] + s_t.ptip[t][k][2] * dvp[2];
             if (lane < kShape)
-                db += __ldg(c.shapedirs + (v * 3 + 0) * kShape + lane) * dvp[0] + __ldg(c.shapedirs + (v * 3 + 1) * kShape + lane) * dvp[1] +
-                      __ldg(c.shapedirs + (v * 3 + 2) * kShape + lane) * dvp[2];
+                db += s_t.stip[t][0][lane] * dvp[0] + s_t.stip[t][1][lane] * dvp[1] + s_t.stip[t][2][lane] * dvp[2];
             if (lane < 3) dc -= dv[lane];
             __syncwarp();
         }
@@ -465,7 +500,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
     }
     __syncwarp();
     if (lane < kShape) {
-        for (int i = 0; i < kJ * 3; ++i) db = fmaf(__ldg(c.js + i * kShape + lane), W.dJ[i / 3][i % 3], db);
+        for (int i = 0; i < kJ * 3; ++i) db = fmaf(s_t.js[i * kShape + lane], W.dJ[i / 3][i % 3], db);
         float* d = dbeta + (long)r * ld_dbeta + lane;
         *d = accumulate ? *d + db : db;
     }
@@ -476,7 +511,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
         if (i < 3) g = W.dpose[i];
         else {
             g = 0.f;
-            for (int j = 0; j < 45; ++j) g = fmaf(__ldg(c.comps + (i - 3) * 45 + j), W.dpose[3 + j], g);
+            for (int j = 0; j < 45; ++j) g = fmaf(s_t.comps[(i - 3) * 45 + j], W.dpose[3 + j], g);
         }
         float* d = dtheta + (long)r * ld_dtheta + i;
         *d = accumulate ? *d + g : g;
