@@ -151,7 +151,14 @@ typedef struct mhe_mano_consts {
     const float* weights;
     const float* jt;
     const float* js;
+    const float* pose_tables;   /* optional (may be NULL): mhe_mano_pose_tables_floats() floats filled by mhe_mano_pack_pose_tables() */
 } mhe_mano_consts;
+
+/* The pose / joints kernels stage the small tables they need (PCA basis, joint regressors, the blend-shape rows and skinning
+ * weights of the five tip vertices) in shared memory.  pose_tables is that set gathered once into one contiguous array, so the
+ * staging is a coalesced copy; with pose_tables == NULL every block gathers it from the full-size constants instead.          */
+size_t mhe_mano_pose_tables_floats(void);
+int mhe_mano_pack_pose_tables(const mhe_mano_consts* c, float* pose_tables, void* stream);
 
 #define MHE_MANO_VERTS 778
 #define MHE_MANO_JOINTS 21

@@ -54,18 +54,25 @@ struct WarpPose {
     float R[kJ][9], J[kJ][3], Gr[kJ][9], Gt[kJ][3], A[kJ][12];
     float dGr[kJ][9], dGt[kJ][3], dJ[kJ][3], dR[kJ][9], dpose[kPose];
     float dA[kJ][12], dpm[kWsPm], dGt_out[kJ * 3], T[12], red[8];
-    float th[48], be[12];
+    float th[48], be[12], dj[64];
 };
 constexpr int kPoseWarps = 4;
 
 // Small constants of the pose / tip path, staged once per block in shared memory: the per-row work is a long chain of short
 // dependent steps, and with a handful of warps per SM every global-memory round trip in it is exposed latency.
-struct PoseTables {
+struct __align__(16) PoseTables {
     float comps[45 * 45], hands_mean[48], jt[kJ * 3], js[kJ * 3 * kShape];
     float ptip[5][kPoseMap][3], stip[5][3][kShape], vtip[5][4], wtip[5][kJ];
 };
+static_assert(sizeof(PoseTables) % 16 == 0, "PoseTables is copied in 16-byte pieces");
 __device__ __forceinline__ void stage_pose_tables(const mhe_mano_consts& c, PoseTables& T, bool tips) {
     const int t = threadIdx.x, n = blockDim.x;
+    if (c.pose_tables) {   // pre-gathered: one coalesced copy
+        const float4* src = reinterpret_cast<const float4*>(c.pose_tables);
+        float4* dst = reinterpret_cast<float4*>(&T);
+        for (int i = t; i < (int)(sizeof(PoseTables) / 16); i += n) dst[i] = __ldg(src + i);
+        return;
+    }
     for (int i = t; i < 45 * 45; i += n) T.comps[i] = __ldg(c.comps + i);
     for (int i = t; i < 45; i += n) T.hands_mean[i] = __ldg(c.hands_mean + i);
     for (int i = t; i < kJ * 3; i += n) T.jt[i] = __ldg(c.jt + i);
@@ -154,6 +161,14 @@ __device__ __forceinline__ void tip_skin_warp(const PoseTables& T, int tip, Warp
         W.T[lane] = t;
     }
     __syncwarp();
+}
+
+__global__ void mano_pack_pose_tables_kernel(mhe_mano_consts c, float* out) {
+    __shared__ PoseTables T;
+    stage_pose_tables(c, T, true);
+    __syncthreads();
+    const float* src = reinterpret_cast<const float*>(&T);
+    for (int i = threadIdx.x; i < (int)(sizeof(PoseTables) / sizeof(float)); i += blockDim.x) out[i] = src[i];
 }
 
 // ---- forward ------------------------------------------------------------------------------------
@@ -426,6 +441,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
     if (r >= R) return;
     WarpPose& W = s_w[warp];
     const float* be = beta + (long)r * ld_beta;
+    if (djtr) for (int i = lane; i < kNJ * 3; i += 32) W.dj[i] = djtr[(long)r * kNJ * 3 + i] * kMM;   // this row's joint gradients, scaled
     pose_fwd_warp(s_t, theta + (long)r * ld_theta, be, W, lane);
 
     // vertex-side gradients -> W.dA, W.dpm, dbeta seed, centre gradient
@@ -442,8 +458,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
         for (int t = 0; t < 5; ++t) {
             int slot = 0;
             for (int i = 0; i < kNJ; ++i) if (c_jtr_src[order][i] == kJ + t) slot = i;
-            const float dv0 = djtr[((long)r * kNJ + slot) * 3 + 0] * kMM, dv1 = djtr[((long)r * kNJ + slot) * 3 + 1] * kMM,
-                        dv2 = djtr[((long)r * kNJ + slot) * 3 + 2] * kMM;
+            const float dv0 = W.dj[slot * 3 + 0], dv1 = W.dj[slot * 3 + 1], dv2 = W.dj[slot * 3 + 2];
             const float dv[3] = {dv0, dv1, dv2};
             float vp[3];
             tip_skin_warp(s_t, t, W, lane, vp);
@@ -469,7 +484,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
         for (int i = 0; i < kNJ; ++i) {
             const int src = c_jtr_src[order][i];
             if (src < kJ) {
-                const float g = djtr[((long)r * kNJ + i) * 3 + lane] * kMM;
+                const float g = W.dj[i * 3 + lane];
                 W.dGt_out[src * 3 + lane] += g;
                 dc -= g;                 // the tips' share of the centring is already in dc
             }
@@ -523,6 +538,16 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
 using namespace mhe;
 
 extern "C" {
+
+size_t mhe_mano_pose_tables_floats(void) { return sizeof(PoseTables) / sizeof(float); }
+
+int mhe_mano_pack_pose_tables(const mhe_mano_consts* c, float* pose_tables, void* stream) {
+    MHE_REQUIRE(c && pose_tables && ((uintptr_t)pose_tables & 15) == 0, "mano_pack_pose_tables: bad args");
+    mhe_mano_consts src = *c;
+    src.pose_tables = nullptr;
+    mano_pack_pose_tables_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(src, pose_tables);
+    return check_launch("mano pack pose tables");
+}
 
 size_t mhe_mano_workspace_bytes(int R, int mesh_grad) { return R < 0 ? 0 : ManoWs::floats(R, mesh_grad != 0) * sizeof(float); }
 

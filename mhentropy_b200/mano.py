@@ -122,7 +122,11 @@ class ManoCore(nn.Module):
                 'js': torch.einsum('jv,vck->jck', jreg, d(self.th_shapedirs)).float(),
             }
             tensors = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in pack.items()}
-            c = ManoConsts(**{k: v.data_ptr() for k, v in tensors.items()})
+            c = ManoConsts(**{k: v.data_ptr() for k, v in tensors.items()}, pose_tables=None)
+            if torch.device(device).type == 'cuda':   # gather the small pose / tip tables once (coalesced staging in the kernels)
+                tensors['pose_tables'] = torch.empty(lib().mhe_mano_pose_tables_floats(), device=device, dtype=torch.float32)
+                check(lib().mhe_mano_pack_pose_tables(c, ptr(tensors['pose_tables']), stream_ptr(torch.device(device))), 'mhe_mano_pack_pose_tables')
+                c.pose_tables = tensors['pose_tables'].data_ptr()
             self._packed = (key, tensors, c)
         return self._packed[2]
 
