@@ -279,16 +279,18 @@ def run_ours(args):
     e2e_value = time_e2e(e2e_step, args.steps)
     e2e_autograd_value = time_e2e(e2e_autograd_step, max(args.steps // 2, 5))
 
-    # ---------------- roofline of the dominant kernel: the 512x512 coupling GEMMs, timed live with events -------
+    # ---------------- roofline of the dominant kernels, timed live with CUDA events on their launching stream -------
+    # The two cluster-fused flow kernels (all 12 coupling layers forward; all 12 layers of data gradients backward) are ~60 % of
+    # the step.  Algorithmic FLOPs per launch: one flow pass = 14,794,752 FLOP per row, both for the forward kernel
+    # and for the backward kernel (which computes the data gradients; the weight gradients are separate batched GEMMs).
     peaks = measured_peaks()
     roof = None
     if rank == 0:
         probe_eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=False)
         probe_eng.load(**devb)
-        tags = [b'flow G1', b'dgrad G1', b'wgrad W1']      # substrings: match both the fp32 and the 'tc ...' labels
-        tot_ms, tot_n = 0.0, 0
         import ctypes
-        for tag in tags:
+
+        def probe(tag):
             _lib.check(L.mhe_probe_configure(tag, 4096), 'probe')
             for _ in range(3):
                 flush.zero_()
@@ -300,28 +302,44 @@ def run_ours(args):
                 probe_eng.run()
             ms, n = ctypes.c_float(), ctypes.c_int()
             _lib.check(L.mhe_probe_read(ctypes.byref(ms), ctypes.byref(n)), 'probe read')
-            tot_ms += ms.value
-            tot_n += n.value
+            return ms.value, n.value
+
+        fused = args.precision == 'bf16x3'
+        if fused:
+            ms_f, n_f = probe(b'fused flow fwd')
+            ms_b, n_b = probe(b'fused flow bwd')
+        else:
+            ms_f, n_f = probe(b'flow G1')
+            ms_b, n_b = probe(b'dgrad G1')
         L.mhe_probe_configure(None, 0)
-        H = 512
-        flop_per_launch = 2.0 * R * H * H * 2           # both nets of one layer, one 512x512 contraction over R rows
-        avg_ms = tot_ms / max(tot_n, 1)
-        achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
-        kname = ('tc_gemm_kernel (tcgen05 bf16x3 + TMA' if args.precision == 'bf16x3' else 'sgemm_kernel (fp32 CUDA cores') + \
-            '; the 512x512 coupling-layer contractions: fwd, dgrad, wgrad)'
-        roof = {'bound': 'tensor', 'kernel': kname,
-                'achieved': achieved, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / peaks['bf16_tflops_sustained'], 'traffic': None,
-                'peak_source': f'{peaks["source"]} bf16 dense sustained', 'launches_timed': tot_n, 'avg_launch_us': avg_ms * 1e3,
-                'share_of_step': (tot_ms / 5) / (total_ms / args.steps),
-                'note': ('bf16x3 split precision issues 3 tensor-core passes per product; judged against the bf16 peak with the 1x '
-                         'algorithmic FLOP count, so 1/3 is the ceiling' if args.precision == 'bf16x3' else
-                         'fp32 CUDA-core path; judged against the bf16 tensor peak with the 1x algorithmic FLOP count')}
+        flop_pass = float(FLOW_PASS_FLOP) * R if fused else 2.0 * R * 512 * 512 * 2
+        us_f, us_b = ms_f / max(n_f, 1) * 1e3, ms_b / max(n_b, 1) * 1e3
+        ach_f, ach_b = flop_pass / (us_f * 1e-6) / 1e12, flop_pass / (us_b * 1e-6) / 1e12
+        step_us = total_ms / args.steps * 1e3
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r1_fused_bwd_traffic.json')
+        if fused and os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get('dram_bytes_per_launch')
+        roof = {'bound': 'tensor',
+                'kernel': ('flow_bwd_fused_kernel (cluster-fused data-gradient pass over all 12 coupling layers: tcgen05 split-bf16x3, TMA '
+                           'weight ring, DSMEM exchanges)' if fused else 'sgemm_kernel (fp32 CUDA cores), dgrad G1'),
+                'achieved': ach_b, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': ach_b / peaks['bf16_tflops_sustained'],
+                'traffic': traffic, 'peak_source': f'{peaks["source"]} bf16 dense sustained',
+                'launches_timed': n_b, 'avg_launch_us': us_b, 'share_of_step': us_b / step_us,
+                'algorithmic_flop_per_launch': flop_pass,
+                'second_kernel': {'kernel': 'flow_fwd_fused_kernel (cluster-fused sampling pass, same mapping)' if fused else 'flow G1',
+                                  'achieved': ach_f, 'frac': ach_f / peaks['bf16_tflops_sustained'], 'avg_launch_us': us_f,
+                                  'share_of_step': us_f / step_us, 'launches_timed': n_f},
+                'note': ('split precision issues 3 tensor-core products per fp32 product (hi*hi + hi*lo + lo*hi, as two instructions); judged '
+                         'against the bf16 dense peak with the 1x algorithmic FLOP count, so 1/3 is the ceiling.  At 640 rows the kernel is bound by '
+                         'the per-SM L2->SMEM ingest of the weights (320 KB per layer per CTA at ~50 B/clk) and by the exchange latency between '
+                         'the 8 CTAs of a cluster, not by the tensor pipe (DESIGN.md §5)')}
         flop_step = train_step_flop_per_hyp(S) * R
         weight_bytes = 20_030_520 * 4
         roof_step = {'algorithmic_gflop': flop_step / 1e9, 't_tensor_us': flop_step / (peaks['bf16_tflops_sustained'] * 1e12) * 1e6,
                      't_hbm_us': (3 * weight_bytes + R * 9_336) / (peaks['hbm_gbs'] * 1e9) * 1e6,
-                     'measured_us': total_ms / args.steps * 1e3}
+                     'measured_us': step_us}
         roof_step['frac_of_governing'] = max(roof_step['t_tensor_us'], roof_step['t_hbm_us']) / roof_step['measured_us']
 
     # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores ----------------
