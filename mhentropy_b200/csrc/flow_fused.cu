@@ -66,7 +66,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// The remote arrivals are RELEASE operations at cluster scope (mbarrier.arrive.release.cluster): they already order every write that
+// happens-before them - this thread's and, through the CTA barrier executed just before, the other threads' - so no separate
+// fence.acq_rel.cluster (which also invalidates L1 and costs ~1-2 us here) is issued.  MHE_FUSED_FENCE=1 at build time restores it.
+#ifdef MHE_FUSED_FENCE
 __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+#else
+__device__ __forceinline__ void fence_cluster() {}
+#endif
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
