@@ -361,23 +361,34 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
     bf16* dcpp = featp + (((size_t)2 * B * L.C + 511) / 512) * 512;   // [2][B][cp_ld]
     MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, false, stream));   // bfloat16: partner of dcp planes
     MHE_TRY(split_planes(dcp, cp_ld, 0, B, (int)cp_ld, nullptr, dcpp, B, (int)cp_ld, 2, 1, false, stream));
+    // The weight / bias gradients and the feature gradient only share their inputs: fork the former onto an internal stream.
+    Aux& aux = aux_ctx();
+    const bool fork = aux.ok && dfeat != nullptr;
+    cudaStream_t wstream = fork ? aux.stream[0] : stream;
+    if (fork) {
+        MHE_TRY(cuda_ok(cudaEventRecord(aux.ready[0], stream), "fork cond wgrad"));
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(wstream, aux.ready[0], 0), "fork cond wgrad"));
+    }
     {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat      (A MN-major: cols = h, rows = b; B MN-major: cols = c, rows = b)
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
         EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
-        MHE_TRY((gemm<true, true, false>(A, Bt, g, e, stream, "tc cond wgrad")));
+        MHE_TRY((gemm<true, true, false>(A, Bt, g, e, wstream, "tc cond wgrad")));
     }
-    cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, stream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
+    cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, wstream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
     MHE_TRY(check_launch("cond bias grad"));
+    if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[0][0], wstream), "join cond wgrad"));
     if (dfeat) {   // dfeat [B][C] = sum_idx dcp[:, idx, :] Cw[idx]   (A K-major over h; B MN-major: cols = c, rows = h)
         MHE_TRY(cuda_ok(cudaMemsetAsync(dfeat, 0, (size_t)B * L.C * sizeof(float), stream), "memset dfeat"));
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(P.cwb, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
         GemmShape g{B, L.C, L.H, L.L * 4, 1, 1, 1};
+        g.kfold = (L.L * 4) % 4 == 0 ? 4 : ((L.L * 4) % 2 == 0 ? 2 : 1);   // every batch lands on the same output: contract 4 per CTA, 4x fewer atomics
         EpiAtomicRows e{dfeat, L.C, L.C};
         MHE_TRY((gemm<false, true, false>(A, Bt, g, e, stream, "tc cond dfeat")));
     }
+    if (fork) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0][0], 0), "join cond wgrad"));
     return MHE_OK;
 }
 

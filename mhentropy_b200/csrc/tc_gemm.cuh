@@ -138,6 +138,7 @@ struct GemmShape {
     int ksplit;
     int a_batch_mul;   // batch coordinate of A = batch * a_batch_mul (0 broadcasts one A to every batch)
     int b_batch_mul;
+    int kfold = 1;     // consecutive batches contracted into ONE accumulator per CTA (batches % kfold == 0; the epilogue sees batch / kfold)
 };
 
 template <int BN, int NPL>
@@ -171,7 +172,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int kb_per = (kb_total + g.ksplit - 1) / g.ksplit;
     const int kb_begin = split * kb_per;
     const int kb_end = min(kb_total, kb_begin + kb_per);
-    const int nkb = max(kb_end - kb_begin, 0);
+    const int nkb1 = max(kb_end - kb_begin, 0);          // k-blocks per batch
+    const int nkb = nkb1 * g.kfold;                      // ... per accumulator
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
@@ -201,18 +203,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
                 const uint32_t full = smem_u32(&bar_full[s]);
                 mbar_expect_tx(full, Plan::kStageBytes);
-                const int k0 = (kb_begin + i) * BK;
+                const int k0 = (kb_begin + i % nkb1) * BK;
+                const int bsrc = batch * g.kfold + i / nkb1;         // source batch of this k-block
 #pragma unroll
                 for (int p = 0; p < NPL; ++p) {
-                    if (!A_MN) tma_load_4d(stage_a(s, p), &mapA, full, k0, m0, p, batch * g.a_batch_mul);
+                    if (!A_MN) tma_load_4d(stage_a(s, p), &mapA, full, k0, m0, p, bsrc * g.a_batch_mul);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, &mapA, full, m0 + 64 * j, k0, p, batch * g.a_batch_mul);
+                        for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, &mapA, full, m0 + 64 * j, k0, p, bsrc * g.a_batch_mul);
                     }
-                    if (!B_MN) tma_load_4d(stage_b(s, p), &mapB, full, k0, n0, p, batch * g.b_batch_mul);
+                    if (!B_MN) tma_load_4d(stage_b(s, p), &mapB, full, k0, n0, p, bsrc * g.b_batch_mul);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, &mapB, full, n0 + 64 * j, k0, p, batch * g.b_batch_mul);
+                        for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, &mapB, full, n0 + 64 * j, k0, p, bsrc * g.b_batch_mul);
                     }
                 }
             }
@@ -334,7 +337,7 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
         attr_set = true;
     }
     ProbeScope probe(what, stream);
-    dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), g.batches * g.ksplit);
+    dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), (g.batches / (g.kfold > 0 ? g.kfold : 1)) * g.ksplit);
     if (launch_chain(kern, grid, dim3(kThreads), (size_t)Plan::kBytes, stream, *ma, *mb, g, epi) != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
         return MHE_ERR_CUDA;
