@@ -27,6 +27,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OUT = sys.stdout
 METRIC = 'hypotheses/sec (flow+MANO fwd+bwd)'
 UNIT = 'hypotheses/s'
 
@@ -160,7 +161,7 @@ def run_reference(args):
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -234,7 +235,7 @@ def run_ours(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({'profile_only': True, 'ms_per_step': total_ms / args.steps, 'gpu_launches_per_step': int(launches_per_step)}))
+            print(json.dumps({'profile_only': True, 'ms_per_step': total_ms / args.steps, 'gpu_launches_per_step': int(launches_per_step)}), file=OUT, flush=True)
         return
 
     # ---------------- e2e: public API with HOST buffers inside the timed region --------------------------------
@@ -368,10 +369,18 @@ def run_ours(args):
             'gpu_launches_per_step': int(launches_per_step),
             'roofline': roof, 'step_roofline': roof_step, 'cpu_baseline': cpu,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL's version banner, ...) that print to fd 1 are sent to stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -388,6 +397,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='value leg only (for ncu launch lists)')
     args = ap.parse_args()
+    global OUT
+    OUT = _claim_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:

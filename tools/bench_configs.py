@@ -1,0 +1,65 @@
+"""Secondary workloads of BASELINE.json through the drop-in API on one GPU (not bench lines; for the record in profiles/):
+config 3: inference sampling B=256 x S=100 (flow sample + MANO mesh + reprojection), config 4: NLL scoring of 16384 poses."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from mhentropy_b200 import MHEntHead
+from mhentropy_b200.mano_assets import synthetic_mano
+
+dev = torch.device('cuda')
+torch.manual_seed(0)
+head = MHEntHead(mano_data=synthetic_mano(0)).to(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, n=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / n
+
+
+out = {}
+B, S = 256, 100
+feat = torch.randn(B, 512, device=dev)
+z0 = torch.randn(B * S, 45, device=dev) * 0.8
+z_det = torch.cat([0.5 * torch.randn(B, 3), 0.02 * torch.randn(B, 10), torch.randn(B, 1) * 0.1 - 1.2, 0.1 * torch.randn(B, 2)], 1).to(dev)
+res = {}
+
+
+def sample():
+    res['o'] = head.sample(feat, N=S, temp=0.8, mods={'uv', 'xyz', 'verts'}, z0=z0, z_det=z_det)
+
+
+ms = timeit(sample)
+o = res['o']
+assert all(torch.isfinite(v).all() for v in o.values() if torch.is_tensor(v) and v.is_floating_point())
+out['config3_inference_sampling'] = {'B': B, 'S': S, 'ms': ms, 'hypotheses_per_s': B * S / (ms * 1e-3),
+                                     'outputs': {k: list(v.shape) for k, v in o.items() if torch.is_tensor(v)}}
+R = 16384
+x = 0.5 * torch.randn(R, 45, device=dev)
+featr = torch.randn(R, 512, device=dev)
+
+
+def nll():
+    with torch.no_grad():
+        res['lp'] = head.q_z_giv_i.log_prob(x, logvar=featr)
+
+
+ms = timeit(nll)
+assert torch.isfinite(res['lp']).all()
+out['config4_nll_scoring'] = {'rows': R, 'ms': ms, 'poses_per_s': R / (ms * 1e-3)}
+print(json.dumps(out))
