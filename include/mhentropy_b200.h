@@ -225,6 +225,23 @@ int mhe_normalize_project(const mhe_loss_cfg* cfg, const float* joints, const fl
                           float* xyz, float* verts_n, float* uv, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Hypothesis selection and multi-hypothesis evaluation metrics.
+ *
+ * mhe_topk_hypotheses: reference hand/network.py:866-871 (torch.topk of log q over the hypothesis axis).
+ *   log_q [N][B] -> idx [k][B] (int64): the k most likely hypotheses of every image, most likely first.
+ * mhe_hypothesis_metrics: reference hand/criteria.py:91-168 (MHEntLoss metrics with aligned = False) and hand/utils.py:21-30.
+ *   xyz [N][B][21][3] (normalised joints), uv [N][B][21][2] (pixels); targets pose3d [B][21][3], scale [B], crop_uv [B][42] in
+ *   [-1, 1], vis [B][21] -> metrics [14][B], rows in the reference's key order:
+ *     eucLoss_3d_rgb_{sample, sample_std, vis, vis_std, vis_mean, invis, invis_std}, then the same seven for 2d:
+ *   best-hypothesis mean joint error per group (worst hypothesis for 2d / vis), spread of the hypotheses, mean over hypotheses.
+ * ------------------------------------------------------------------------------------------ */
+size_t mhe_hypothesis_metrics_workspace_bytes(int B);
+int mhe_hypothesis_metrics(const float* xyz, const float* uv, const float* pose3d, const float* scale, const float* crop_uv,
+                           const float* vis, int N, int B, int root_idx, float image_size, float* metrics,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int mhe_topk_hypotheses(const float* log_q, int N, int B, int k, long long* idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Tensor-core building blocks (tcgen05 + TMA), exposed for tests and tools.
  * fp32 values travel as split 16-bit planes x = hi + lo, [batches][planes][rows_p][cols_p]: IEEE half planes (f16 = 1,
  * ~22 significant bits, for range-safe data: weights, activations) or bfloat16 planes (f16 = 0, ~16 bits, full fp32

@@ -190,7 +190,8 @@ class MHEntHead(nn.Module):
         z = z.reshape(N, B, 61)
         if N_quant < N:
             log_q = self._reverse_log_q(z.flatten(0, 1), feat).reshape(N, -1)
-            idx = torch.topk(log_q, N_quant, dim=0)[1][..., None].repeat(1, 1, 61)
+            from .metrics import topk_hypotheses
+            idx = (topk_hypotheses(log_q, N_quant) if log_q.is_cuda else torch.topk(log_q, N_quant, dim=0)[1])[..., None].repeat(1, 1, 61)
             z = torch.gather(z, 0, idx)
             N = N_quant
         out = {'th_bt': z[..., :58], 'logs_t': z[..., -3:]}

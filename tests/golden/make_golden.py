@@ -16,6 +16,9 @@ Fixtures
   mano.npz         ManoLayer forward + gradients of a fixed linear functional
   mhent_small.npz  MHEnt.get_loss fwd+bwd and MHEnt.sample with the small flow
   mhent_prod.npz   MHEnt.get_loss fwd+bwd with the production flow (B=4, N=10)
+  metrics.npz      MHEntLoss.forward metrics (criteria.py:47-173) and torch.topk selection (network.py:866-871) on
+                   seeded (N, B, .) outputs: N = 7 with occluded / all-visible / none-visible images, and N = 1
+                   (``python tests/golden/make_golden.py metrics`` regenerates only this one)
 """
 from __future__ import annotations
 
@@ -166,9 +169,46 @@ def mhent_fixture(mano, cfg, B, N, seed, with_weight_grads, with_sample):
     return fx
 
 
+def metrics_fixture(mano):
+    """Reference ``MHEntLoss.forward`` (``criteria.py:47-173``) run on seeded stand-ins for the outputs of ``MHEnt.sample``."""
+    ref_shim.install_stubs(mano)
+    with ref_shim.cpu_mode():
+        import criteria  # reference hand/criteria.py
+    fx = {}
+    for tag, N, B, seed in (('a', 7, 6, 21), ('b', 1, 5, 22), ('c', 12, 3, 23)):
+        g = torch.Generator().manual_seed(seed)
+        pose3d = torch.randn(B, 63, generator=g)
+        xyz = pose3d[None] + 0.2 * torch.randn(N, B, 63, generator=g)
+        crop_uv = torch.rand(B, 42, generator=g) * 2 - 1
+        uv = (crop_uv[None] + 1) / 2 * 256 + 6. * torch.randn(N, B, 42, generator=g)
+        scale = 0.05 + 0.1 * torch.rand(B, generator=g)
+        vis = (torch.rand(B, 21, generator=g) < 0.7).float()
+        if tag == 'a':
+            vis[0] = 1.                       # nothing occluded in image 0
+            vis[1] = 0.                       # nothing visible in image 1
+        if tag == 'c':
+            vis[:] = 1.                       # the occluded group is empty for the whole batch (num_valid == 0 branch)
+        log_q = torch.randn(N, B, generator=g)
+        log_p = torch.randn(B, generator=g)
+        target = {'pose3d': pose3d, 'scale': scale, 'crop_uv': crop_uv, 'vis': vis}
+        with ref_shim.cpu_mode():
+            _, _, metrics = criteria.MHEntLoss()({'log_p': log_p, 'xyz': xyz.clone(), 'uv': uv.clone()}, target)
+        for k, v in (('xyz', xyz), ('uv', uv), ('pose3d', pose3d), ('scale', scale), ('crop_uv', crop_uv), ('vis', vis), ('log_q', log_q)):
+            fx[f'{tag}/{k}'] = npy(v)
+        for k, v in metrics.items():
+            fx[f'{tag}/m/{k}'] = npy(v)
+        for kk in sorted({1, min(3, N), N}):
+            fx[f'{tag}/topk{kk}'] = npy(torch.topk(log_q, kk, dim=0)[1])      # network.py:866-871
+    return fx
+
+
 def main():
     assert ref_shim.reference_available(), 'needs /root/reference'
     mano = synthetic_mano(0)
+    if 'metrics' in sys.argv[1:]:
+        np.savez_compressed(os.path.join(HERE, 'metrics.npz'), **metrics_fixture(mano))
+        print('metrics.npz', os.path.getsize(os.path.join(HERE, 'metrics.npz')))
+        return
     flows = ref_shim.import_flows(mano)
     np.savez_compressed(os.path.join(HERE, 'flow_small.npz'), **flow_fixture(flows, SMALL, seed=3, R=10, with_weights=True))
     np.savez_compressed(os.path.join(HERE, 'flow_prod.npz'), **flow_fixture(flows, PROD, seed=0, R=12, with_weights=False))
@@ -177,6 +217,7 @@ def main():
                         **mhent_fixture(mano, SMALL, B=3, N=10, seed=11, with_weight_grads=True, with_sample=True))
     np.savez_compressed(os.path.join(HERE, 'mhent_prod.npz'),
                         **mhent_fixture(mano, PROD, B=4, N=10, seed=0, with_weight_grads=False, with_sample=False))
+    np.savez_compressed(os.path.join(HERE, 'metrics.npz'), **metrics_fixture(mano))
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

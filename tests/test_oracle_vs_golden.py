@@ -175,3 +175,21 @@ def test_oracle_vs_live_reference_flow():
     assert all(torch.equal(sd[k], sd2[k]) for k in sd)
     assert torch.allclose(fo.sample(sd, z0, feat), x_ref, atol=1e-6)
     assert torch.allclose(fo.log_prob(sd, x_ref, feat), lp_ref, rtol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_metrics_oracle_against_golden(golden_dir, tag):
+    """oracle/metrics_oracle.py against reference criteria.py:MHEntLoss outputs (tests/golden/metrics.npz): occluded /
+    all-visible / none-visible images (a), N = 1 (b), an empty joint group for the whole batch (c)."""
+    from oracle import metrics_oracle as meo
+    fx = np.load(os.path.join(golden_dir, 'metrics.npz'))
+    t = lambda k: torch.from_numpy(fx[f'{tag}/{k}'])  # noqa: E731
+    out = meo.hypothesis_metrics(t('xyz'), t('uv'), t('pose3d'), t('scale'), t('crop_uv'), t('vis'))
+    assert sorted(out) == sorted(meo.METRIC_KEYS)
+    for k in meo.METRIC_KEYS:
+        ref = fx[f'{tag}/m/{k}']
+        np.testing.assert_allclose(out[k].numpy(), ref, rtol=1e-5, atol=1e-6 * max(1.0, float(np.abs(ref).max())))
+    for name in fx.files:
+        if name.startswith(f'{tag}/topk'):
+            kk = int(name.split('topk')[1])
+            assert np.array_equal(meo.topk_hypotheses(t('log_q'), kk).numpy(), fx[name])
