@@ -291,6 +291,8 @@ def run_ours(args):
         probe_eng.load(**devb)
         import ctypes
 
+        PROBE_RUNS = 5
+
         def probe(tag):
             _lib.check(L.mhe_probe_configure(tag, 4096), 'probe')
             for _ in range(3):
@@ -298,7 +300,7 @@ def run_ours(args):
                 probe_eng.run()
             torch.cuda.synchronize()
             L.mhe_probe_reset()
-            for _ in range(5):
+            for _ in range(PROBE_RUNS):
                 flush.zero_()
                 probe_eng.run()
             ms, n = ctypes.c_float(), ctypes.c_int()
@@ -314,8 +316,10 @@ def run_ours(args):
             ms_b, n_b = probe(b'dgrad G1')
         L.mhe_probe_configure(None, 0)
         flop_pass = float(FLOW_PASS_FLOP) * R if fused else 2.0 * R * 512 * 512 * 2
+        # a pass may be cut into several launches of the same kernel (chunks of consecutive layers): FLOPs per launch scale with it
+        lpp_f, lpp_b = max(n_f, 1) / PROBE_RUNS, max(n_b, 1) / PROBE_RUNS
         us_f, us_b = ms_f / max(n_f, 1) * 1e3, ms_b / max(n_b, 1) * 1e3
-        ach_f, ach_b = flop_pass / (us_f * 1e-6) / 1e12, flop_pass / (us_b * 1e-6) / 1e12
+        ach_f, ach_b = flop_pass / lpp_f / (us_f * 1e-6) / 1e12, flop_pass / lpp_b / (us_b * 1e-6) / 1e12
         step_us = total_ms / args.steps * 1e3
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'r1_fused_bwd_traffic.json')
@@ -327,11 +331,11 @@ def run_ours(args):
                            'weight ring, DSMEM exchanges)' if fused else 'sgemm_kernel (fp32 CUDA cores), dgrad G1'),
                 'achieved': ach_b, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': ach_b / peaks['bf16_tflops_sustained'],
                 'traffic': traffic, 'peak_source': f'{peaks["source"]} bf16 dense sustained',
-                'launches_timed': n_b, 'avg_launch_us': us_b, 'share_of_step': us_b / step_us,
-                'algorithmic_flop_per_launch': flop_pass,
+                'launches_timed': n_b, 'avg_launch_us': us_b, 'launches_per_step': lpp_b, 'share_of_step': us_b * lpp_b / step_us,
+                'algorithmic_flop_per_launch': flop_pass / lpp_b,
                 'second_kernel': {'kernel': 'flow_fwd_fused_kernel (cluster-fused sampling pass, same mapping)' if fused else 'flow G1',
                                   'achieved': ach_f, 'frac': ach_f / peaks['bf16_tflops_sustained'], 'avg_launch_us': us_f,
-                                  'share_of_step': us_f / step_us, 'launches_timed': n_f},
+                                  'launches_per_step': lpp_f, 'share_of_step': us_f * lpp_f / step_us, 'launches_timed': n_f},
                 'note': ('split precision issues 3 tensor-core products per fp32 product (hi*hi + hi*lo + lo*hi, as two instructions); judged '
                          'against the bf16 dense peak with the 1x algorithmic FLOP count, so 1/3 is the ceiling.  At 640 rows the kernel is bound by '
                          'the per-SM L2->SMEM ingest of the weights (320 KB per layer per CTA at ~50 B/clk) and by the exchange latency between '

@@ -123,7 +123,9 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
  *          needs dcp); mhe_flow_join(stream) makes `stream` wait for them and must be called before dparams is read or the
  *          captured graph ends.
  *   bit 1  the caller promises that the WEIGHT slots of dparams (W0, W1, W2, Cw) are zero when mhe_flow_pass_bwd /
- *          mhe_flow_cond_bwd run: their epilogues then store instead of read-modify-write (bias slots always accumulate).      */
+ *          mhe_flow_cond_bwd run: their epilogues then store instead of read-modify-write (bias slots always accumulate).
+ *   bit 2  the caller promises that dfeat is zero when mhe_flow_cond_bwd runs on the tensor-core path (it is accumulated into with
+ *          atomics there): the memset that would otherwise sit on the critical path is skipped.                                 */
 int mhe_flow_set_async(int on);
 int mhe_flow_join(void* stream);
 
@@ -216,6 +218,21 @@ int mhe_reproj_loss_fwd(const mhe_loss_cfg* cfg, const float* joints, const floa
 int mhe_reproj_loss_bwd(const mhe_loss_cfg* cfg, const float* joints, const float* z, const float* crop_uv,
                         const float* vis, int R, int B, const float* dlog_p, const float* dloss,
                         float* djoints, float* dz, float* dlog_q, void* stream);
+
+/* The image-level reductions of mhe_reproj_loss_fwd alone (network.py:793-808, criteria.py:55,173): row_log_p [R], log_q [R] ->
+ *   log_p [B], h [B], q_log_p [B] (any may be NULL), loss [1] (may be NULL; needs log_p).                                        */
+int mhe_image_loss_reduce(const float* row_log_p, const float* log_q, int R, int B, float* log_p, float* h, float* q_log_p,
+                          float* loss, void* stream);
+
+/* The joints-only training path of every hypothesis in ONE launch: MANO forward (mhe_mano_fwd without the mesh; reference
+ * manolayer.py:110-274), root / bone normalisation, projection, Laplace(visible) and priors (mhe_reproj_loss_fwd's row part;
+ * utils.py:46-66, network.py:497-514, 233-258, 155-165), and the backward of both down to dz (mhe_reproj_loss_bwd + mhe_mano_bwd).
+ * The loss is linear in the row terms, so the gradient seed of every row is the constant -dloss / R and nothing waits for a
+ * reduction.  z [R][61] (theta = z[:, 0:48], beta = z[:, 48:58]), crop_uv [B][42], vis [B][21] ->
+ *   jtr [R][21][3] (may be NULL), uv [R][42] (may be NULL), row_log_p [R], dz [R][61] (overwritten), dlog_q [R] (may be NULL).     */
+int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* crop_uv,
+                                const float* vis, int R, int B, int joint_order, float dloss,
+                                float* jtr, float* uv, float* row_log_p, float* dz, float* dlog_q, void* stream);
 
 /* xyz / verts normalisation and projection for MHEnt.sample (network.py:466-483, 497-514, 876-877):
  * joints [R][21][3], verts [R][778][3] (NULL ok), logs_t = z[:, 58:61] with row stride ld_z ->

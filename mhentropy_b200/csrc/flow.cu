@@ -487,6 +487,7 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
 int mhe_flow_set_async(int on) {
     fused::set_async_wgrad(on & 1);
     tcflow::set_grads_are_zero((on >> 1) & 1);
+    tcflow::set_dfeat_is_zero((on >> 2) & 1);
     return MHE_OK;
 }
 int mhe_flow_join(void* stream) { return fused::join((cudaStream_t)stream); }

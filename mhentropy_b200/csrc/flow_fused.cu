@@ -620,6 +620,7 @@ struct BwdArgs {
     float* partial;
     long long* dbg;
     int R, Rp, D, H, L, direction, tiles, two_mma;
+    int s_lo, s_hi;                             // the steps [s_lo, s_hi) this launch runs (descending): the pass may be cut into chunks
     size_t blk, ob2;
 };
 
@@ -683,7 +684,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 ++q;
                 return s;
             };
-            for (int step = p.L - 1; step >= 0; --step) {
+            for (int step = p.s_hi - 1; step >= p.s_lo; --step) {
                 const int layer = p.direction == 0 ? step : p.L - 1 - step;
                 const int wb = layer * 2 + net;
                 {   // W2^T slice: k = flow dim (64 rows of W2), m = feature slice (two 64-column groups)
@@ -714,8 +715,8 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         // ===================== gradient (B) producer: the three peers' dh1T k-blocks from global memory
         if (lane == 0) {
             uint32_t q = 0;
-            for (int step = p.L - 1; step >= 0; --step) {
-                const int it = p.L - 1 - step;
+            for (int step = p.s_hi - 1; step >= p.s_lo; --step) {
+                const int it = p.s_hi - 1 - step;
                 const int ab = (p.direction == 0 ? step : p.L - 1 - step) * 2 + net;
                 mbar_wait_cluster(smem_u32(&bar_a0), it & 1);
                 fence_proxy_async();
@@ -741,8 +742,8 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 ++qa;
                 return s;
             };
-            for (int step = p.L - 1; step >= 0; --step) {
-                const uint32_t par = (p.L - 1 - step) & 1;
+            for (int step = p.s_hi - 1; step >= p.s_lo; --step) {
+                const uint32_t par = (p.s_hi - 1 - step) & 1;
                 {   // bG2: acc0 = W2^T slice . dpre^T   (B K-major in xa)
                     const uint32_t s = wait_a();
                     mbar_wait(smem_u32(&bar_xm), par);
@@ -908,12 +909,12 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         // every CTA's dpre tile is zeroed before any owner writes into it: cluster-wide rendezvous of the worker warps via bar_part
         if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
         worker_wait(&bar_part, 0, true);
-        owner_coupling(p.L - 1, p.direction == 0 ? p.L - 1 : 0);
+        owner_coupling(p.s_hi - 1, p.direction == 0 ? p.s_hi - 1 : p.L - p.s_hi);
 
         float v[32];
-        for (int step = p.L - 1; step >= 0; --step) {
+        for (int step = p.s_hi - 1; step >= p.s_lo; --step) {
             const int layer = p.direction == 0 ? step : p.L - 1 - step;
-            const int it = p.L - 1 - step;
+            const int it = p.s_hi - 1 - step;
             const uint32_t par = it & 1;
             const uint64_t mb = mbits[layer];
             const size_t sbatch = (size_t)(step * 2 + net) * 2;    // plane index base of the saved activations (indexed by step)
@@ -996,7 +997,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                     gs[urow * kXs + d] += a;
                 }
                 worker_sync();
-                if (step > 0) owner_coupling(step - 1, p.direction == 0 ? step - 1 : p.L - step);
+                if (step > p.s_lo) owner_coupling(step - 1, p.direction == 0 ? step - 1 : p.L - step);
             }
         }
         for (int i = t; i < 8 * D; i += kWorkers) {   // every CTA writes the rows it owns
@@ -1087,24 +1088,35 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
 
 // ---- small kernels around the backward ---------------------------------------------------------------------------------
 // saved half planes [step][net][2][n] -> bfloat16 planes [layer][net][2][n] of the same values (operands of the weight-gradient GEMMs)
-__global__ void replane_by_layer_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long n, int L, int direction) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+// for the steps [step0, step0 + gridDim.y / 2); 8 values per thread (16-byte loads and stores; n is a multiple of 8)
+__global__ void __launch_bounds__(256) replane_by_layer_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long n, int L, int direction, int step0) {
+    const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
     if (i >= n) return;
-    const int sb = blockIdx.y;                    // step * 2 + net
-    const int step = sb >> 1, net = sb & 1;
+    const int step = step0 + (blockIdx.y >> 1), net = blockIdx.y & 1;
     const int layer = direction == 0 ? step : L - 1 - step;
-    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + (long)sb * 2 * n;
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + (long)(step * 2 + net) * 2 * n;
     uint16_t* d16 = reinterpret_cast<uint16_t*>(dst) + (long)(layer * 2 + net) * 2 * n;
-    const float v = from16<true>(s16[i]) + from16<true>(s16[n + i]);
-    const uint16_t h = to16<false>(v);
-    d16[i] = h;
-    d16[n + i] = to16<false>(v - from16<false>(h));
+    const uint4 h4 = *reinterpret_cast<const uint4*>(s16 + i), l4 = *reinterpret_cast<const uint4*>(s16 + n + i);
+    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[k])), c = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+        const float v0 = a.x + c.x, v1 = a.y + c.y;
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+        const float2 hf = __bfloat1622float2(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+        oh[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        ol[k] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(d16 + i) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(d16 + n + i) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
 }
 // xmT[layer][net][plane][d][r] = bfloat16 planes of mask[layer][d] * x_step[r][d]  (zero for d >= D, r >= R)
 __global__ void xm_transposed_kernel(const float* __restrict__ saved_x, const float* __restrict__ mask, int R, int Rp, int D, int L, int direction,
-                                     bf16* __restrict__ xmT) {
+                                     bf16* __restrict__ xmT, int layer0) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = blockIdx.y, layer = blockIdx.z;
+    const int d = blockIdx.y, layer = layer0 + blockIdx.z;
     if (r >= Rp) return;
     const int step = direction == 0 ? layer : L - 1 - layer;
     float v = 0.f;
@@ -1122,9 +1134,9 @@ __global__ void xm_transposed_kernel(const float* __restrict__ saved_x, const fl
 // block: 32 features x 64 images; thread = (feature, 8 consecutive images), 16-byte plane loads; transposed through shared memory
 // so that the rows of dcp receive 32 consecutive features (128 B) per store
 __global__ void __launch_bounds__(256) dcp_from_planes_kernel(const bf16* __restrict__ dh0T, const bf16* __restrict__ dh1T, int R, int Rp, int B, int H,
-                                                               float* __restrict__ dcp, long cp_ld) {
+                                                               float* __restrict__ dcp, long cp_ld, int ln0) {
     __shared__ float tile[32][65];
-    const int f0 = blockIdx.x * 32, ln = blockIdx.y, jj = blockIdx.z & 1, b0 = (blockIdx.z >> 1) * 64;       // ln = layer * 2 + net
+    const int f0 = blockIdx.x * 32, ln = ln0 + blockIdx.y, jj = blockIdx.z & 1, b0 = (blockIdx.z >> 1) * 64;       // ln = layer * 2 + net
     const uint16_t* src = reinterpret_cast<const uint16_t*>(jj == 0 ? dh0T : dh1T) + (size_t)ln * 2 * H * Rp;
     const int layer = ln >> 1, net = ln & 1;
     const int fl = threadIdx.x >> 3, bg = threadIdx.x & 7;
@@ -1170,9 +1182,11 @@ static int cuda_ok(cudaError_t e, const char* what) {
     return MHE_ERR_CUDA;
 }
 
+constexpr int kMaxChunks = 4;
 struct BwdAux {
-    cudaStream_t stream[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t start = nullptr, replaned = nullptr, bwd_done = nullptr, wgrad_done[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t stream[4] = {nullptr, nullptr, nullptr, nullptr};     // [0..2]: weight gradients (W1, W0 + dcp, W2), [3]: re-planes
+    cudaEvent_t start = nullptr, replaned[kMaxChunks] = {}, chunk_done[kMaxChunks] = {}, dcp_done[kMaxChunks] = {},
+                wgrad_done[3] = {nullptr, nullptr, nullptr};
     bool has_pending = false;
     bool ok = false;
 };
@@ -1182,12 +1196,11 @@ static BwdAux& bwd_aux() {
     if (!tried) {
         tried = true;
         bool ok = true;
-        for (int i = 0; i < 3 && ok; ++i)
-            ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&a.wgrad_done[i], cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&a.start, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&a.replaned, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&a.bwd_done, cudaEventDisableTiming) == cudaSuccess;
+        auto ev = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+        for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 3; ++i) ev(&a.wgrad_done[i]);
+        for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); }
+        ev(&a.start);
         a.ok = ok;
     }
     return a;
@@ -1206,6 +1219,19 @@ int join(cudaStream_t stream) {
     BwdAux& ax = bwd_aux();
     if (!ax.ok || !ax.has_pending) return MHE_OK;
     return join_pending_on(stream);
+}
+// The pass is cut into chunks of consecutive layers (MHE_FUSED_BWD_CHUNKS, default 2): the data-gradient kernel of chunk c + 1 runs
+// on 80 of the 148 SMs while the weight-gradient GEMMs and the dcp sums of chunk c fill the others, instead of all of them
+// queueing up behind the last layer.
+static int bwd_chunks(int L) {
+    static int n = -1;
+    if (n < 0) {
+        const char* e = getenv("MHE_FUSED_BWD_CHUNKS");
+        n = e ? atoi(e) : 2;
+        if (n < 1) n = 1;
+        if (n > kMaxChunks) n = kMaxChunks;
+    }
+    return n < L ? n : L;
 }
 
 int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* saved, int R, int B, int direction,
@@ -1244,8 +1270,19 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         }
         attr_set = true;
     }
-    if (bwd_aux().ok) MHE_TRY(cuda_ok(cudaEventRecord(bwd_aux().start, stream), "fork replane"));
-    {
+    BwdAux& ax = bwd_aux();
+    const bool par = ax.ok;
+    const int nchunk = bwd_chunks(L.L);
+    cudaStream_t s0 = par ? ax.stream[0] : stream, s1 = par ? ax.stream[1] : stream, s2 = par ? ax.stream[2] : stream,
+                 sr = par ? ax.stream[3] : stream;
+    // steps [lo, hi) of chunk c (the pass walks the steps downwards); its layers are consecutive too
+    auto chunk_lo = [&](int c) { return L.L - (L.L * (c + 1)) / nchunk; };
+    auto chunk_hi = [&](int c) { return L.L - (L.L * c) / nchunk; };
+    auto first_layer = [&](int c) { return direction == 0 ? chunk_lo(c) : L.L - chunk_hi(c); };
+    auto launch_chunk = [&](int c) -> int {
+        BwdArgs ac = a;
+        ac.s_lo = chunk_lo(c); ac.s_hi = chunk_hi(c);
+        if (c > 0) ac.dout = din;                      // every CTA reads the rows it owns at the start and writes them at the end: in place
         ProbeScope probe("fused flow bwd", stream);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(tiles * kCluster); cfg.blockDim = dim3(kThreadsF); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
@@ -1253,61 +1290,76 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (cudaLaunchKernelEx(&cfg, flow_bwd_fused_kernel, *mW0, *mW1, *mW2, *mDh1, a) != cudaSuccess) {
+        if (cudaLaunchKernelEx(&cfg, flow_bwd_fused_kernel, *mW0, *mW1, *mW2, *mDh1, ac) != cudaSuccess) {
             set_error("fused flow bwd: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             return MHE_ERR_CUDA;
         }
-        MHE_TRY(check_launch("fused flow bwd"));
-    }
-    // (launched after the kernel so that its 80 clusters' CTAs get their SMs first; the re-planes fill the remaining ones)
-    {   // operands of the weight gradients (bfloat16 planes of the saved activations by layer, masked inputs): side stream, concurrent
-        BwdAux& ax0 = bwd_aux();
-        cudaStream_t sr = ax0.ok ? ax0.stream[0] : stream;
-        if (ax0.ok) {
-            MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax0.start, 0), "fork replane"));
-        }
-        dim3 grid(cdiv((int)nact, 256), L.L * 2);
-        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a0_, ws.a0b, nact, L.L, direction);
+        return check_launch("fused flow bwd");
+    };
+    // operands of the weight gradients (bfloat16 planes of the saved activations by layer, masked inputs) of chunk c: they only
+    // depend on the forward pass, so they run on their own stream while the data-gradient kernels run
+    auto launch_replane = [&](int c) -> int {
+        const int lo = chunk_lo(c), n = chunk_hi(c) - lo;
+        dim3 grid(cdiv((int)(nact / 8), 256), n * 2);
+        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a0_, ws.a0b, nact, L.L, direction, lo);
         MHE_TRY(check_launch("replane a0"));
-        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a1_, ws.a1b, nact, L.L, direction);
+        replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a1_, ws.a1b, nact, L.L, direction, lo);
         MHE_TRY(check_launch("replane a1"));
-        dim3 gx(cdiv(Rp, 128), kDp, L.L);
-        xm_transposed_kernel<<<gx, 128, 0, sr>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT);
+        dim3 gx(cdiv(Rp, 128), kDp, n);
+        xm_transposed_kernel<<<gx, 128, 0, sr>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT, first_layer(c));
         MHE_TRY(check_launch("xm transposed"));
-        if (ax0.ok) MHE_TRY(cuda_ok(cudaEventRecord(ax0.replaned, sr), "replaned"));
+        if (par) MHE_TRY(cuda_ok(cudaEventRecord(ax.replaned[c], sr), "replaned"));
+        return MHE_OK;
+    };
+    // weight gradients and dcp sums of chunk c: mutually independent, off the critical path of the data gradients
+    auto launch_wgrads = [&](int c) -> int {
+        const int l0 = first_layer(c), nb = (chunk_hi(c) - chunk_lo(c)) * 2;
+        const size_t po = (size_t)l0 * 2 * L.blk;                                  // parameter blocks of the chunk's first layer
+        const size_t ao = (size_t)l0 * 4 * L.H * Rp, so = (size_t)l0 * 4 * kDp * Rp;   // plane offsets (elements) by layer
+        if (par) {
+            MHE_TRY(cuda_ok(cudaEventRecord(ax.chunk_done[c], stream), "fork"));
+            for (int i = 0; i < 3; ++i) {
+                MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[i], ax.chunk_done[c], 0), "fork"));
+                MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[i], ax.replaned[c], 0), "fork"));
+            }
+        }
+        {   // dcp += sums over the hypotheses of dh0 / dh1 (the conditioning backward waits for it)
+            dim3 grid(L.H / 32, nb, 2 * cdiv(B, 64));
+            dcp_from_planes_kernel<<<grid, 256, 0, s1>>>(ws.dh0T, ws.dh1T, R, Rp, B, L.H, dcp, (long)L.L * 4 * L.H, l0 * 2);
+            MHE_TRY(check_launch("dcp from planes"));
+            if (par) MHE_TRY(cuda_ok(cudaEventRecord(ax.dcp_done[c], s1), "dcp done"));
+        }
+        {   // dW1 [out][in] += dh1T . a0T^T  (contraction over the rows)
+            GemmShape g{L.H, L.H, Rp, nb, 1, 1, 1};
+            MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh1T + ao, Rp, L.H, nb), ptk(ws.a0b + ao, Rp, L.H, nb), g, dparams + po + L.oW1, L.H, (long)L.blk, L.H, 0, s0,
+                                         "fused wgrad W1"));
+        }
+        {   // dW0 [feat][d] += dh0T . xmT^T
+            GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
+            MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh0T + ao, Rp, L.H, nb), ptk(ws.xmT + so, Rp, kDp, nb), g, dparams + po + L.oW0, L.D, (long)L.blk, L.D, 0, s1,
+                                         "fused wgrad W0"));
+        }
+        {   // dW2 [d][feat] += dpreT . a1T^T, computed as (a1T . dpreT^T)[feat][d] and stored transposed
+            GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
+            MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.a1b + ao, Rp, L.H, nb), ptk(ws.dpreT + so, Rp, kDp, nb), g, dparams + po + L.oW2, L.H, (long)L.blk, L.D, 1, s2,
+                                         "fused wgrad W2"));
+        }
+        return MHE_OK;
+    };
+
+    if (par) MHE_TRY(cuda_ok(cudaEventRecord(ax.start, stream), "fork replane"));
+    MHE_TRY(launch_chunk(0));
+    // (launched after the first kernel so that its clusters' CTAs get their SMs first; the re-planes fill the remaining ones)
+    if (par) MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax.start, 0), "fork replane"));
+    for (int c = 0; c < nchunk; ++c) MHE_TRY(launch_replane(c));
+    for (int c = 0; c < nchunk; ++c) {
+        if (c > 0) MHE_TRY(launch_chunk(c));
+        MHE_TRY(launch_wgrads(c));
     }
-    // Everything after the data-gradient kernel is off its critical path and mutually independent: the re-planes run on a side
-    // stream while the kernel runs (it fills 80 of the 148 SMs), the three weight-gradient GEMMs on three streams, the dcp sums on
-    // the caller's stream.  Fork / join with events (graph-capture safe).
-    BwdAux& ax = bwd_aux();
-    const bool par = ax.ok;
-    cudaStream_t s0 = par ? ax.stream[0] : stream, s1 = par ? ax.stream[1] : stream, s2 = par ? ax.stream[2] : stream;
-    const int nb = L.L * 2;
     if (par) {
-        MHE_TRY(cuda_ok(cudaEventRecord(ax.bwd_done, stream), "fork"));
-        for (int i = 0; i < 3; ++i) MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[i], ax.bwd_done, 0), "fork"));
-        MHE_TRY(cuda_ok(cudaStreamWaitEvent(s1, ax.replaned, 0), "fork"));
-        MHE_TRY(cuda_ok(cudaStreamWaitEvent(s2, ax.replaned, 0), "fork"));
-    }
-    {   // dW1 [out][in] += dh1T . a0T^T  (contraction over the rows)
-        GemmShape g{L.H, L.H, Rp, nb, 1, 1, 1};
-        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh1T, Rp, L.H, nb), ptk(ws.a0b, Rp, L.H, nb), g, dparams + L.oW1, L.H, (long)L.blk, L.H, 0, s0, "fused wgrad W1"));
-    }
-    {   // dW0 [feat][d] += dh0T . xmT^T
-        GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
-        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh0T, Rp, L.H, nb), ptk(ws.xmT, Rp, kDp, nb), g, dparams + L.oW0, L.D, (long)L.blk, L.D, 0, s1, "fused wgrad W0"));
-    }
-    {   // dW2 [d][feat] += dpreT . a1T^T, computed as (a1T . dpreT^T)[feat][d] and stored transposed
-        GemmShape g{L.H, kDp, Rp, nb, 1, 1, 1};
-        MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.a1b, Rp, L.H, nb), ptk(ws.dpreT, Rp, kDp, nb), g, dparams + L.oW2, L.H, (long)L.blk, L.D, 1, s2, "fused wgrad W2"));
-    }
-    {   // dcp += sums over the hypotheses of dh0 / dh1
-        dim3 grid(L.H / 32, nb, 2 * cdiv(B, 64));
-        dcp_from_planes_kernel<<<grid, 256, 0, stream>>>(ws.dh0T, ws.dh1T, R, Rp, B, L.H, dcp, (long)L.L * 4 * L.H);
-        MHE_TRY(check_launch("dcp from planes"));
-    }
-    if (par) {
+        for (int c = 0; c < nchunk; ++c) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, ax.dcp_done[c], 0), "join dcp"));
         for (int i = 0; i < 3; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.wgrad_done[i], ax.stream[i]), "join"));
+        // the re-plane stream is joined through the weight-gradient streams (they waited for replaned[c])
         if (async_wgrad()) ax.has_pending = true;    // the caller joins with mhe_flow_join() before reading dparams
         else MHE_TRY(join_pending_on(stream));
     }

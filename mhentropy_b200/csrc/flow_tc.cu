@@ -281,9 +281,10 @@ static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const E
     return launch_tc_gemm<64, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
 }
 
-static int g_grads_zero = 0;
+static int g_grads_zero = 0, g_dfeat_zero = 0;
 void set_grads_are_zero(int on) { g_grads_zero = on; }
 bool grads_are_zero() { return g_grads_zero != 0; }
+void set_dfeat_is_zero(int on) { g_dfeat_zero = on; }
 
 int wgrad_kmajor(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, float* dW, long ld, long batch_stride, int ncols, int transposed,
                  cudaStream_t stream, const char* what) {
@@ -380,7 +381,9 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
     MHE_TRY(check_launch("cond bias grad"));
     if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[0][0], wstream), "join cond wgrad"));
     if (dfeat) {   // dfeat [B][C] = sum_idx dcp[:, idx, :] Cw[idx]   (A K-major over h; B MN-major: cols = c, rows = h)
-        MHE_TRY(cuda_ok(cudaMemsetAsync(dfeat, 0, (size_t)B * L.C * sizeof(float), stream), "memset dfeat"));
+        // (a memset node between the dcp planes and this GEMM costs a scheduling hop inside a captured graph: the caller may zero
+        // dfeat ahead of time instead, mhe_flow_set_async bit 2)
+        if (!g_dfeat_zero) MHE_TRY(cuda_ok(cudaMemsetAsync(dfeat, 0, (size_t)B * L.C * sizeof(float), stream), "memset dfeat"));
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(P.cwb, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
         GemmShape g{B, L.C, L.H, L.L * 4, 1, 1, 1};

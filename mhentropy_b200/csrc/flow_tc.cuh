@@ -87,6 +87,7 @@ inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
 // The caller may promise that the weight slots of dparams are zero when the backward entry points run (mhe_flow_set_async bit 1):
 // the weight-gradient epilogues then store instead of read-modify-write.
 void set_grads_are_zero(int on);
+void set_dfeat_is_zero(int on);   // mhe_flow_set_async bit 2: dfeat is zero when cond_bwd runs (its memset is skipped)
 bool grads_are_zero();
 
 int wgrad_kmajor(const tc::PlaneTensor& A, const tc::PlaneTensor& B, tc::GemmShape g, float* dW, long ld, long batch_stride, int ncols,

@@ -1,6 +1,5 @@
 // z assembly, visible-keypoint reprojection, Laplace / prior / entropy reductions (reference network.py:455-831).
-#include "common.cuh"
-#include "loss_math.cuh"
+#include "loss_rows.cuh"
 
 namespace mhe {
 using namespace loss;
@@ -31,23 +30,7 @@ __global__ void combine_z_bwd_kernel(const float* __restrict__ dz, int R, int B,
     }
 }
 
-// Warp per row: lane k < 21 owns joint k (root / bone broadcast by shuffles), the 58 prior terms are spread over
-// the lanes, sums are warp reductions.  Same formulas as loss_math.cuh (host-checked there).
-struct RowGeom { float x0, x1, x2, bone, s, mu0, mu1; };
-
-__device__ __forceinline__ RowGeom row_geom(const mhe_loss_cfg& cfg, const float* __restrict__ j, const float* __restrict__ z, int lane) {
-    const bool on = lane < kNJ;
-    const float jx = on ? j[lane * 3] : 0.f, jy = on ? j[lane * 3 + 1] : 0.f, jz = on ? j[lane * 3 + 2] : 0.f;
-    const float rx = __shfl_sync(0xffffffffu, jx, cfg.root_idx), ry = __shfl_sync(0xffffffffu, jy, cfg.root_idx), rz = __shfl_sync(0xffffffffu, jz, cfg.root_idx);
-    const float bx = __shfl_sync(0xffffffffu, jx, cfg.norm_idx) - rx, by = __shfl_sync(0xffffffffu, jy, cfg.norm_idx) - ry, bz = __shfl_sync(0xffffffffu, jz, cfg.norm_idx) - rz;
-    RowGeom g;
-    g.bone = sqrtf(bx * bx + by * by + bz * bz);
-    g.x0 = (jx - rx) / g.bone; g.x1 = (jy - ry) / g.bone; g.x2 = (jz - rz) / g.bone;
-    g.s = expf(z[58]);
-    g.mu0 = g.s * g.x0 + z[59]; g.mu1 = g.s * g.x1 + z[60];
-    return g;
-}
-
+// Warp per row (loss_rows.cuh).
 __global__ void __launch_bounds__(128) reproj_rows_fwd_kernel(mhe_loss_cfg cfg, const float* __restrict__ joints, const float* __restrict__ z,
                                        const float* __restrict__ crop_uv, const float* __restrict__ vis, int R, int B,
                                        float* __restrict__ uv, float* __restrict__ row_lp) {
@@ -56,24 +39,7 @@ __global__ void __launch_bounds__(128) reproj_rows_fwd_kernel(mhe_loss_cfg cfg, 
     const int b = r % B;
     const float* zz = z + (long)r * kZ;
     const RowGeom g = row_geom(cfg, joints + (long)r * 63, zz, lane);
-    float lp = 0.f;
-    if (lane < kNJ) {
-        if (uv) { uv[(long)r * 42 + lane * 2] = g.mu0; uv[(long)r * 42 + lane * 2 + 1] = g.mu1; }
-        if (vis[b * kNJ + lane] == 1.f) {
-            const float log2b = logf(2.f * cfg.laplace_b);
-            lp = -(relu(fabsf(crop_uv[b * 42 + lane * 2] - g.mu0) - kLapEps) + kLapEps) / cfg.laplace_b - log2b
-                 - (relu(fabsf(crop_uv[b * 42 + lane * 2 + 1] - g.mu1) - kLapEps) + kLapEps) / cfg.laplace_b - log2b;
-        }
-    }
-    const float t3 = lane < 3 ? zz[lane] : 0.f;
-    const float r3 = sqrtf(warp_sum(t3 * t3));
-    if (lane == 0) { const float u = relu(r3 / cfg.th3_radius - 1.f); lp -= cfg.th3_alpha * u * u; }
-    for (int i = lane; i < 55; i += 32) {
-        const float box = i < 45 ? cfg.th45_box : cfg.bt_box, alpha = i < 45 ? cfg.th45_alpha : cfg.bt_alpha;
-        const float u = relu(fabsf(zz[3 + i]) / box - 1.f);
-        lp -= alpha * u * u;
-    }
-    lp = warp_sum(lp);
+    const float lp = reproj_row_fwd(cfg, g, zz, crop_uv + b * 42, vis + b * kNJ, lane, uv ? uv + (long)r * 42 : nullptr);
     if (lane == 0) row_lp[r] = lp;
 }
 
@@ -113,37 +79,8 @@ __global__ void __launch_bounds__(128) reproj_rows_bwd_kernel(mhe_loss_cfg cfg, 
     const float gr = gb / N;
     const float* zz = z + (long)r * kZ;
     const RowGeom g = row_geom(cfg, joints + (long)r * 63, zz, lane);
-    float dmu0 = 0.f, dmu1 = 0.f;
-    if (lane < kNJ && vis[b * kNJ + lane] == 1.f) {
-        const float d0 = crop_uv[b * 42 + lane * 2] - g.mu0, d1 = crop_uv[b * 42 + lane * 2 + 1] - g.mu1;
-        if (fabsf(d0) - kLapEps > 0.f) dmu0 = gr * sgn(d0) / cfg.laplace_b;
-        if (fabsf(d1) - kLapEps > 0.f) dmu1 = gr * sgn(d1) / cfg.laplace_b;
-    }
-    const float dt0 = warp_sum(dmu0), dt1 = warp_sum(dmu1), ds = warp_sum(dmu0 * g.x0 + dmu1 * g.x1);
-    const float dx0 = dmu0 * g.s, dx1 = dmu1 * g.s;
-    const float dbone = -warp_sum(dx0 * g.x0 + dx1 * g.x1) / g.bone;
-    float dr0 = dx0 / g.bone, dr1 = dx1 / g.bone, dr2 = 0.f;
-    if (lane == cfg.norm_idx) { dr0 += dbone * g.x0; dr1 += dbone * g.x1; dr2 += dbone * g.x2; }
-    const float s0 = warp_sum(dr0), s1 = warp_sum(dr1), s2 = warp_sum(dr2);
-    if (lane == cfg.root_idx) { dr0 -= s0; dr1 -= s1; dr2 -= s2; }
-    if (lane < kNJ) {
-        float* dj = djoints + (long)r * 63 + lane * 3;
-        dj[0] = dr0; dj[1] = dr1; dj[2] = dr2;
-    }
-    float* dzr = dz + (long)r * kZ;
-    const float t3 = lane < 3 ? zz[lane] : 0.f;
-    const float r3 = sqrtf(warp_sum(t3 * t3));
-    if (lane < 3) {
-        const float u = r3 / cfg.th3_radius - 1.f;
-        dzr[lane] = u > 0.f ? -gr * cfg.th3_alpha * 2.f * u / cfg.th3_radius * t3 / r3 : 0.f;
-    }
-    for (int i = lane; i < 55; i += 32) {
-        const float box = i < 45 ? cfg.th45_box : cfg.bt_box, alpha = i < 45 ? cfg.th45_alpha : cfg.bt_alpha;
-        const float v = zz[3 + i];
-        const float u = fabsf(v) / box - 1.f;
-        dzr[3 + i] = u > 0.f ? -gr * alpha * 2.f * u * sgn(v) / box : 0.f;
-    }
-    if (lane == 0) { dzr[58] = ds * g.s; dzr[59] = dt0; dzr[60] = dt1; if (dlog_q) dlog_q[r] = -gr; }
+    reproj_row_bwd(cfg, g, zz, crop_uv + b * 42, vis + b * kNJ, gr, lane, djoints + (long)r * 63, dz + (long)r * kZ);
+    if (lane == 0 && dlog_q) dlog_q[r] = -gr;
 }
 
 // MHEnt.sample epilogue: xyz, normalised verts and (pixel) uv
@@ -211,6 +148,23 @@ int mhe_reproj_loss_fwd(const mhe_loss_cfg* cfg, const float* joints, const floa
     cudaStream_t stream = (cudaStream_t)stream_;
     reproj_rows_fwd_kernel<<<cdiv(R, 4), 128, 0, stream>>>(*cfg, joints, z, crop_uv, vis, R, B, uv, row_log_p);
     MHE_TRY(check_launch("reproj rows fwd"));
+    if (log_p || h || q_log_p) {
+        image_reduce_kernel<<<cdiv(B, 64), 64, 0, stream>>>(row_log_p, log_q, R, B, log_p, h, q_log_p);
+        MHE_TRY(check_launch("image reduce"));
+    }
+    if (loss) {
+        loss_reduce_kernel<<<1, 256, 0, stream>>>(log_p, B, loss);
+        MHE_TRY(check_launch("loss reduce"));
+    }
+    return MHE_OK;
+}
+
+int mhe_image_loss_reduce(const float* row_log_p, const float* log_q, int R, int B, float* log_p, float* h, float* q_log_p, float* loss,
+                          void* stream_) {
+    MHE_REQUIRE(row_log_p && log_q && R >= 0 && B > 0 && R % B == 0, "image_loss_reduce: bad args");
+    MHE_REQUIRE(!loss || log_p, "image_loss_reduce: loss needs log_p");
+    if (R == 0) return MHE_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
     if (log_p || h || q_log_p) {
         image_reduce_kernel<<<cdiv(B, 64), 64, 0, stream>>>(row_log_p, log_q, R, B, log_p, h, q_log_p);
         MHE_TRY(check_launch("image reduce"));

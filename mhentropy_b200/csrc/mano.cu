@@ -2,6 +2,7 @@
 // vertex, row-tiled so each posedirs element is reused across the tile), regressed joint set, and
 // the exact backward.  Reference: hand/manopth/manolayer.py:110-274, hand/ManoLayer.py:45-60,141-148.
 #include "gemm_simt.cuh"
+#include "loss_rows.cuh"
 #include "mano_math.cuh"
 
 namespace mhe {
@@ -424,37 +425,13 @@ __device__ __forceinline__ void chain_bwd_step(WarpPose& W, int k, int p) {
     for (int cc = 0; cc < 3; ++cc) { W.dJ[k][cc] += o[cc]; W.dJ[p][cc] -= o[cc]; W.dGt[p][cc] += W.dGt[k][cc]; }
 }
 
-// Backward of the pose / chain, warp per row.  Vertex gradients arrive either through the workspace
-// (dA, dpm, dbv, dcen written by the mesh kernels) or, with tips_in_kernel, are formed here from djtr for the
-// five tip vertices (the joints-only training path: one kernel for the whole MANO backward).
-__global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano_consts c, const float* __restrict__ theta, int ld_theta,
-                                     const float* __restrict__ beta, int ld_beta, int R, int order, int tips_in_kernel,
-                                     const float* __restrict__ djtr, const float* __restrict__ dA_g, const float* __restrict__ dpm_g,
-                                     const float* __restrict__ dbv_g, const float* __restrict__ dcen_g,
-                                     float* __restrict__ dtheta, int ld_dtheta, float* __restrict__ dbeta, int ld_dbeta, int accumulate) {
-    __shared__ WarpPose s_w[kPoseWarps];
-    __shared__ PoseTables s_t;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kPoseWarps + warp;
-    stage_pose_tables(c, s_t, tips_in_kernel != 0);
-    __syncthreads();
-    if (r >= R) return;
-    WarpPose& W = s_w[warp];
-    const float* be = beta + (long)r * ld_beta;
-    if (djtr) for (int i = lane; i < kNJ * 3; i += 32) W.dj[i] = djtr[(long)r * kNJ * 3 + i] * kMM;   // this row's joint gradients, scaled
-    pose_fwd_warp(s_t, theta + (long)r * ld_theta, be, W, lane);
-
-    // vertex-side gradients -> W.dA, W.dpm, dbeta seed, centre gradient
-    float db = 0.f;                       // lane b < 10 owns dbeta[b]
-    float dc = 0.f;                       // lane cc < 3 owns the centre gradient component
-    for (int i = lane; i < kWsA; i += 32) W.dA[i / 12][i % 12] = (dA_g && !tips_in_kernel) ? dA_g[(long)r * 192 + i] : 0.f;
-    for (int k = lane; k < kWsPm; k += 32) W.dpm[k] = (dpm_g && !tips_in_kernel) ? dpm_g[(long)r * 136 + k] : 0.f;
-    if (!tips_in_kernel) {
-        if (dbv_g && lane < kShape) db = dbv_g[(long)r * 12 + lane];
-        if (dcen_g && lane < 3) dc = dcen_g[(long)r * 4 + lane];
-    }
-    __syncwarp();
-    if (tips_in_kernel && djtr) {
+// Backward of the pose / chain for the row a warp owns.  On entry W holds the forward state (pose_fwd_warp), W.dj the joint
+// gradients (already scaled to metres; read when have_dj), W.dA / W.dpm the vertex-side seeds (zero on the joints-only path); db
+// (lane b < 10: dbeta seed) and dc (lane cc < 3: centre gradient seed) are per-lane.  With tips_in_kernel the five tip vertices'
+// gradients are formed here from W.dj.  Leaves W.dpose (the 48 axis-angle gradients) and returns this lane's dbeta.
+__device__ __forceinline__ float pose_bwd_warp(const PoseTables& s_t, WarpPose& W, int lane, int order, bool tips_in_kernel, bool have_dj,
+                                               float db, float dc) {
+    if (tips_in_kernel && have_dj) {
         for (int t = 0; t < 5; ++t) {
             int slot = 0;
             for (int i = 0; i < kNJ; ++i) if (c_jtr_src[order][i] == kJ + t) slot = i;
@@ -480,7 +457,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
     // joint-position gradients: chain joints of djtr, and the centring (every output is relative to joint 4)
     for (int i = lane; i < kJ * 3; i += 32) W.dGt_out[i] = 0.f;
     __syncwarp();
-    if (djtr && lane < 3) {
+    if (have_dj && lane < 3) {
         for (int i = 0; i < kNJ; ++i) {
             const int src = c_jtr_src[order][i];
             if (src < kJ) {
@@ -514,23 +491,115 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
         for (int cc = 0; cc < 3; ++cc) W.dJ[0][cc] += W.dGt[0][cc];
     }
     __syncwarp();
-    if (lane < kShape) {
+    if (lane < kShape)
         for (int i = 0; i < kJ * 3; ++i) db = fmaf(s_t.js[i * kShape + lane], W.dJ[i / 3][i % 3], db);
+    if (lane < kJ) rodrigues_bwd(&W.pose[3 * lane], W.dR[lane], &W.dpose[3 * lane]);
+    __syncwarp();
+    return db;
+}
+// dtheta[i] from W.dpose: the root rotation directly, the 45 PCA coefficients through the component matrix
+__device__ __forceinline__ float pose_dtheta(const PoseTables& s_t, const WarpPose& W, int i) {
+    if (i < 3) return W.dpose[i];
+    float g = 0.f;
+    for (int j = 0; j < 45; ++j) g = fmaf(s_t.comps[(i - 3) * 45 + j], W.dpose[3 + j], g);
+    return g;
+}
+
+// Warp per row.  Vertex gradients arrive either through the workspace (dA, dpm, dbv, dcen written by the mesh kernels) or, with
+// tips_in_kernel, are formed here from djtr for the five tip vertices (the joints-only training path: one kernel for the whole
+// MANO backward).
+__global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano_consts c, const float* __restrict__ theta, int ld_theta,
+                                     const float* __restrict__ beta, int ld_beta, int R, int order, int tips_in_kernel,
+                                     const float* __restrict__ djtr, const float* __restrict__ dA_g, const float* __restrict__ dpm_g,
+                                     const float* __restrict__ dbv_g, const float* __restrict__ dcen_g,
+                                     float* __restrict__ dtheta, int ld_dtheta, float* __restrict__ dbeta, int ld_dbeta, int accumulate) {
+    __shared__ WarpPose s_w[kPoseWarps];
+    __shared__ PoseTables s_t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kPoseWarps + warp;
+    stage_pose_tables(c, s_t, tips_in_kernel != 0);
+    __syncthreads();
+    if (r >= R) return;
+    WarpPose& W = s_w[warp];
+    const float* be = beta + (long)r * ld_beta;
+    if (djtr) for (int i = lane; i < kNJ * 3; i += 32) W.dj[i] = djtr[(long)r * kNJ * 3 + i] * kMM;   // this row's joint gradients, scaled
+    pose_fwd_warp(s_t, theta + (long)r * ld_theta, be, W, lane);
+
+    // vertex-side gradients -> W.dA, W.dpm, dbeta seed, centre gradient
+    float db = 0.f;                       // lane b < 10 owns dbeta[b]
+    float dc = 0.f;                       // lane cc < 3 owns the centre gradient component
+    for (int i = lane; i < kWsA; i += 32) W.dA[i / 12][i % 12] = (dA_g && !tips_in_kernel) ? dA_g[(long)r * 192 + i] : 0.f;
+    for (int k = lane; k < kWsPm; k += 32) W.dpm[k] = (dpm_g && !tips_in_kernel) ? dpm_g[(long)r * 136 + k] : 0.f;
+    if (!tips_in_kernel) {
+        if (dbv_g && lane < kShape) db = dbv_g[(long)r * 12 + lane];
+        if (dcen_g && lane < 3) dc = dcen_g[(long)r * 4 + lane];
+    }
+    __syncwarp();
+    db = pose_bwd_warp(s_t, W, lane, order, tips_in_kernel != 0, djtr != nullptr, db, dc);
+    if (lane < kShape) {
         float* d = dbeta + (long)r * ld_dbeta + lane;
         *d = accumulate ? *d + db : db;
     }
-    if (lane < kJ) rodrigues_bwd(&W.pose[3 * lane], W.dR[lane], &W.dpose[3 * lane]);
-    __syncwarp();
     for (int i = lane; i < kPose; i += 32) {
-        float g;
-        if (i < 3) g = W.dpose[i];
-        else {
-            g = 0.f;
-            for (int j = 0; j < 45; ++j) g = fmaf(s_t.comps[(i - 3) * 45 + j], W.dpose[3 + j], g);
-        }
+        const float g = pose_dtheta(s_t, W, i);
         float* d = dtheta + (long)r * ld_dtheta + i;
         *d = accumulate ? *d + g : g;
     }
+}
+
+// The joints-only training path of one hypothesis in ONE launch (warp per row): MANO pose / chain / tip vertices forward, root / bone
+// normalisation + orthographic projection + Laplace(visible) + priors, and their backward down to dz.  The loss is linear in the row
+// terms, loss = -mean_b mean_n (row_log_p - log_q) (network.py:793-808, criteria.py:55,173), so with dloss = 1 every row's gradient
+// seed is the constant -1 / (B N) and nothing of the backward waits for a reduction.  z [R][61] = th3 | th45 | bt | logs | t.
+__global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_mano_consts c, mhe_loss_cfg cfg, const float* __restrict__ z,
+                                     const float* __restrict__ crop_uv, const float* __restrict__ vis, int R, int B, int order, float dloss,
+                                     float* __restrict__ jtr, float* __restrict__ uv, float* __restrict__ row_lp, float* __restrict__ dz,
+                                     float* __restrict__ dlog_q) {
+    __shared__ WarpPose s_w[kPoseWarps];
+    __shared__ PoseTables s_t;
+    __shared__ float s_jo[kPoseWarps][64], s_dz[kPoseWarps][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kPoseWarps + warp;
+    stage_pose_tables(c, s_t, true);
+    __syncthreads();
+    if (r >= R) return;
+    WarpPose& W = s_w[warp];
+    float* jo = s_jo[warp];
+    float* dzr = s_dz[warp];
+    const float* zz = z + (long)r * loss::kZ;
+    const int b = r % B;
+    pose_fwd_warp(s_t, zz, zz + 48, W, lane);
+    // the 21 output joints (chain joints + tip vertices, reordered, centred, millimetres)
+    for (int i = lane; i < kNJ * 3; i += 32) {
+        const int src = c_jtr_src[order][i / 3];
+        if (src < kJ) jo[i] = (W.Gt[src][i % 3] - W.Gt[kCenterJoint][i % 3]) * kMM;
+    }
+    for (int t = 0; t < 5; ++t) {
+        float vp[3];
+        tip_skin_warp(s_t, t, W, lane, vp);
+        if (lane < 3) {
+            const float o = (W.T[lane * 3 + 0] * vp[0] + W.T[lane * 3 + 1] * vp[1] + W.T[lane * 3 + 2] * vp[2] + W.T[9 + lane] - W.Gt[kCenterJoint][lane]) * kMM;
+            for (int i = 0; i < kNJ; ++i) if (c_jtr_src[order][i] == kJ + t) jo[i * 3 + lane] = o;
+        }
+        __syncwarp();
+    }
+    if (jtr) for (int i = lane; i < kNJ * 3; i += 32) jtr[(long)r * kNJ * 3 + i] = jo[i];
+    // reprojection + likelihood + priors, and their gradient with the constant seed
+    const loss::RowGeom g = loss::row_geom(cfg, jo, zz, lane);
+    const float lp = loss::reproj_row_fwd(cfg, g, zz, crop_uv + b * 42, vis + b * kNJ, lane, uv ? uv + (long)r * 42 : nullptr);
+    const float gr = -dloss / (float)R;                                   // -dloss / B / N
+    if (lane == 0) { row_lp[r] = lp; if (dlog_q) dlog_q[r] = -gr; }
+    loss::reproj_row_bwd(cfg, g, zz, crop_uv + b * 42, vis + b * kNJ, gr, lane, W.dj, dzr);
+    __syncwarp();
+    for (int i = lane; i < kNJ * 3; i += 32) W.dj[i] *= kMM;
+    for (int i = lane; i < kWsA; i += 32) W.dA[i / 12][i % 12] = 0.f;
+    for (int k = lane; k < kWsPm; k += 32) W.dpm[k] = 0.f;
+    __syncwarp();
+    const float db = pose_bwd_warp(s_t, W, lane, order, true, true, 0.f, 0.f);
+    if (lane < kShape) dzr[48 + lane] += db;
+    for (int i = lane; i < kPose; i += 32) dzr[i] += pose_dtheta(s_t, W, i);
+    __syncwarp();
+    for (int i = lane; i < loss::kZ; i += 32) dz[(long)r * loss::kZ + i] = dzr[i];
 }
 
 }  // namespace mhe
@@ -623,6 +692,17 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
                                                                                  mesh ? ws.dA : nullptr, mesh ? ws.dpm : nullptr, mesh ? ws.dbv : nullptr,
                                                                                  mesh ? ws.dcen : nullptr, dtheta, ld_dtheta, dbeta, ld_dbeta, accumulate);
     return check_launch("mano pose bwd");
+}
+
+int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* crop_uv, const float* vis,
+                                int R, int B, int joint_order, float dloss, float* jtr, float* uv, float* row_log_p, float* dz, float* dlog_q,
+                                void* stream) {
+    if (R == 0) return MHE_OK;
+    MHE_REQUIRE(c && cfg && z && crop_uv && vis && row_log_p && dz, "hypothesis_rows_fwd_bwd: null pointer");
+    MHE_REQUIRE(R > 0 && B > 0 && R % B == 0 && joint_order >= 0 && joint_order <= 1, "hypothesis_rows_fwd_bwd: bad sizes");
+    hypothesis_rows_kernel<<<cdiv(R, kPoseWarps), kPoseWarps * 32, 0, (cudaStream_t)stream>>>(*c, *cfg, z, crop_uv, vis, R, B, joint_order, dloss, jtr,
+                                                                                               uv, row_log_p, dz, dlog_q);
+    return check_launch("hypothesis rows fwd+bwd");
 }
 
 }  // extern "C"

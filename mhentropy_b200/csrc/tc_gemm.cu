@@ -1,7 +1,9 @@
 // Host side of the tensor-core GEMM: TMA tensor-map construction (driver entry point, no libcuda link),
 // a small tensor-map cache, the fp32 -> split-bf16 plane conversion and a raw GEMM entry point for tests.
 #include <cudaTypedefs.h>
+#include <cstring>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 #include "tc_gemm.cuh"
@@ -60,6 +62,31 @@ struct MapKeyHash {
         return h;
     }
 };
+
+int stages_for(const char* what, int requested, int max_stages) {
+    static std::vector<std::pair<std::string, int>> overrides;
+    static bool parsed = false;
+    if (!parsed) {
+        parsed = true;
+        if (const char* e = getenv("MHE_TC_STAGES")) {
+            std::string s(e);
+            size_t pos = 0;
+            while (pos < s.size()) {
+                size_t end = s.find(',', pos);
+                if (end == std::string::npos) end = s.size();
+                const std::string item = s.substr(pos, end - pos);
+                const size_t eq = item.find('=');
+                if (eq != std::string::npos) overrides.emplace_back(item.substr(0, eq), atoi(item.c_str() + eq + 1));
+                pos = end + 1;
+            }
+        }
+    }
+    int n = requested;
+    for (const auto& o : overrides)
+        if (what && strstr(what, o.first.c_str())) n = o.second;
+    if (n <= 0 || n > max_stages) n = max_stages;
+    return n;
+}
 
 // Tensor maps depend only on (pointer, geometry); they are pure descriptors, so caching them is safe even
 // when a buffer is freed and a new one is later allocated at the same address with the same geometry.

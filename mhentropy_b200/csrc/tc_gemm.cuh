@@ -139,6 +139,8 @@ struct GemmShape {
     int a_batch_mul;   // batch coordinate of A = batch * a_batch_mul (0 broadcasts one A to every batch)
     int b_batch_mul;
     int kfold = 1;     // consecutive batches contracted into ONE accumulator per CTA (batches % kfold == 0; the epilogue sees batch / kfold)
+    int stages = 0;    // operand ring depth (0 = as deep as shared memory allows).  Short contractions with large outputs run better with a
+                       // shallow ring: several CTAs share an SM and one's epilogue overlaps the others' loads and MMAs
 };
 
 template <int BN, int NPL>
@@ -157,9 +159,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi) {
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
     using Plan = SmemPlan<BN, NPL>;
-    constexpr int NS = Plan::kStages;
+    constexpr int NSmax = Plan::kStages;
+    const int NS = g.stages;          // launcher: 1 <= stages <= NSmax
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_accum;
+    __shared__ __align__(8) uint64_t bar_full[NSmax], bar_empty[NSmax], bar_accum;
     __shared__ uint32_t tmem_base_slot;
     __shared__ float s_stage[Epi::kStaged ? 4 : 1][32][33];   // epilogue transpose buffers, one per epilogue warp
 
@@ -314,6 +317,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// ring depth of a launch: the caller's choice, overridden by MHE_TC_STAGES="label=n,label=n" (substring match on the launch label)
+int stages_for(const char* what, int requested, int max_stages);
+
 // launch helper: builds (cached) tensor maps and launches.  A: rows = M (K-major) or K (MN-major), etc.
 const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status);
 
@@ -338,7 +344,10 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
     }
     ProbeScope probe(what, stream);
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), (g.batches / (g.kfold > 0 ? g.kfold : 1)) * g.ksplit);
-    if (launch_chain(kern, grid, dim3(kThreads), (size_t)Plan::kBytes, stream, *ma, *mb, g, epi) != cudaSuccess) {
+    GemmShape gs = g;
+    gs.stages = stages_for(what, g.stages, Plan::kStages);
+    const size_t smem = (size_t)gs.stages * Plan::kStageBytes + 1024;
+    if (launch_chain(kern, grid, dim3(kThreads), smem, stream, *ma, *mb, gs, epi) != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
         return MHE_ERR_CUDA;
     }

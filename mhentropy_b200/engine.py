@@ -56,6 +56,7 @@ class TrainStep:
         self.side = torch.cuda.Stream(self.dev)
         self.side2 = torch.cuda.Stream(self.dev)
         self.side3 = torch.cuda.Stream(self.dev)
+        self.side4 = torch.cuda.Stream(self.dev)
         self.jtr_mesh = f(R, 21, 3)
         self.mws_bytes = L.mhe_mano_workspace_bytes(R, 0)
         self.mws = torch.empty(self.mws_bytes, dtype=torch.uint8, device=dev)
@@ -85,42 +86,46 @@ class TrainStep:
                 check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 2, _lib.stream_ptr(self.dev)), 'pack_weights')
                 self.dflat.zero_()
                 self.dcp.zero_()
+                self.dfeat.zero_()
         check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
         if self.tc:
             torch.cuda.current_stream(self.dev).wait_stream(self.side3)
         check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
                                   ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
-        check(L.mhe_std_normal_logp_fwd(ptr(self.z0), ptr(self.logdet), -1.0, R, shape.dim, ptr(self.log_q), s), 'log_q')
+        main = torch.cuda.current_stream(self.dev)
+        # log q and the image-level reductions are outputs only (the loss is linear in the row terms, so the backward's seeds are
+        # constants): they run on a side stream, off the chain flow forward -> z -> per-row kernel -> flow backward
+        self.side4.wait_stream(main)
+        with torch.cuda.stream(self.side4):
+            check(L.mhe_std_normal_logp_fwd(ptr(self.z0), ptr(self.logdet), -1.0, R, shape.dim, ptr(self.log_q),
+                                            _lib.stream_ptr(self.dev)), 'log_q')
         check(L.mhe_combine_z_fwd(ptr(self.x), ptr(self.z_det), R, B, ptr(z), s), 'combine_z')
-        # joints (chain + the five tip vertices) feed the loss: one kernel on the main stream.  The 778-vertex mesh is an
-        # output nothing downstream reads, so it is skinned on the side stream while the loss and the backward run.
-        check(L.mhe_mano_fwd(self.consts, theta, 61, beta, 61, R, 1, None, ptr(self.jtr), None, ws, wsb, s), 'mano_fwd')
+        # The 778-vertex mesh is an output nothing downstream reads: it is skinned on a side stream while the loss and the
+        # backward run.
         if self.verts is not None:
-            main = torch.cuda.current_stream(self.dev)
             self.side2.wait_stream(main)
             with torch.cuda.stream(self.side2):
                 check(L.mhe_mano_fwd(self.consts, theta, 61, beta, 61, R, 1, ptr(self.verts), ptr(self.jtr_mesh), None, ptr(self.mws),
                                      self.mws_bytes, _lib.stream_ptr(self.dev)), 'mano_fwd mesh')
-        check(L.mhe_reproj_loss_fwd(self.cfg, ptr(self.jtr), ptr(z), ptr(self.crop_uv), ptr(self.vis), ptr(self.log_q), R, B,
-                                    ptr(self.uv), ptr(self.row_lp), ptr(self.log_p), ptr(self.h), ptr(self.qlp), ptr(self.loss), s),
-              'reproj_loss_fwd')
-        # ---- backward (dloss = 1)
         if self.tc:
-            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+            main.wait_stream(self.side)                    # dflat / dcp / dfeat zeroed, bfloat16 planes converted
         else:
             self.dflat.zero_()
             self.dcp.zero_()
-        check(L.mhe_reproj_loss_bwd(self.cfg, ptr(self.jtr), ptr(z), ptr(self.crop_uv), ptr(self.vis), R, B, None, None,
-                                    ptr(self.djtr), ptr(self.dz), ptr(self.dlog_q), s), 'reproj_loss_bwd')
-        dz = self.dz.data_ptr()
-        check(L.mhe_mano_bwd(self.consts, theta, 61, beta, 61, R, 1, None, ptr(self.djtr), None, dz, 61, dz + 48 * 4, 61, 1,
-                             ws, wsb, s), 'mano_bwd')
+        # ---- MANO joints + reprojection / priors forward AND backward (dloss = 1) of every hypothesis: one kernel
+        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), ptr(self.crop_uv), ptr(self.vis), R, B, 1, 1.0,
+                                            ptr(self.jtr), ptr(self.uv), ptr(self.row_lp), ptr(self.dz), ptr(self.dlog_q), s), 'hypothesis_rows')
+        self.side4.wait_stream(main)
+        with torch.cuda.stream(self.side4):
+            check(L.mhe_image_loss_reduce(ptr(self.row_lp), ptr(self.log_q), R, B, ptr(self.log_p), ptr(self.h), ptr(self.qlp),
+                                          ptr(self.loss), _lib.stream_ptr(self.dev)), 'image_loss_reduce')
         check(L.mhe_combine_z_bwd(ptr(self.dz), R, B, ptr(self.dx), ptr(self.dz_det), s), 'combine_z_bwd')
         # log_q = log N(z0) - logdet  ->  dL/dlogdet = -dL/dlog_q
         # the weight-gradient GEMMs of the pass keep running on the library's streams while the conditioning backward (which only
         # needs dcp) is enqueued; mhe_flow_join() brings them back before the step ends
-        # (bit 1: dflat was zeroed at the start of the step, so the weight-gradient epilogues may store instead of accumulate)
-        check(L.mhe_flow_set_async(3), 'set_async')
+        # (bit 1: dflat was zeroed at the start of the step, so the weight-gradient epilogues may store instead of accumulate;
+        #  bit 2: so was dfeat)
+        check(L.mhe_flow_set_async(7 if self.tc else 3), 'set_async')
         try:
             check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
                                       ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
@@ -130,6 +135,7 @@ class TrainStep:
             check(L.mhe_flow_set_async(0), 'set_async')
         check(L.mhe_flow_join(s), 'flow_join')
         torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
+        torch.cuda.current_stream(self.dev).wait_stream(self.side4)    # ... and the loss reductions
 
     def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
         """Copy one batch (host or device tensors) into the static input buffers."""

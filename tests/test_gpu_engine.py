@@ -61,3 +61,40 @@ def test_engine_matches_autograd_path_and_oracle(use_graph, B, S, precision):
     # mesh is materialised in the engine exactly as the reference's get_loss does
     dec = mo.mano_wrapper_forward(mo.mano_constants(mano), ref['z'][:, :48].detach(), ref['z'][:, 48:58].detach())
     assert (eng.verts.cpu() - dec['mesh']).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize('R,B', [(640, 64), (15, 5), (7, 7)])
+def test_hypothesis_rows_kernel_matches_separate_kernels(R, B):
+    """mhe_hypothesis_rows_fwd_bwd (one launch) == mano_fwd + reproj_loss_fwd + reproj_loss_bwd + mano_bwd, through the C ABI."""
+    from mhentropy_b200 import _lib
+    from mhentropy_b200._lib import check, lib, ptr
+    head = MHEntHead(mano_data=synthetic_mano(0)).to(DEV)
+    consts, cfg, L = head.mano_dec.mano_layer._consts(torch.device(DEV)), head.loss_cfg, lib()
+    g = torch.Generator().manual_seed(R)
+    z = torch.cat([0.5 * torch.randn(R, 3, generator=g), 1.2 * torch.randn(R, 45, generator=g), 0.03 * torch.randn(R, 10, generator=g),
+                   -1.2 + 0.1 * torch.randn(R, 1, generator=g), 0.1 * torch.randn(R, 2, generator=g)], 1).to(DEV).contiguous()
+    crop_uv = (torch.rand(B, 42, generator=g) * 2 - 1).to(DEV)
+    vis = (torch.rand(B, 21, generator=g) < 0.7).float().to(DEV)
+    log_q = torch.randn(R, generator=g).to(DEV)
+    s = _lib.stream_ptr(torch.device(DEV))
+    f = lambda *sh: torch.empty(*sh, device=DEV)  # noqa: E731
+    wsb = L.mhe_mano_workspace_bytes(R, 0)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    theta, beta = z.data_ptr(), z.data_ptr() + 48 * 4
+    jtr0, uv0, lp0, dj0, dz0, dlq0 = f(R, 21, 3), f(R, 42), f(R), f(R, 21, 3), f(R, 61), f(R)
+    logp, h, qlp, loss = f(B), f(B), f(B), f(1)
+    check(L.mhe_mano_fwd(consts, theta, 61, beta, 61, R, 1, None, ptr(jtr0), None, ptr(ws), wsb, s), 'mano_fwd')
+    check(L.mhe_reproj_loss_fwd(cfg, ptr(jtr0), ptr(z), ptr(crop_uv), ptr(vis), ptr(log_q), R, B, ptr(uv0), ptr(lp0), ptr(logp), ptr(h),
+                                ptr(qlp), ptr(loss), s), 'reproj_fwd')
+    check(L.mhe_reproj_loss_bwd(cfg, ptr(jtr0), ptr(z), ptr(crop_uv), ptr(vis), R, B, None, None, ptr(dj0), ptr(dz0), ptr(dlq0), s), 'reproj_bwd')
+    check(L.mhe_mano_bwd(consts, theta, 61, beta, 61, R, 1, None, ptr(dj0), None, dz0.data_ptr(), 61, dz0.data_ptr() + 48 * 4, 61, 1,
+                         ptr(ws), wsb, s), 'mano_bwd')
+    jtr1, uv1, lp1, dz1, dlq1 = f(R, 21, 3), f(R, 42), f(R), f(R, 61), f(R)
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(z), ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr1), ptr(uv1), ptr(lp1), ptr(dz1),
+                                        ptr(dlq1), s), 'rows')
+    logp1, loss1 = f(B), f(1)
+    check(L.mhe_image_loss_reduce(ptr(lp1), ptr(log_q), R, B, ptr(logp1), None, None, ptr(loss1), s), 'reduce')
+    torch.cuda.synchronize()
+    assert torch.equal(jtr1, jtr0) and torch.equal(uv1, uv0) and torch.equal(lp1, lp0) and torch.equal(dlq1, dlq0)
+    assert rel(dz1, dz0) < 1e-6
+    assert torch.equal(logp1, logp) and torch.equal(loss1, loss)
