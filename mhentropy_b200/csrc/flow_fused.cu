@@ -1183,9 +1183,16 @@ static int cuda_ok(cudaError_t e, const char* what) {
 }
 
 constexpr int kMaxChunks = 4;
+// Keeps the weight-gradient GEMMs of a chunk off the SMs for a few microseconds after the chunk's data-gradient kernel ends, so that
+// the NEXT chunk's cluster kernel (which needs 80 entirely free SMs) is placed first; otherwise it waits for the GEMM CTAs that won
+// the race to drain (~12 us measured).
+__global__ void head_start_kernel(unsigned ns) {
+    const long long t0 = gtime();
+    while (gtime() - t0 < (long long)ns) __nanosleep(256);
+}
 struct BwdAux {
     cudaStream_t stream[4] = {nullptr, nullptr, nullptr, nullptr};     // [0..2]: weight gradients (W1, W0 + dcp, W2), [3]: re-planes
-    cudaEvent_t start = nullptr, replaned[kMaxChunks] = {}, chunk_done[kMaxChunks] = {}, dcp_done[kMaxChunks] = {},
+    cudaEvent_t start = nullptr, replaned[kMaxChunks] = {}, chunk_done[kMaxChunks] = {}, dcp_done[kMaxChunks] = {}, gate[kMaxChunks] = {},
                 wgrad_done[3] = {nullptr, nullptr, nullptr};
     bool has_pending = false;
     bool ok = false;
@@ -1199,7 +1206,7 @@ static BwdAux& bwd_aux() {
         auto ev = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
         for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 3; ++i) ev(&a.wgrad_done[i]);
-        for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); }
+        for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); ev(&a.gate[i]); }
         ev(&a.start);
         a.ok = ok;
     }
@@ -1232,6 +1239,12 @@ static int bwd_chunks(int L) {
         if (n > kMaxChunks) n = kMaxChunks;
     }
     return n < L ? n : L;
+}
+
+static unsigned head_start_ns() {
+    static int ns = -1;
+    if (ns < 0) { const char* e = getenv("MHE_FUSED_HEAD_START_NS"); ns = e ? atoi(e) : 6000; if (ns < 0) ns = 0; }
+    return (unsigned)ns;
 }
 
 int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* saved, int R, int B, int direction,
@@ -1318,8 +1331,16 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         const size_t ao = (size_t)l0 * 4 * L.H * Rp, so = (size_t)l0 * 4 * kDp * Rp;   // plane offsets (elements) by layer
         if (par) {
             MHE_TRY(cuda_ok(cudaEventRecord(ax.chunk_done[c], stream), "fork"));
+            cudaEvent_t go = ax.chunk_done[c];
+            if (c + 1 < nchunk && head_start_ns() > 0) {   // another cluster kernel follows: let it take its SMs first
+                MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax.chunk_done[c], 0), "fork"));
+                head_start_kernel<<<1, 1, 0, sr>>>(head_start_ns());
+                MHE_TRY(check_launch("head start"));
+                MHE_TRY(cuda_ok(cudaEventRecord(ax.gate[c], sr), "fork"));
+                go = ax.gate[c];
+            }
             for (int i = 0; i < 3; ++i) {
-                MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[i], ax.chunk_done[c], 0), "fork"));
+                MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[i], go, 0), "fork"));
                 MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[i], ax.replaned[c], 0), "fork"));
             }
         }

@@ -249,15 +249,16 @@ __global__ void replane_kernel(const bf16* __restrict__ src, bf16* __restrict__ 
     put_planes<false>(dst + b * 2 * n + k, n, v);
 }
 
+// grid (cp_ld / 256, 8): block row y sums images y, y + 8, ... and adds its share (the slots accumulate anyway)
 __global__ void cond_bias_grad_kernel(const float* __restrict__ dcp, int B, long cp_ld, int H, float* __restrict__ dparams,
                                       size_t cb_base, size_t cb_stride, size_t blk, size_t ob0, size_t ob1) {
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= cp_ld) return;
     float acc = 0.f;
-    for (int b = 0; b < B; ++b) acc += dcp[(long)b * cp_ld + n];
+    for (int b = blockIdx.y; b < B; b += gridDim.y) acc += dcp[(long)b * cp_ld + n];
     const int idx = (int)(n / H), h = (int)(n % H);
-    dparams[cb_base + (size_t)idx * cb_stride + h] += acc;
-    dparams[(size_t)(idx >> 1) * blk + ((idx & 1) ? ob1 : ob0) + h] += acc;
+    atomicAdd(dparams + cb_base + (size_t)idx * cb_stride + h, acc);
+    atomicAdd(dparams + (size_t)(idx >> 1) * blk + ((idx & 1) ? ob1 : ob0) + h, acc);
 }
 
 static int cuda_ok(cudaError_t e, const char* what) {
@@ -370,6 +371,14 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         MHE_TRY(cuda_ok(cudaEventRecord(aux.ready[0], stream), "fork cond wgrad"));
         MHE_TRY(cuda_ok(cudaStreamWaitEvent(wstream, aux.ready[0], 0), "fork cond wgrad"));
     }
+    {   // bias gradients: column sums of dcp, independent of both GEMMs -> their own stream, enqueued first (a small kernel behind a
+        // many-wave GEMM only starts when that GEMM's last wave has been placed)
+        cudaStream_t bstream = fork ? aux.stream[1] : stream;
+        if (fork) MHE_TRY(cuda_ok(cudaStreamWaitEvent(bstream, aux.ready[0], 0), "fork cond bias grad"));
+        cond_bias_grad_kernel<<<dim3(cdiv((int)cp_ld, 256), 8), 256, 0, bstream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
+        MHE_TRY(check_launch("cond bias grad"));
+        if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[1][0], bstream), "join cond bias grad"));
+    }
     {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat      (A MN-major: cols = h, rows = b; B MN-major: cols = c, rows = b)
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
@@ -377,8 +386,6 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
         MHE_TRY((gemm<true, true, false>(A, Bt, g, e, wstream, "tc cond wgrad")));
     }
-    cond_bias_grad_kernel<<<cdiv((int)cp_ld, 256), 256, 0, wstream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
-    MHE_TRY(check_launch("cond bias grad"));
     if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[0][0], wstream), "join cond wgrad"));
     if (dfeat) {   // dfeat [B][C] = sum_idx dcp[:, idx, :] Cw[idx]   (A K-major over h; B MN-major: cols = c, rows = h)
         // (a memset node between the dcp planes and this GEMM costs a scheduling hop inside a captured graph: the caller may zero
@@ -387,11 +394,15 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(P.cwb, L.C, L.H, L.C, (long)L.H * L.C, L.L * 4, (long)2 * L.H * L.C);
         GemmShape g{B, L.C, L.H, L.L * 4, 1, 1, 1};
-        g.kfold = (L.L * 4) % 4 == 0 ? 4 : ((L.L * 4) % 2 == 0 ? 2 : 1);   // every batch lands on the same output: contract 4 per CTA, 4x fewer atomics
+        g.kfold = (L.L * 4) % 4 == 0 ? 4 : ((L.L * 4) % 2 == 0 ? 2 : 1);
+        if (const char* e = getenv("MHE_DFEAT_KFOLD")) { const int kf = atoi(e); if (kf >= 1 && (L.L * 4) % kf == 0) g.kfold = kf; }   // every batch lands on the same output: contract 4 per CTA, 4x fewer atomics
         EpiAtomicRows e{dfeat, L.C, L.C};
         MHE_TRY((gemm<false, true, false>(A, Bt, g, e, stream, "tc cond dfeat")));
     }
-    if (fork) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0][0], 0), "join cond wgrad"));
+    if (fork) {
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[0][0], 0), "join cond wgrad"));
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[1][0], 0), "join cond bias grad"));
+    }
     return MHE_OK;
 }
 

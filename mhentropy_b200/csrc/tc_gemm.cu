@@ -130,6 +130,39 @@ __global__ void split_planes_kernel(const float* __restrict__ src, long src_ld, 
     if (planes > 1) d[per] = to16<F16>(v - from16<F16>(hi));
 }
 
+// padded / strided sources, 8 outputs per thread (16-byte stores into both planes; cols_p % 8 == 0): scalar loads, L1-cached
+template <bool F16>
+__global__ void __launch_bounds__(256) split_planes_pad8_kernel(const float* __restrict__ src, long src_ld, long src_batch, int rows, int cols,
+                                                                const float* __restrict__ colscale, uint16_t* __restrict__ dst, int rows_p, int cols_p) {
+    const long i8 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const long per = (long)rows_p * cols_p;
+    if (i8 >= per) return;
+    const int b = blockIdx.y;
+    const int r = (int)(i8 / cols_p), c0 = (int)(i8 % cols_p);
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = c0 + 2 * k + e;
+            float x = 0.f;
+            if (r < rows && c < cols) {
+                x = __ldg(src + (long)b * src_batch + (long)r * src_ld + c);
+                if (colscale) x *= __ldg(colscale + c);
+            }
+            v[e] = x;
+        }
+        const uint16_t h0 = to16<F16>(v[0]), h1 = to16<F16>(v[1]);
+        const uint16_t l0 = to16<F16>(v[0] - from16<F16>(h0)), l1 = to16<F16>(v[1] - from16<F16>(h1));
+        hw[k] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        lw[k] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    uint16_t* d = dst + (long)b * 2 * per + i8;
+    *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(d + per) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
 // dense, unpadded, 4 elements per thread (weights): src [batches][n4*4] -> hi / lo planes
 template <bool F16>
 __global__ void split_planes_vec4_kernel(const float4* __restrict__ src, long src_batch4, long n4, uint16_t* __restrict__ dst) {
@@ -159,6 +192,12 @@ int split_planes(const float* src, long src_ld, long src_batch, int rows, int co
         if (f16) split_planes_vec4_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), src_batch / 4, n / 4, dst);
         else split_planes_vec4_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), src_batch / 4, n / 4, dst);
         return check_launch("split planes vec4");
+    }
+    if (planes == 2 && cols_p % 8 == 0 && ((uintptr_t)dst & 15) == 0) {
+        dim3 grid8(cdiv((int)((long)rows_p * cols_p / 8), 256), batches);
+        if (f16) split_planes_pad8_kernel<true><<<grid8, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p);
+        else split_planes_pad8_kernel<false><<<grid8, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p);
+        return check_launch("split planes pad8");
     }
     dim3 grid(cdiv((int)((long)rows_p * cols_p), 256), batches);
     if (f16) split_planes_kernel<true><<<grid, 256, 0, stream>>>(src, src_ld, src_batch, rows, cols, colscale, dst, rows_p, cols_p, planes);

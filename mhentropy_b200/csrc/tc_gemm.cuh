@@ -346,6 +346,10 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), (g.batches / (g.kfold > 0 ? g.kfold : 1)) * g.ksplit);
     GemmShape gs = g;
     gs.stages = stages_for(what, g.stages, Plan::kStages);
+    {   // a ring deeper than the contraction is wasted shared memory: short contractions leave room for several CTAs per SM
+        const int kb_total = cdiv(g.K, BK), kb_per = cdiv(kb_total, g.ksplit > 0 ? g.ksplit : 1) * (g.kfold > 0 ? g.kfold : 1);
+        if (gs.stages > kb_per) gs.stages = kb_per > 0 ? kb_per : 1;
+    }
     const size_t smem = (size_t)gs.stages * Plan::kStageBytes + 1024;
     if (launch_chain(kern, grid, dim3(kThreads), smem, stream, *ma, *mb, gs, epi) != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
