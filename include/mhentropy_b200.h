@@ -94,6 +94,9 @@ size_t mhe_flow_cond_workspace_bytes(mhe_flow_shape s, int B);
 /* Hoisted conditioning projections (reference flows.py:107-109 "Can be pre-processed"):
  *   cp[b][idx][h] = sum_c feat[b][c]*Cw[idx][h][c] + Cb[idx][h] + b_j[h]      (b_j = l.j.bias folded in)
  * feat [B][C] -> cp [B][L*4][H].                                                               */
+/* 1 when mhe_flow_cond_fwd on the tensor-core path reads the conditioning half planes of `packed` for B images (so
+ * mhe_flow_pack_weights(which & 4) must have refreshed them); 0 when it streams the fp32 weights directly (B <= 128). */
+int mhe_flow_cond_fwd_uses_planes(mhe_flow_shape s, int B);
 int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* feat, int B, float* cp,
                       void* workspace, size_t workspace_bytes, void* stream);
 /* dcp [B][L*4][H] -> dparams (accumulate: Cw, Cb, b0, b1 slots), dfeat [B][C] (overwritten; may be NULL) */

@@ -21,7 +21,7 @@ LIB = os.path.join(PKG, 'libmhentropy_b200.so')
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '-Xcompiler', '-fPIC', '-DMHE_SM=100', '--expt-relaxed-constexpr',
-]
+] + os.environ.get('MHE_NVCC_EXTRA', '').split()
 
 
 def _nvcc() -> str:

@@ -295,6 +295,12 @@ int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, i
     return tcflow::pack_weights(L, params, packed, which, (cudaStream_t)stream);
 }
 
+int mhe_flow_cond_fwd_uses_planes(mhe_flow_shape s, int B) {
+    if (!valid_shape(s)) return 0;
+    FlowLayout L(s);
+    return tcflow::supported(L) && !tcflow::cond_direct_supported(L, B) ? 1 : 0;
+}
+
 int mhe_flow_cond_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* feat, int B, float* cp,
                       void* workspace, size_t workspace_bytes, void* stream_) {
     MHE_REQUIRE(valid_shape(s), "cond_fwd: bad shape");

@@ -20,6 +20,10 @@ constexpr int kXs = 49;                        // row stride of the fp32 x tile 
 constexpr int kActMax = 24;                    // active (transformed) dims per layer the in-cluster exchange is sized for
 constexpr int kRecvBytes = 2 * kCluster * kActMax * 8 * 4;   // [parity][source CTA][active dim][8 rows] fp32
 constexpr int kSmemBytes = kASlots * kABytes + kBSlots * kBBytes + kXaBytes + NT * kXs * 4 + kRecvBytes + 1024 /*align*/;
+// the backward keeps only the 8 gradient rows a CTA owns (not the 64-row x tile): the room buys a third B slot
+constexpr int kBSlotsBwd = 3;
+constexpr int kSmemBytesBwd = kASlots * kABytes + kBSlotsBwd * kBBytes + kXaBytes + 8 * kXs * 4 + kRecvBytes + 1024 /*align*/;
+static_assert(kSmemBytesBwd <= 232448, "shared memory of the fused backward kernel");
 constexpr int kTmemCols = 512;                 // three accumulators of 128 columns: [0,64) = Ah.Bh + Al.Bh, [64,128) = Ah.Bl (summed in the epilogue)
 constexpr int kAcc0 = 0, kAcc1 = 128, kAcc2 = 256;
 
@@ -59,7 +63,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            MHE_MBAR_POLL ".parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (spin > (1u << 24)) __trap();
@@ -136,6 +140,7 @@ __device__ __forceinline__ float fast_tanh_f(float x) {   // 1 - 2/(e^{2x}+1); s
 }
 
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define BSTAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[(p.L - 1 - step) * 64 + (slot)] = clock64(); } while (0)
 #define MHE_STAMP(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[step * 64 + (slot)] = clock64(); } while (0)
 
 // Copy the CTA's slice (128 features x 64 rows, split planes, in xa: [k-block][hi | lo][64 k-rows][128 B], 16-byte chunks swizzled)
@@ -510,7 +515,8 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 store_slice(v, nullptr, nullptr);
                 tcgen05_fence_before();
                 mbar_arrive(smem_u32(&bar_a1));
-                if (p.save) {   // saved for the backward; off the critical path (G2 only reads xa)
+                if (p.save) {   // saved for the backward; off the critical path (G2 only reads xa).  (Storing the planes straight from
+                    // the registers instead - 32 scattered 16-byte segments per instruction - measured slower than this coalesced copy.)
                     worker_sync();
                     copy_slice_to_global(xa, p.a1T + (size_t)ab * 2 * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
                 }
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(kThreadsF, 1)
 flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
                       const __grid_constant__ CUtensorMap mapW2, const __grid_constant__ CUtensorMap mapDh1, BwdArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_fullA[kASlots], bar_emptyA[kASlots], bar_fullB[kBSlots], bar_emptyB[kBSlots], bar_acc[3];
+    __shared__ __align__(8) uint64_t bar_fullA[kASlots], bar_emptyA[kASlots], bar_fullB[kBSlotsBwd], bar_emptyB[kBSlotsBwd], bar_acc[3];
     __shared__ __align__(8) uint64_t bar_xm, bar_own, bar_a1, bar_a0, bar_part, bar_dpre;
     __shared__ uint32_t tmem_slot;
     __shared__ float gls[8];
@@ -637,9 +643,9 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
     __shared__ int nact_s[16], npas_s[16];
 
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t ringA = smem0, ringB = ringA + kASlots * kABytes, xa = ringB + kBSlots * kBBytes;
+    const uint32_t ringA = smem0, ringB = ringA + kASlots * kABytes, xa = ringB + kBSlotsBwd * kBBytes;
     float* gs = reinterpret_cast<float*>(smem_raw + (xa - smem_u32(smem_raw)) + kXaBytes);   // [8][kXs]: gradient rows this CTA owns (rows 8 rank ..)
-    float* recv = gs + NT * kXs;                // [2 parities][8 source CTAs][kActMax][8 rows]: partial input gradients of the owned rows
+    float* recv = gs + 8 * kXs;                // [2 parities][8 source CTAs][kActMax][8 rows]: partial input gradients of the owned rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int net = rank >> 2, j = rank & 3;
@@ -649,7 +655,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kASlots; ++s) { mbar_init(smem_u32(&bar_fullA[s]), 1); mbar_init(smem_u32(&bar_emptyA[s]), 1); }
-        for (int s = 0; s < kBSlots; ++s) { mbar_init(smem_u32(&bar_fullB[s]), 1); mbar_init(smem_u32(&bar_emptyB[s]), 1); }
+        for (int s = 0; s < kBSlotsBwd; ++s) { mbar_init(smem_u32(&bar_fullB[s]), 1); mbar_init(smem_u32(&bar_emptyB[s]), 1); }
         for (int s = 0; s < 3; ++s) mbar_init(smem_u32(&bar_acc[s]), 1);
         mbar_init(smem_u32(&bar_xm), 1);
         mbar_init(smem_u32(&bar_a1), kWorkers);
@@ -722,7 +728,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 fence_proxy_async();
                 for (int i = 2; i < nkb; ++i) {
                     const int kb = (2 * j + i) % nkb;
-                    const uint32_t s = q % kBSlots, use = q / kBSlots;
+                    const uint32_t s = q % kBSlotsBwd, use = q / kBSlotsBwd;
                     ++q;
                     mbar_wait(smem_u32(&bar_emptyB[s]), (use & 1) ^ 1);
                     const uint32_t full = smem_u32(&bar_fullB[s]), base = ringB + s * kBBytes;
@@ -763,7 +769,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                             tcgen05_fence_after();
                             issue_kblock<true, true, false>(tmem + kAcc1, abase, kAPlane, xa + i * 16384, 8192, acc, p.two_mma);
                         } else {
-                            const uint32_t sb = qb % kBSlots, useb = qb / kBSlots;
+                            const uint32_t sb = qb % kBSlotsBwd, useb = qb / kBSlotsBwd;
                             ++qb;
                             mbar_wait(smem_u32(&bar_fullB[sb]), useb & 1);
                             tcgen05_fence_after();
@@ -816,7 +822,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             }
         };
         // 32 gradients of feature fl (rows 32 ch ..) masked by lrelu'(saved activation), as bfloat16 planes -> xa slice
-        auto store_grad_slice = [&](float* v, const uint4* sg) {
+        auto store_grad_slice = [&](float* v, const uint4* sg, uint4* ghi, uint4* glo) {
             uint32_t sw[16];
 #pragma unroll
             for (int i = 0; i < 4; ++i) { sw[4 * i] = sg[i].x; sw[4 * i + 1] = sg[i].y; sw[4 * i + 2] = sg[i].z; sw[4 * i + 3] = sg[i].w; }
@@ -833,6 +839,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 const uint32_t off = rowoff + (uint32_t)((cc ^ (fl & 7)) << 4);
                 st_shared_v4(xa + off, hi);
                 st_shared_v4(xa + 8192 + off, lo);
+                if (ghi) { ghi[cc] = hi; glo[cc] = lo; }      // straight from the registers (consumed only by the weight gradients)
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         };
@@ -842,15 +849,24 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             for (int i = 0; i < 4; ++i) st_shared_v4(xa + (uint32_t)(t * 4 + i) * 16u, z);
         };
         // coupling backward of the owned row for the `step` about to run: g -> direct path in place, head gradients -> the nets' CTAs
+        // the saved layer input / head outputs the owner's coupling backward of `step` reads: issued a layer ahead, they are global
+        // loads whose latency would otherwise sit between the partial sums and the next layer's first GEMM
+        float pf_x = 0.f, pf_s = 0.f, pf_t = 0.f;
+        auto owner_prefetch = [&](int step, int layer) {
+            if (uk < nact_s[layer] && own_r < p.R) {
+                const int d = actd[layer][uk];
+                pf_x = __ldg(p.saved_x + ((size_t)step * p.R + own_r) * D + d);
+                pf_s = __ldg(p.saved_st + ((size_t)(step * 2 + 0) * p.R + own_r) * D + d);
+                pf_t = __ldg(p.saved_st + ((size_t)(step * 2 + 1) * p.R + own_r) * D + d);
+            }
+        };
         auto owner_coupling = [&](int step, int layer) {
             const bool on = uk < nact_s[layer];
             const int d = on ? actd[layer][uk] : 0;
             float ds = 0.f, dt = 0.f;
             if (on && own_r < p.R) {
                 const float g = gs[urow * kXs + d];
-                const float xv = __ldg(p.saved_x + ((size_t)step * p.R + own_r) * D + d);
-                const float s = __ldg(p.saved_st + ((size_t)(step * 2 + 0) * p.R + own_r) * D + d);
-                const float tt = __ldg(p.saved_st + ((size_t)(step * 2 + 1) * p.R + own_r) * D + d);
+                const float xv = pf_x, s = pf_s, tt = pf_t;
                 const float gl = gls[urow];
                 float dx;
                 if (p.direction == 0) { const float e = expf(s); dx = g * e; dt = g; ds = g * xv * e + gl; }
@@ -909,6 +925,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         // every CTA's dpre tile is zeroed before any owner writes into it: cluster-wide rendezvous of the worker warps via bar_part
         if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
         worker_wait(&bar_part, 0, true);
+        owner_prefetch(p.s_hi - 1, p.direction == 0 ? p.s_hi - 1 : p.L - p.s_hi);
         owner_coupling(p.s_hi - 1, p.direction == 0 ? p.s_hi - 1 : p.L - p.s_hi);
 
         float v[32];
@@ -919,6 +936,8 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             const uint64_t mb = mbits[layer];
             const size_t sbatch = (size_t)(step * 2 + net) * 2;    // plane index base of the saved activations (indexed by step)
             const size_t gbatch = (size_t)(layer * 2 + net) * 2;   // ... of the gradient planes (indexed by layer, like the parameters)
+            if (t == 0) BSTAMP(0);
+            if (step > p.s_lo) owner_prefetch(step - 1, p.direction == 0 ? step - 1 : p.L - step);
             // ---------------- the head gradients of all 64 rows have been written into xa by their owners
             {
                 uint4 sg[4];
@@ -927,23 +946,26 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 for (int i = 0; i < 4; ++i) sg[i] = __ldg(sp + i);
                 if (t == 0) {
                     mbar_wait_cluster(smem_u32(&bar_dpre), par);
+                    BSTAMP(1);
                     fence_proxy_async();                               // the tile was written through the generic proxy (by peers)
                     mbar_arrive(smem_u32(&bar_xm));
                 }
                 // ---------------- bE2: dh1 = acc0 * lrelu'(a1) -> xa slice + global dh1T (exchange, weight gradients)
                 worker_wait(&bar_acc[0], par, false);
                 tcgen05_fence_after();
+                if (t == 0) BSTAMP(2);
                 load_acc(kAcc0, v);
-                store_grad_slice(v, sg);
+                store_grad_slice(v, sg, nullptr, nullptr);
                 tcgen05_fence_before();
                 worker_sync();
-                if (t == 0) mbar_arrive(smem_u32(&bar_own));
+                if (t == 0) { BSTAMP(3); mbar_arrive(smem_u32(&bar_own)); }
                 copy_slice_to_global(xa, p.dh1T + gbatch * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
                 worker_sync();
                 if (t < 4) {
                     fence_proxy_async();
                     fence_cluster();
                     mbar_arrive_remote(smem_u32(&bar_a0), net * 4 + t);
+                    if (t == 0) BSTAMP(4);
                 }
             }
             // ---------------- bE1: dh0 = acc1 * lrelu'(a0) -> xa slice (B operand of bG0) + global dh0T (weight gradients)
@@ -954,17 +976,20 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 for (int i = 0; i < 4; ++i) sg[i] = __ldg(sp + i);
                 worker_wait(&bar_acc[1], par, false);
                 tcgen05_fence_after();
+                if (t == 0) BSTAMP(6);
                 load_acc(kAcc1, v);
-                store_grad_slice(v, sg);
+                store_grad_slice(v, sg, nullptr, nullptr);
                 tcgen05_fence_before();
                 mbar_arrive(smem_u32(&bar_a1));
                 worker_sync();      // kept for the weight gradients; off the critical path (bG0 only reads xa)
                 copy_slice_to_global(xa, p.dh0T + gbatch * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
+                if (t == 0) BSTAMP(7);
             }
             // ---------------- bE0: partial input gradients of this CTA's feature slice -> the CTAs that own the rows (DSMEM)
             {
                 worker_wait(&bar_acc[2], par, false);
                 tcgen05_fence_after();
+                if (t == 0) BSTAMP(8);
                 if (lq < 2) {   // accumulator rows = flow dims
                     load_acc(kAcc2, v);
                     if (fl < D && ((mb >> fl) & 1)) {   // only the dims the nets read (mask = 1) receive this gradient
@@ -984,10 +1009,12 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 zero_dpre_tile();                                      // bG0 is done with xa; the owners refill the tile for the next layer
                 worker_sync();
                 if (t < kCluster) { fence_cluster(); mbar_arrive_remote(smem_u32(&bar_part), t); }
+                if (t == 0) BSTAMP(9);
             }
             // ---------------- owner: g[row][d] += sum over the 8 CTAs of the partials (conditioning dims), then the next layer's coupling
             {
-                worker_wait(&bar_part, 1 - par, true);                 // completion it + 1 of bar_part (completion 0 was the start rendezvous)
+                worker_wait(&bar_part, 1 - par, true);
+                if (t == 0) BSTAMP(10);                                // completion it + 1 of bar_part (completion 0 was the start rendezvous)
                 if (uk < npas_s[layer]) {
                     const int d = pasd[layer][uk];
                     const float* rv = recv + ((size_t)((1 - (int)par) * kCluster) * kActMax + uk) * 8 + urow;
@@ -998,6 +1025,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 }
                 worker_sync();
                 if (step > p.s_lo) owner_coupling(step - 1, p.direction == 0 ? step - 1 : p.L - step);
+                if (t == 0) BSTAMP(11);
             }
         }
         for (int i = t; i < 8 * D; i += kWorkers) {   // every CTA writes the rows it owns
@@ -1259,7 +1287,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     BwdArgs a{};
     a.mask = mask; a.saved_x = S.x_; a.saved_st = S.st_; a.a0T = S.a0_; a.a1T = S.a1_;
     a.dout = dout; a.dlogdet = dlogdet; a.dlogdet_scale = dlogdet_scale; a.din = din; a.dparams = dparams;
-    a.dh1T = ws.dh1T; a.dh0T = ws.dh0T; a.dpreT = ws.dpreT; a.partial = ws.partial; a.dbg = nullptr;
+    a.dh1T = ws.dh1T; a.dh0T = ws.dh0T; a.dpreT = ws.dpreT; a.partial = ws.partial; a.dbg = getenv("MHE_FUSED_DEBUG_BWD") ? debug_buffer() : nullptr;
     a.R = R; a.Rp = Rp; a.D = L.D; a.H = L.H; a.L = L.L; a.direction = direction; a.tiles = tiles;
     { const char* e = getenv("MHE_FUSED_TWO_MMA"); a.two_mma = e ? (atoi(e) != 0) : 1; }
     a.blk = L.blk; a.ob2 = L.ob2;
@@ -1277,8 +1305,8 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
 
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(flow_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
-            set_error("fused flow bwd: cannot raise dynamic shared memory to %d", kSmemBytes);
+        if (cudaFuncSetAttribute(flow_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesBwd) != cudaSuccess) {
+            set_error("fused flow bwd: cannot raise dynamic shared memory to %d", kSmemBytesBwd);
             return MHE_ERR_CUDA;
         }
         attr_set = true;
@@ -1298,7 +1326,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         if (c > 0) ac.dout = din;                      // every CTA reads the rows it owns at the start and writes them at the end: in place
         ProbeScope probe("fused flow bwd", stream);
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(tiles * kCluster); cfg.blockDim = dim3(kThreadsF); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = stream;
+        cfg.gridDim = dim3(tiles * kCluster); cfg.blockDim = dim3(kThreadsF); cfg.dynamicSmemBytes = kSmemBytesBwd; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

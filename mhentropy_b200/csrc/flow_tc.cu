@@ -345,6 +345,7 @@ int pack_weights(const FlowLayout& L, const float* params, void* packed, int whi
 
 // ---- conditioning ---------------------------------------------------------------------------------------
 int cond_fwd(const FlowLayout& L, const float* params, const void* packed, const float* feat, int B, float* cp, void* ws_, cudaStream_t stream) {
+    if (cond_direct_supported(L, B)) return cond_fwd_direct(L, params, feat, B, cp, ws_, stream);
     Packed P(L, (bf16*)packed);
     bf16* featp = (bf16*)ws_;   // [2][B][C]
     MHE_TRY(split_planes(feat, L.C, 0, B, L.C, nullptr, featp, B, L.C, 2, 1, true, stream));

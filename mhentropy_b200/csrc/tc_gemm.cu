@@ -63,6 +63,36 @@ struct MapKeyHash {
     }
 };
 
+// fp32 [batches][rows][cols] (row_pitch / batch_stride in elements) as a 3-D map with SWIZZLE_128B boxes of 32 floats x box_rows: the
+// staging format of kernels that convert fp32 weights to split planes on the fly (cond_direct.cu)
+const CUtensorMap* cached_map_f32(const float* base, int cols, int rows, int batches, long row_pitch, long batch_stride, int box_rows, int* status) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap*, MapKeyHash> cache;
+    MapKey key{base, cols, rows, -4, batches, box_rows, row_pitch, 0, batch_stride};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *status = MHE_OK; return it->second; }
+    auto encode = get_encode();
+    if (!encode) { set_error("cuTensorMapEncodeTiled entry point not available"); *status = MHE_ERR_CUDA; return nullptr; }
+    if (((uintptr_t)base & 15) || (row_pitch % 4) || (batch_stride % 4)) { set_error("fp32 tensor map: base/strides must be 16-byte aligned"); *status = MHE_ERR_INVALID_ARG; return nullptr; }
+    CUtensorMap* map = new CUtensorMap;
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+    cuuint64_t gstr[2] = {(cuuint64_t)row_pitch * 4, (cuuint64_t)batch_stride * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (fp32) failed (%d) cols=%d rows=%d batches=%d", (int)r, cols, rows, batches);
+        delete map;
+        *status = MHE_ERR_CUDA;
+        return nullptr;
+    }
+    cache.emplace(key, map);
+    *status = MHE_OK;
+    return map;
+}
+
 int stages_for(const char* what, int requested, int max_stages) {
     static std::vector<std::pair<std::string, int>> overrides;
     static bool parsed = false;

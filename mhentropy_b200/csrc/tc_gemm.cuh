@@ -62,13 +62,19 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait may suspend the thread for an implementation-defined time before it re-checks; -DMHE_MBAR_TEST polls with test_wait
+#ifdef MHE_MBAR_TEST
+#define MHE_MBAR_POLL "mbarrier.test_wait"
+#else
+#define MHE_MBAR_POLL "mbarrier.try_wait"
+#endif
 // parity wait with a watchdog: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            MHE_MBAR_POLL ".parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (spin > (1u << 24)) __trap();
@@ -316,6 +322,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
     }
 }
+
+const CUtensorMap* cached_map_f32(const float* base, int cols, int rows, int batches, long row_pitch, long batch_stride, int box_rows, int* status);
 
 // ring depth of a launch: the caller's choice, overridden by MHE_TC_STAGES="label=n,label=n" (substring match on the launch label)
 int stages_for(const char* what, int requested, int max_stages);

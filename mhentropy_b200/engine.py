@@ -77,7 +77,8 @@ class TrainStep:
             # backward only) on another one while the forward runs.
             main = torch.cuda.current_stream(self.dev)
             self.side.wait_stream(main)
-            check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 4, s), 'pack_weights')
+            if L.mhe_flow_cond_fwd_uses_planes(shape, B):  # (at <= 128 images the conditioning GEMM streams the fp32 weights itself)
+                check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 4, s), 'pack_weights')
             self.side3.wait_stream(main)               # after the conditioning planes: those gate the first GEMM
             with torch.cuda.stream(self.side3):
                 check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 8, _lib.stream_ptr(self.dev)), 'pack_weights')
