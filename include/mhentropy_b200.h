@@ -81,7 +81,8 @@ size_t mhe_flow_cp_floats_per_image(mhe_flow_shape s);
  *                    (mhe_flow_packed_bytes() returns 0 otherwise).                                   */
 size_t mhe_flow_packed_bytes(mhe_flow_shape s);
 /* which (bit set): 1 = the half planes the forward GEMMs read, 2 = the bfloat16 planes the backward GEMMs read; 4 / 8 = only the
- * conditioning / only the coupling part of the half planes (so the conditioning GEMM can start while the rest is converted) */
+ * conditioning / only the coupling part of the half planes (so the conditioning GEMM can start while the rest is converted);
+ * 16 / 32 = only the coupling / only the conditioning part of the bfloat16 planes */
 int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, int which, void* stream);
 /* bytes of scratch needed by the flow passes over R rows (forward and backward) on the chosen path */
 size_t mhe_flow_workspace_bytes(mhe_flow_shape s, int R, int tensor_core);
@@ -120,6 +121,16 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
                       float* din, float* dparams, float* dcp,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Optional head start for mhe_flow_pass_bwd on the fused tensor-core path: everything its weight-gradient GEMMs need that depends only
+ * on the forward pass (re-planed saved activations, masked inputs, zeroed scratch).  May run on any stream once the forward pass that
+ * filled `saved` has completed - e.g. while the loss is computed; the caller orders it before mhe_flow_pass_bwd and sets
+ * mhe_flow_set_async bit 3.  Returns MHE_ERR_UNSUPPORTED (and does nothing) when the pass would not take the fused path.          */
+int mhe_flow_pass_bwd_prepare(mhe_flow_shape s, const float* mask, const float* saved, int R, int direction, void* workspace,
+                              size_t workspace_bytes, void* stream);
+/* Zero the slots of a gradient buffer that accumulate even with mhe_flow_set_async bit 1 (the biases); the weight slots are then
+ * stored by the backward entry points and need no zeroing.                                                                         */
+int mhe_flow_zero_bias_grads(mhe_flow_shape s, float* dparams, void* stream);
+
 /* Gradient-accumulation options (bit set; default 0).
  *   bit 0  asynchronous weight gradients: mhe_flow_pass_bwd may return while its weight-gradient GEMMs (the dparams W0/W1/W2
  *          slots) still run on internal streams, so that the caller can enqueue independent work (the conditioning backward only
@@ -127,6 +138,7 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
  *          captured graph ends.
  *   bit 1  the caller promises that the WEIGHT slots of dparams (W0, W1, W2, Cw) are zero when mhe_flow_pass_bwd /
  *          mhe_flow_cond_bwd run: their epilogues then store instead of read-modify-write (bias slots always accumulate).
+ *   bit 3  the caller has run mhe_flow_pass_bwd_prepare on the same saved block / workspace and ordered it before mhe_flow_pass_bwd.
  *   bit 2  the caller promises that dfeat is zero when mhe_flow_cond_bwd runs on the tensor-core path (it is accumulated into with
  *          atomics there): the memset that would otherwise sit on the critical path is skipped.                                 */
 int mhe_flow_set_async(int on);

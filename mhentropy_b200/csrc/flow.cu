@@ -289,10 +289,16 @@ size_t mhe_flow_packed_bytes(mhe_flow_shape s) {
 }
 
 int mhe_flow_pack_weights(mhe_flow_shape s, const float* params, void* packed, int which, void* stream) {
-    MHE_REQUIRE(valid_shape(s) && params && packed && which >= 1 && which <= 15, "pack_weights: bad args");
+    MHE_REQUIRE(valid_shape(s) && params && packed && which >= 1 && which <= 63, "pack_weights: bad args");
     FlowLayout L(s);
     if (!tcflow::supported(L)) { set_error("pack_weights: shape outside the tensor-core path (dim <= 64, hidden %% 64 == 0, cond %% 8 == 0)"); return MHE_ERR_UNSUPPORTED; }
     return tcflow::pack_weights(L, params, packed, which, (cudaStream_t)stream);
+}
+
+int mhe_flow_zero_bias_grads(mhe_flow_shape s, float* dparams, void* stream) {
+    MHE_REQUIRE(valid_shape(s) && dparams, "zero_bias_grads: bad args");
+    FlowLayout L(s);
+    return tcflow::zero_bias_grads(L, dparams, (cudaStream_t)stream);
 }
 
 int mhe_flow_cond_fwd_uses_planes(mhe_flow_shape s, int B) {
@@ -395,6 +401,17 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed,
     return MHE_OK;
 }
 
+int mhe_flow_pass_bwd_prepare(mhe_flow_shape s, const float* mask, const float* saved, int R, int direction, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    MHE_REQUIRE(valid_shape(s) && R >= 0 && direction >= 0 && direction <= 1, "pass_bwd_prepare: bad args");
+    if (R == 0) return MHE_OK;
+    MHE_REQUIRE(mask && saved && workspace, "pass_bwd_prepare: null pointer");
+    FlowLayout L(s);
+    if (!tcflow::supported(L) || !fused::supported(L, R)) return MHE_ERR_UNSUPPORTED;   // nothing to prepare on the other paths
+    if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 1)) { set_error("pass_bwd_prepare: workspace too small"); return MHE_ERR_WORKSPACE; }
+    return fused::pass_bwd_prepare(L, mask, saved, R, direction, workspace, (cudaStream_t)stream);
+}
+
 int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
                       const float* saved, int R, int B, int direction,
                       const float* dout, const float* dlogdet, float dlogdet_scale,
@@ -494,6 +511,7 @@ int mhe_flow_set_async(int on) {
     fused::set_async_wgrad(on & 1);
     tcflow::set_grads_are_zero((on >> 1) & 1);
     tcflow::set_dfeat_is_zero((on >> 2) & 1);
+    fused::set_wgrad_operands_prepared((on >> 3) & 1);
     return MHE_OK;
 }
 int mhe_flow_join(void* stream) { return fused::join((cudaStream_t)stream); }

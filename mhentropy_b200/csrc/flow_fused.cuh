@@ -91,6 +91,8 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
 // Asynchronous weight gradients: with set_async_wgrad(1) pass_bwd returns with its weight-gradient GEMMs still running on internal
 // streams; join(stream) makes `stream` wait for them (mhe_flow_set_async / mhe_flow_join in the C ABI).
 void set_async_wgrad(int on);
+void set_wgrad_operands_prepared(int on);
+int pass_bwd_prepare(const FlowLayout& L, const float* mask, const float* saved, int R, int direction, void* workspace, cudaStream_t stream);
 int join(cudaStream_t stream);
 
 int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,

@@ -282,6 +282,25 @@ static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const E
     return launch_tc_gemm<64, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
 }
 
+// zero the slots of a gradient buffer that ACCUMULATE on the tensor-core path (the biases): with mhe_flow_set_async bit 1 the weight
+// slots are stored, not accumulated, so they need no zeroing
+__global__ void zero_bias_grads_kernel(float* __restrict__ d, int nblk, size_t blk, size_t ob0, size_t ob1, size_t ob2, int H, int D,
+                                       size_t cb_base, size_t cb_stride, int ncb) {
+    const int b = blockIdx.x;
+    if (b < nblk) {
+        float* p = d + (size_t)b * blk;
+        for (int i = threadIdx.x; i < H; i += blockDim.x) { p[ob0 + i] = 0.f; p[ob1 + i] = 0.f; }
+        for (int i = threadIdx.x; i < D; i += blockDim.x) p[ob2 + i] = 0.f;
+    } else if (b - nblk < ncb) {
+        float* p = d + cb_base + (size_t)(b - nblk) * cb_stride;
+        for (int i = threadIdx.x; i < H; i += blockDim.x) p[i] = 0.f;
+    }
+}
+int zero_bias_grads(const FlowLayout& L, float* dparams, cudaStream_t stream) {
+    zero_bias_grads_kernel<<<L.L * 2 + L.L * 4, 256, 0, stream>>>(dparams, L.L * 2, L.blk, L.ob0, L.ob1, L.ob2, L.H, L.D, L.cb_base, L.cb_stride, L.L * 4);
+    return check_launch("zero bias grads");
+}
+
 static int g_grads_zero = 0, g_dfeat_zero = 0;
 void set_grads_are_zero(int on) { g_grads_zero = on; }
 bool grads_are_zero() { return g_grads_zero != 0; }
@@ -334,12 +353,14 @@ int pack_weights(const FlowLayout& L, const float* params, void* packed, int whi
         MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1, L.H, L.H, 2, L.L * 2, true, stream));
         MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2, kDp, L.H, 2, L.L * 2, true, stream));
     }
-    if (which & 2) {   // bfloat16 planes: backward GEMMs
+    // bfloat16 planes (backward GEMMs): bit 1 = all of them, bit 4 = only the coupling weights, bit 5 = only the conditioning weights
+    if (which & (2 | 16)) {
         MHE_TRY(split_planes(params + L.oW0, L.D, (long)L.blk, L.H, L.D, nullptr, P.w0b, L.H, kDp, 2, L.L * 2, false, stream));
         MHE_TRY(split_planes(params + L.oW1, L.H, (long)L.blk, L.H, L.H, nullptr, P.w1b, L.H, L.H, 2, L.L * 2, false, stream));
         MHE_TRY(split_planes(params + L.oW2, L.H, (long)L.blk, L.D, L.H, nullptr, P.w2b, kDp, L.H, 2, L.L * 2, false, stream));
-        MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cwb, L.H, L.C, 2, L.L * 4, false, stream));
     }
+    if (which & (2 | 32))
+        MHE_TRY(split_planes(params + L.cw_base, L.C, (long)L.cw_stride, L.H, L.C, nullptr, P.cwb, L.H, L.C, 2, L.L * 4, false, stream));
     return MHE_OK;
 }
 

@@ -89,6 +89,7 @@ inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
 // conditioning projections straight from the fp32 weights (cond_direct.cu): no conditioning planes needed for the forward
 bool cond_direct_supported(const FlowLayout& L, int B);
 int cond_fwd_direct(const FlowLayout& L, const float* params, const float* feat, int B, float* cp, void* ws, cudaStream_t stream);
+int zero_bias_grads(const FlowLayout& L, float* dparams, cudaStream_t stream);
 void set_grads_are_zero(int on);
 void set_dfeat_is_zero(int on);   // mhe_flow_set_async bit 2: dfeat is zero when cond_bwd runs (its memset is skipped)
 bool grads_are_zero();

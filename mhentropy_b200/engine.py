@@ -9,6 +9,8 @@ kernel launches on preallocated buffers, so it can be captured in a CUDA graph. 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -84,8 +86,10 @@ class TrainStep:
                 check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 8, _lib.stream_ptr(self.dev)), 'pack_weights')
             with torch.cuda.stream(self.side):
                 self.side.wait_stream(self.side3)      # the forward-critical conversions get the memory system first
+                # bfloat16 planes (read by the backward only)
                 check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 2, _lib.stream_ptr(self.dev)), 'pack_weights')
-                self.dflat.zero_()
+                # the weight slots of dflat are stored (not accumulated) by the backward: only the bias slots need zeroing
+                check(L.mhe_flow_zero_bias_grads(shape, ptr(self.dflat), _lib.stream_ptr(self.dev)), 'zero_bias_grads')
                 self.dcp.zero_()
                 self.dfeat.zero_()
         check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
@@ -94,6 +98,11 @@ class TrainStep:
         check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
                                   ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
         main = torch.cuda.current_stream(self.dev)
+        # (Re-planing the saved activations for the weight gradients right here (mhe_flow_pass_bwd_prepare) and converting the
+        # bfloat16 conditioning planes in this window were measured: they delay the per-row kernel and collide with the first
+        # backward chunk more than they relieve the forward kernel, so the former stays inside mhe_flow_pass_bwd and the latter at
+        # the start of the step.)
+        self.prepared = False
         # log q and the image-level reductions are outputs only (the loss is linear in the row terms, so the backward's seeds are
         # constants): they run on a side stream, off the chain flow forward -> z -> per-row kernel -> flow backward
         self.side4.wait_stream(main)
@@ -126,7 +135,7 @@ class TrainStep:
         # needs dcp) is enqueued; mhe_flow_join() brings them back before the step ends
         # (bit 1: dflat was zeroed at the start of the step, so the weight-gradient epilogues may store instead of accumulate;
         #  bit 2: so was dfeat)
-        check(L.mhe_flow_set_async(7 if self.tc else 3), 'set_async')
+        check(L.mhe_flow_set_async((7 if self.tc else 3) | (8 if self.prepared else 0)), 'set_async')
         try:
             check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
                                       ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
