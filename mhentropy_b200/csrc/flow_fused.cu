@@ -1220,7 +1220,7 @@ __global__ void head_start_kernel(unsigned ns) {
 }
 struct BwdAux {
     cudaStream_t stream[4] = {nullptr, nullptr, nullptr, nullptr};     // [0..2]: weight gradients (W1, W0 + dcp, W2), [3]: re-planes
-    cudaEvent_t start = nullptr, prep_fork = nullptr, prep_memset = nullptr, prep_done = nullptr, replaned[kMaxChunks] = {}, chunk_done[kMaxChunks] = {}, dcp_done[kMaxChunks] = {}, gate[kMaxChunks] = {},
+    cudaEvent_t start = nullptr, replaned[kMaxChunks] = {}, chunk_done[kMaxChunks] = {}, dcp_done[kMaxChunks] = {}, gate[kMaxChunks] = {},
                 wgrad_done[3] = {nullptr, nullptr, nullptr};
     bool has_pending = false;
     bool ok = false;
@@ -1235,7 +1235,7 @@ static BwdAux& bwd_aux() {
         for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 3; ++i) ev(&a.wgrad_done[i]);
         for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); ev(&a.gate[i]); }
-        ev(&a.start); ev(&a.prep_fork); ev(&a.prep_memset); ev(&a.prep_done);
+        ev(&a.start);
         a.ok = ok;
     }
     return a;
@@ -1273,30 +1273,22 @@ static int g_prepared = 0;
 void set_wgrad_operands_prepared(int on) { g_prepared = on; }
 
 // The operands of the weight gradients that only depend on the forward pass (bfloat16 planes of the saved activations by layer, the
-// masked layer inputs, the zeroed dpreT planes).  Forked from `stream` onto the library's re-plane stream, so `stream` itself is not
-// held up: callable right after the forward pass, it then runs while the loss is computed; pass_bwd (mhe_flow_set_async bit 3)
-// makes its data-gradient kernel wait for the memset only and its weight-gradient GEMMs for the rest.
+// masked layer inputs, the zeroed dpreT planes), enqueued on `stream`: callable any time after the forward pass, e.g. on a side stream
+// while the loss is computed.  The caller orders it before pass_bwd, which then skips them (mhe_flow_set_async bit 3).
 int pass_bwd_prepare(const FlowLayout& L, const float* mask, const float* saved, int R, int direction, void* workspace, cudaStream_t stream) {
-    BwdAux& ax = bwd_aux();
-    if (!ax.ok) return MHE_ERR_UNSUPPORTED;
     BWs ws(workspace, L, R);
     FSaved S(const_cast<float*>(saved), L, R);
     const int Rp = padded_rows(R);
     const long nact = (long)L.H * Rp;
-    cudaStream_t sr = ax.stream[3];
-    MHE_TRY(cuda_ok(cudaEventRecord(ax.prep_fork, stream), "fork prepare"));
-    MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax.prep_fork, 0), "fork prepare"));
-    MHE_TRY(cuda_ok(cudaMemsetAsync(ws.dpreT, 0, (size_t)L.L * 4 * kDp * Rp * 2, sr), "memset dpreT"));
-    MHE_TRY(cuda_ok(cudaEventRecord(ax.prep_memset, sr), "prepare"));
+    MHE_TRY(cuda_ok(cudaMemsetAsync(ws.dpreT, 0, (size_t)L.L * 4 * kDp * Rp * 2, stream), "memset dpreT"));
     dim3 grid(cdiv((int)(nact / 8), 256), L.L * 2);
-    replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a0_, ws.a0b, nact, L.L, direction, 0);
+    replane_by_layer_kernel<<<grid, 256, 0, stream>>>(S.a0_, ws.a0b, nact, L.L, direction, 0);
     MHE_TRY(check_launch("replane a0"));
-    replane_by_layer_kernel<<<grid, 256, 0, sr>>>(S.a1_, ws.a1b, nact, L.L, direction, 0);
+    replane_by_layer_kernel<<<grid, 256, 0, stream>>>(S.a1_, ws.a1b, nact, L.L, direction, 0);
     MHE_TRY(check_launch("replane a1"));
     dim3 gx(cdiv(Rp, 128), kDp, L.L);
-    xm_transposed_kernel<<<gx, 128, 0, sr>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT, 0);
-    MHE_TRY(check_launch("xm transposed"));
-    return cuda_ok(cudaEventRecord(ax.prep_done, sr), "prepare");
+    xm_transposed_kernel<<<gx, 128, 0, stream>>>(S.x_, mask, R, Rp, L.D, L.L, direction, ws.xmT, 0);
+    return check_launch("xm transposed");
 }
 
 static unsigned head_start_ns() {
@@ -1331,9 +1323,8 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     const CUtensorMap* mDh1 = cached_map(pt4(ws.dh1T, Rp, L.H, L.L * 2), 64, &st);
     if (st != MHE_OK) return st;
     // only the active dims of dpreT are written by the kernel
-    const bool prepared = g_prepared != 0 && bwd_aux().ok;   // pass_bwd_prepare was called for this saved block / workspace
+    const bool prepared = g_prepared != 0;            // pass_bwd_prepare already ran on this saved block / workspace (caller-ordered)
     if (!prepared) MHE_TRY(cuda_ok(cudaMemsetAsync(ws.dpreT, 0, (size_t)L.L * 4 * kDp * Rp * 2, stream), "memset dpreT"));
-    else MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, bwd_aux().prep_memset, 0), "join prepare"));
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -1434,8 +1425,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     if (par) MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax.start, 0), "fork replane"));
     for (int c = 0; c < nchunk; ++c) {
         if (!prepared) MHE_TRY(launch_replane(c));
-        else if (c == 0) MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax.prep_done, 0), "join prepare"));   // (sr: the prepare ran there)
-        if (prepared && par) MHE_TRY(cuda_ok(cudaEventRecord(ax.replaned[c], sr), "replaned"));
+        else if (par) MHE_TRY(cuda_ok(cudaEventRecord(ax.replaned[c], sr), "replaned"));
     }
     for (int c = 0; c < nchunk; ++c) {
         if (c > 0) MHE_TRY(launch_chunk(c));

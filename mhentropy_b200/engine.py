@@ -19,7 +19,8 @@ from .losses import MHEntHead
 
 
 class TrainStep:
-    def __init__(self, head: MHEntHead, B: int, S: int, device, want_verts: bool = True, use_graph: bool = True):
+    def __init__(self, head: MHEntHead, B: int, S: int, device, want_verts: bool = True, use_graph: bool = True,
+                 prepare_ahead: bool = False):
         self.head, self.B, self.S, self.R = head, B, S, B * S
         self.dev = torch.device(device)
         flow = head.q_z_giv_i
@@ -59,11 +60,15 @@ class TrainStep:
         self.side2 = torch.cuda.Stream(self.dev)
         self.side3 = torch.cuda.Stream(self.dev)
         self.side4 = torch.cuda.Stream(self.dev)
+        self.side5 = torch.cuda.Stream(self.dev)
         self.jtr_mesh = f(R, 21, 3)
         self.mws_bytes = L.mhe_mano_workspace_bytes(R, 0)
         self.mws = torch.empty(self.mws_bytes, dtype=torch.uint8, device=dev)
         self.graph = None
         self.use_graph = use_graph
+        # re-plane the weight-gradient operands right after the forward pass (see _enqueue); eager launches only for now: the
+        # extra fork invalidates the stream capture (cause not found yet), and it measured slower anyway
+        self.prepare_ahead = prepare_ahead and not use_graph
         self.launches_per_step = None
 
     # ------------------------------------------------------------------
@@ -100,9 +105,14 @@ class TrainStep:
         main = torch.cuda.current_stream(self.dev)
         # (Re-planing the saved activations for the weight gradients right here (mhe_flow_pass_bwd_prepare) and converting the
         # bfloat16 conditioning planes in this window were measured: they delay the per-row kernel and collide with the first
-        # backward chunk more than they relieve the forward kernel, so the former stays inside mhe_flow_pass_bwd and the latter at
-        # the start of the step.)
+        # backward chunk more than they relieve the forward kernel, so by default the former stays inside mhe_flow_pass_bwd
+        # (prepare_ahead = False) and the latter at the start of the step.)
         self.prepared = False
+        if self.tc and self.prepare_ahead:
+            self.side5.wait_stream(main)
+            with torch.cuda.stream(self.side5):
+                self.prepared = L.mhe_flow_pass_bwd_prepare(shape, ptr(self.mask), ptr(self.saved), R, 0, ws, wsb,
+                                                            _lib.stream_ptr(self.dev)) == 0
         # log q and the image-level reductions are outputs only (the loss is linear in the row terms, so the backward's seeds are
         # constants): they run on a side stream, off the chain flow forward -> z -> per-row kernel -> flow backward
         self.side4.wait_stream(main)
@@ -135,6 +145,8 @@ class TrainStep:
         # needs dcp) is enqueued; mhe_flow_join() brings them back before the step ends
         # (bit 1: dflat was zeroed at the start of the step, so the weight-gradient epilogues may store instead of accumulate;
         #  bit 2: so was dfeat)
+        if self.tc and self.prepare_ahead:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side5)
         check(L.mhe_flow_set_async((7 if self.tc else 3) | (8 if self.prepared else 0)), 'set_async')
         try:
             check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),

@@ -98,3 +98,24 @@ def test_hypothesis_rows_kernel_matches_separate_kernels(R, B):
     assert torch.equal(jtr1, jtr0) and torch.equal(uv1, uv0) and torch.equal(lp1, lp0) and torch.equal(dlq1, dlq0)
     assert rel(dz1, dz0) < 1e-6
     assert torch.equal(logp1, logp) and torch.equal(loss1, loss)
+
+
+def test_engine_prepare_ahead_matches_default():
+    """mhe_flow_pass_bwd_prepare + mhe_flow_set_async bit 3 (weight-gradient operands re-planed right after the forward pass) gives the
+    same gradients as the default schedule."""
+    head = MHEntHead(mano_data=synthetic_mano(0))
+    head.q_z_giv_i.load_state_dict(fo.init_state_dict(seed=0))
+    head.q_z_giv_i.precision = 'bf16x3'
+    head = head.to(DEV)
+    devb = {k: v.to(DEV) for k, v in synthetic_batch(64, 10, seed=5).items()}
+    outs = []
+    for ahead in (False, True):
+        eng = TrainStep(head, 64, 10, DEV, want_verts=False, use_graph=False, prepare_ahead=ahead)   # (eager: see engine.py)
+        eng.load(**devb)
+        for _ in range(2):
+            eng.run()
+        torch.cuda.synchronize()
+        outs.append((eng.loss.clone(), eng.dflat.clone(), eng.dfeat.clone(), eng.dz0.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert rel(a, b) < 1e-5
