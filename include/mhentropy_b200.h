@@ -121,6 +121,16 @@ int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed,
                       float* din, float* dparams, float* dcp,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* mhe_flow_pass_bwd followed by mhe_flow_cond_bwd as ONE call (same results).  On the fused tensor-core path the conditioning backward
+ * is pipelined into the pass: the layers' dcp sums, conditioning weight / bias gradients and their share of dfeat are enqueued chunk by
+ * chunk behind the data-gradient kernel of the chunk, on internal streams, so most of it overlaps the remaining layers instead of
+ * following the last one.  With mhe_flow_set_async bit 0 it returns with that work pending (mhe_flow_join).  dfeat may be NULL.        */
+int mhe_flow_pass_cond_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
+                           const float* saved, int R, int B, int direction,
+                           const float* dout, const float* dlogdet, float dlogdet_scale,
+                           float* din, float* dparams, float* dcp, const float* feat, float* dfeat,
+                           void* workspace, size_t workspace_bytes, void* cond_workspace, size_t cond_workspace_bytes, void* stream);
+
 /* Optional head start for mhe_flow_pass_bwd on the fused tensor-core path: everything its weight-gradient GEMMs need that depends only
  * on the forward pass (re-planed saved activations, masked inputs, zeroed scratch), enqueued on `stream`.  May run on any stream once
  * the forward pass that filled `saved` has completed - e.g. while the loss is computed; the caller orders it before

@@ -401,6 +401,27 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed,
     return MHE_OK;
 }
 
+int mhe_flow_pass_cond_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
+                           const float* saved, int R, int B, int direction, const float* dout, const float* dlogdet, float dlogdet_scale,
+                           float* din, float* dparams, float* dcp, const float* feat, float* dfeat,
+                           void* workspace, size_t workspace_bytes, void* cond_workspace, size_t cond_workspace_bytes, void* stream_) {
+    MHE_REQUIRE(valid_shape(s) && feat, "pass_cond_bwd: bad shape or null feat");
+    FlowLayout L(s);
+    if (R > 0 && packed && tcflow::supported(L) && fused::supported(L, R)) {
+        MHE_REQUIRE(B > 0 && direction >= 0 && direction <= 1, "pass_cond_bwd: bad B/direction");
+        MHE_REQUIRE(params && mask && cp && saved && dout && din && dparams && dcp && workspace && cond_workspace, "pass_cond_bwd: null pointer");
+        if (workspace_bytes < mhe_flow_workspace_bytes(s, R, 1)) { set_error("pass_cond_bwd: workspace too small"); return MHE_ERR_WORKSPACE; }
+        if (cond_workspace_bytes < tcflow::cond_ws_bytes(L, B)) { set_error("pass_cond_bwd: conditioning workspace too small"); return MHE_ERR_WORKSPACE; }
+        fused::CondBwd c{feat, dfeat, cond_workspace};
+        return fused::pass_bwd(L, params, packed, mask, saved, R, B, direction, dout, dlogdet, dlogdet_scale, din, dparams, dcp, workspace,
+                               (cudaStream_t)stream_, &c);
+    }
+    // other paths: the two entry points one after the other
+    MHE_TRY(mhe_flow_pass_bwd(s, params, packed, mask, cp, saved, R, B, direction, dout, dlogdet, dlogdet_scale, din, dparams, dcp, workspace,
+                              workspace_bytes, stream_));
+    return mhe_flow_cond_bwd(s, params, packed, feat, dcp, B, dparams, dfeat, cond_workspace, cond_workspace_bytes, stream_);
+}
+
 int mhe_flow_pass_bwd_prepare(mhe_flow_shape s, const float* mask, const float* saved, int R, int direction, void* workspace,
                               size_t workspace_bytes, void* stream) {
     MHE_REQUIRE(valid_shape(s) && R >= 0 && direction >= 0 && direction <= 1, "pass_bwd_prepare: bad args");

@@ -1219,10 +1219,11 @@ __global__ void head_start_kernel(unsigned ns) {
     while (gtime() - t0 < (long long)ns) __nanosleep(256);
 }
 struct BwdAux {
-    cudaStream_t stream[4] = {nullptr, nullptr, nullptr, nullptr};     // [0..2]: weight gradients (W1, W0 + dcp, W2), [3]: re-planes
+    cudaStream_t stream[7] = {};     // [0..2]: weight gradients (W1, W0 + dcp, W2), [3]: re-planes, [4..6]: conditioning backward
     cudaEvent_t start = nullptr, replaned[kMaxChunks] = {}, chunk_done[kMaxChunks] = {}, dcp_done[kMaxChunks] = {}, gate[kMaxChunks] = {},
-                wgrad_done[3] = {nullptr, nullptr, nullptr};
+                wgrad_done[6] = {}, dcpp_ready[kMaxChunks] = {};
     bool has_pending = false;
+    int pending_n = 3;               // how many of wgrad_done[] the pending pass recorded (6 with the conditioning backward)
     bool ok = false;
 };
 static BwdAux& bwd_aux() {
@@ -1232,9 +1233,9 @@ static BwdAux& bwd_aux() {
         tried = true;
         bool ok = true;
         auto ev = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-        for (int i = 0; i < 4 && ok; ++i) ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < 3; ++i) ev(&a.wgrad_done[i]);
-        for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); ev(&a.gate[i]); }
+        for (int i = 0; i < 7 && ok; ++i) ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 6; ++i) ev(&a.wgrad_done[i]);
+        for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); ev(&a.gate[i]); ev(&a.dcpp_ready[i]); }
         ev(&a.start);
         a.ok = ok;
     }
@@ -1245,7 +1246,7 @@ void set_async_wgrad(int on) { g_async_wgrad = on; }
 static bool async_wgrad() { return g_async_wgrad != 0; }
 static int join_pending_on(cudaStream_t stream) {
     BwdAux& ax = bwd_aux();
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < ax.pending_n; ++i)
         if (cudaStreamWaitEvent(stream, ax.wgrad_done[i], 0) != cudaSuccess) { set_error("join weight gradients: %s", cudaGetErrorString(cudaGetLastError())); return MHE_ERR_CUDA; }
     ax.has_pending = false;
     return MHE_OK;
@@ -1299,7 +1300,7 @@ static unsigned head_start_ns() {
 
 int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* saved, int R, int B, int direction,
              const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp, void* workspace,
-             cudaStream_t stream) {
+             cudaStream_t stream, const CondBwd* cond) {
     (void)params;
     tcflow::Packed P(L, (bf16*)packed);
     BWs ws(workspace, L, R);
@@ -1401,6 +1402,15 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
             MHE_TRY(check_launch("dcp from planes"));
             if (par) MHE_TRY(cuda_ok(cudaEventRecord(ax.dcp_done[c], s1), "dcp done"));
         }
+        if (cond && par) {   // conditioning backward of the chunk's layers: only needs their dcp
+            const int nl = chunk_hi(c) - chunk_lo(c);
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[4], ax.dcp_done[c], 0), "fork cond"));
+            MHE_TRY(tcflow::cond_bwd_dcp_planes(L, dcp, B, cond->ws, l0, nl, ax.stream[4]));
+            MHE_TRY(cuda_ok(cudaEventRecord(ax.dcpp_ready[c], ax.stream[4]), "fork cond"));
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[5], ax.dcpp_ready[c], 0), "fork cond"));
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[6], ax.dcp_done[c], 0), "fork cond"));
+            MHE_TRY(tcflow::cond_bwd_layers(L, packed, dcp, B, dparams, cond->dfeat, cond->ws, l0, nl, ax.stream[6], ax.stream[4], ax.stream[5]));
+        }
         {   // dW1 [out][in] += dh1T . a0T^T  (contraction over the rows)
             GemmShape g{L.H, L.H, Rp, nb, 1, 1, 1};
             MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.dh1T + ao, Rp, L.H, nb), ptk(ws.a0b + ao, Rp, L.H, nb), g, dparams + po + L.oW1, L.H, (long)L.blk, L.H, 0, s0,
@@ -1420,7 +1430,16 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     };
 
     if (par) MHE_TRY(cuda_ok(cudaEventRecord(ax.start, stream), "fork replane"));
+    if (cond && !par) { set_error("fused pass + conditioning backward: internal streams unavailable"); return MHE_ERR_CUDA; }
     MHE_TRY(launch_chunk(0));
+    if (cond) {
+        MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[4], ax.start, 0), "fork cond"));
+        MHE_TRY(tcflow::cond_bwd_feat_planes(L, cond->feat, B, cond->ws, ax.stream[4]));
+        if (cond->dfeat && !tcflow::dfeat_is_zero()) {
+            MHE_TRY(cuda_ok(cudaStreamWaitEvent(ax.stream[5], ax.start, 0), "fork cond"));
+            MHE_TRY(cuda_ok(cudaMemsetAsync(cond->dfeat, 0, (size_t)B * L.C * sizeof(float), ax.stream[5]), "memset dfeat"));
+        }
+    }
     // (launched after the first kernel so that its clusters' CTAs get their SMs first; the re-planes fill the remaining ones)
     if (par) MHE_TRY(cuda_ok(cudaStreamWaitEvent(sr, ax.start, 0), "fork replane"));
     for (int c = 0; c < nchunk; ++c) {
@@ -1434,6 +1453,8 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     if (par) {
         for (int c = 0; c < nchunk; ++c) MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, ax.dcp_done[c], 0), "join dcp"));
         for (int i = 0; i < 3; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.wgrad_done[i], ax.stream[i]), "join"));
+        if (cond) for (int i = 3; i < 6; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.wgrad_done[i], ax.stream[i + 1]), "join"));
+        ax.pending_n = cond ? 6 : 3;
         // the re-plane stream is joined through the weight-gradient streams (they waited for replaned[c])
         if (async_wgrad()) ax.has_pending = true;    // the caller joins with mhe_flow_join() before reading dparams
         else MHE_TRY(join_pending_on(stream));

@@ -84,9 +84,12 @@ struct BWs {
     }
 };
 
+// optional: the conditioning backward (mhe_flow_cond_bwd) pipelined into the pass, chunk by chunk (feat [B][C], dfeat [B][C] or NULL,
+// ws: the conditioning workspace)
+struct CondBwd { const float* feat; float* dfeat; void* ws; };
 int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* saved, int R, int B, int direction,
              const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp, void* workspace,
-             cudaStream_t stream);
+             cudaStream_t stream, const CondBwd* cond = nullptr);
 
 // Asynchronous weight gradients: with set_async_wgrad(1) pass_bwd returns with its weight-gradient GEMMs still running on internal
 // streams; join(stream) makes `stream` wait for them (mhe_flow_set_async / mhe_flow_join in the C ABI).

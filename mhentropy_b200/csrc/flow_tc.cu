@@ -251,9 +251,9 @@ __global__ void replane_kernel(const bf16* __restrict__ src, bf16* __restrict__ 
 
 // grid (cp_ld / 256, 8): block row y sums images y, y + 8, ... and adds its share (the slots accumulate anyway)
 __global__ void cond_bias_grad_kernel(const float* __restrict__ dcp, int B, long cp_ld, int H, float* __restrict__ dparams,
-                                      size_t cb_base, size_t cb_stride, size_t blk, size_t ob0, size_t ob1) {
-    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= cp_ld) return;
+                                      size_t cb_base, size_t cb_stride, size_t blk, size_t ob0, size_t ob1, long n_begin, long n_end) {
+    const long n = n_begin + (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_end) return;
     float acc = 0.f;
     for (int b = blockIdx.y; b < B; b += gridDim.y) acc += dcp[(long)b * cp_ld + n];
     const int idx = (int)(n / H), h = (int)(n % H);
@@ -397,7 +397,7 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         // many-wave GEMM only starts when that GEMM's last wave has been placed)
         cudaStream_t bstream = fork ? aux.stream[1] : stream;
         if (fork) MHE_TRY(cuda_ok(cudaStreamWaitEvent(bstream, aux.ready[0], 0), "fork cond bias grad"));
-        cond_bias_grad_kernel<<<dim3(cdiv((int)cp_ld, 256), 8), 256, 0, bstream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
+        cond_bias_grad_kernel<<<dim3(cdiv((int)cp_ld, 256), 8), 256, 0, bstream>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1, 0, cp_ld);
         MHE_TRY(check_launch("cond bias grad"));
         if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[1][0], bstream), "join cond bias grad"));
     }
@@ -427,6 +427,47 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
     }
     return MHE_OK;
 }
+
+// ---- conditioning backward by layer range (the chunked fused pass pipelines it behind each chunk's dcp sums) ----------------
+// feat planes (bfloat16: partner of the dcp planes), once per pass
+int cond_bwd_feat_planes(const FlowLayout& L, const float* feat, int B, void* ws_, cudaStream_t stream) {
+    return split_planes(feat, L.C, 0, B, L.C, nullptr, (bf16*)ws_, B, L.C, 2, 1, false, stream);
+}
+// dcp planes of layers [l0, l0 + nl): dense [2][B][nl*4*H] at their own offset of the workspace
+int cond_bwd_dcp_planes(const FlowLayout& L, const float* dcp, int B, void* ws_, int l0, int nl, cudaStream_t stream) {
+    const long cp_ld = (long)L.L * 4 * L.H;
+    bf16* dcpp = (bf16*)ws_ + (((size_t)2 * B * L.C + 511) / 512) * 512 + (size_t)2 * B * l0 * 4 * L.H;
+    return split_planes(dcp + (size_t)l0 * 4 * L.H, cp_ld, 0, B, nl * 4 * L.H, nullptr, dcpp, B, nl * 4 * L.H, 2, 1, false, stream);
+}
+// the three independent pieces for layers [l0, l0 + nl), each on the stream given (no fork / join here)
+int cond_bwd_layers(const FlowLayout& L, const void* packed, const float* dcp, int B, float* dparams, float* dfeat, void* ws_, int l0, int nl,
+                    cudaStream_t s_bias, cudaStream_t s_wgrad, cudaStream_t s_dfeat) {
+    Packed P(L, (bf16*)packed);
+    const long cp_ld = (long)L.L * 4 * L.H, ld_c = (long)nl * 4 * L.H;
+    bf16* featp = (bf16*)ws_;
+    bf16* dcpp = featp + (((size_t)2 * B * L.C + 511) / 512) * 512 + (size_t)2 * B * l0 * 4 * L.H;
+    const int nb = nl * 4;
+    cond_bias_grad_kernel<<<dim3(cdiv((int)ld_c, 256), 8), 256, 0, s_bias>>>(dcp, B, cp_ld, L.H, dparams, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1,
+                                                                              (long)l0 * 4 * L.H, (long)(l0 + nl) * 4 * L.H);
+    MHE_TRY(check_launch("cond bias grad"));
+    {   // dCw[idx] [H][C] (+)= dcp[:, idx, :]^T feat
+        PlaneTensor A = pt(dcpp, L.H, B, ld_c, (long)B * ld_c, nb, L.H);
+        PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
+        GemmShape g{L.H, L.C, B, nb, 1, 1, 0};
+        EpiWgrad e{dparams + L.cw_base + (size_t)l0 * 4 * L.cw_stride, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
+        MHE_TRY((gemm<true, true, false>(A, Bt, g, e, s_wgrad, "tc cond wgrad")));
+    }
+    if (dfeat) {   // dfeat [B][C] += sum_idx dcp[:, idx, :] Cw[idx]   (dfeat zeroed by the caller of the pass)
+        PlaneTensor A = pt(dcpp, L.H, B, ld_c, (long)B * ld_c, nb, L.H);
+        PlaneTensor Bt = pt(P.cwb + (size_t)l0 * 4 * 2 * L.H * L.C, L.C, L.H, L.C, (long)L.H * L.C, nb, (long)2 * L.H * L.C);
+        GemmShape g{B, L.C, L.H, nb, 1, 1, 1};
+        g.kfold = nb % 4 == 0 ? 4 : (nb % 2 == 0 ? 2 : 1);
+        EpiAtomicRows e{dfeat, L.C, L.C};
+        MHE_TRY((gemm<false, true, false>(A, Bt, g, e, s_dfeat, "tc cond dfeat")));
+    }
+    return MHE_OK;
+}
+bool dfeat_is_zero() { return g_dfeat_zero != 0; }
 
 // ---- coupling layers ------------------------------------------------------------------------------------
 struct LayerBufs {   // where one layer's activations live (workspace, or the saved-for-backward block)

@@ -119,3 +119,24 @@ def test_engine_prepare_ahead_matches_default():
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert rel(a, b) < 1e-5
+
+
+def test_engine_pipelined_cond_bwd_matches_default():
+    """mhe_flow_pass_cond_bwd (one call, conditioning backward pipelined into the chunked pass) == mhe_flow_pass_bwd + mhe_flow_cond_bwd."""
+    head = MHEntHead(mano_data=synthetic_mano(0))
+    head.q_z_giv_i.load_state_dict(fo.init_state_dict(seed=0))
+    head.q_z_giv_i.precision = 'bf16x3'
+    head = head.to(DEV)
+    for B, S in ((64, 10), (5, 3)):
+        devb = {k: v.to(DEV) for k, v in synthetic_batch(B, S, seed=6).items()}
+        outs = []
+        for piped in (False, True):
+            eng = TrainStep(head, B, S, DEV, want_verts=False, use_graph=True, pipelined_cond_bwd=piped)
+            eng.load(**devb)
+            for _ in range(2):
+                eng.run()
+            torch.cuda.synchronize()
+            outs.append((eng.loss.clone(), eng.dflat.clone(), eng.dfeat.clone(), eng.dz0.clone()))
+        assert torch.equal(outs[0][0], outs[1][0])
+        for a, b in zip(outs[0][1:], outs[1][1:]):
+            assert rel(a, b) < 1e-5
