@@ -199,13 +199,19 @@ def run_ours(args):
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    # multi-GPU: ONE NCCL all-reduce of the flat gradient (+ the loss) after the step.  MHE_BENCH_ALLREDUCE_INSIDE=1 runs it inside the
+    # engine's captured step instead, bucketed by backward chunk (mhe_flow_join_chunk) and overlapped with the remaining chunk: measured
+    # slower on 2 GPUs (0.774 vs 0.743 ms/step) - inside the graph NCCL runs the 15-25 MB buckets with its LL protocol and its CTAs
+    # compete with the cluster kernel for SMs - so it is not the default.
+    ar_inside = world > 1 and bool(os.environ.get('MHE_BENCH_ALLREDUCE_INSIDE'))
+
     def allreduce(engine):
-        if world > 1:
+        if world > 1 and not engine.allreduce:
             dist.all_reduce(engine.dflat)
             dist.all_reduce(engine.loss)
 
     # ---------------- value: inputs resident in HBM, fused engine (CUDA graph) ----------------
-    eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=not args.no_graph)
+    eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=not args.no_graph, allreduce=ar_inside)
     eng.load(**devb)
     for _ in range(max(args.warmup, 3)):
         flush.zero_()

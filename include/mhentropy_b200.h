@@ -131,6 +131,15 @@ int mhe_flow_pass_cond_bwd(mhe_flow_shape s, const float* params, const void* pa
                            float* din, float* dparams, float* dcp, const float* feat, float* dfeat,
                            void* workspace, size_t workspace_bytes, void* cond_workspace, size_t cond_workspace_bytes, void* stream);
 
+/* Bucketed gradient exchange.  On the fused tensor-core path the backward pass runs as mhe_flow_bwd_chunk_count() chunks of consecutive
+ * layers (1 on the other paths), chunk 0 first (it holds the layers the backward reaches first); mhe_flow_bwd_chunk_layers() gives
+ * chunk c's layers.  After an asynchronous mhe_flow_pass_cond_bwd (mhe_flow_set_async bit 0), mhe_flow_join_chunk(stream, c) makes
+ * `stream` wait until EVERY gradient of those layers (coupling and conditioning weights and biases) is complete, so that the caller can
+ * all-reduce that part of dparams while the remaining chunks still run.  mhe_flow_join() still ends the pass.                         */
+int mhe_flow_bwd_chunk_count(mhe_flow_shape s, int R);
+int mhe_flow_bwd_chunk_layers(mhe_flow_shape s, int R, int direction, int chunk, int* first_layer, int* layers);
+int mhe_flow_join_chunk(void* stream, int chunk);
+
 /* Optional head start for mhe_flow_pass_bwd on the fused tensor-core path: everything its weight-gradient GEMMs need that depends only
  * on the forward pass (re-planed saved activations, masked inputs, zeroed scratch), enqueued on `stream`.  May run on any stream once
  * the forward pass that filled `saved` has completed - e.g. while the loss is computed; the caller orders it before

@@ -422,6 +422,20 @@ int mhe_flow_pass_cond_bwd(mhe_flow_shape s, const float* params, const void* pa
     return mhe_flow_cond_bwd(s, params, packed, feat, dcp, B, dparams, dfeat, cond_workspace, cond_workspace_bytes, stream_);
 }
 
+int mhe_flow_bwd_chunk_count(mhe_flow_shape s, int R) {
+    if (!valid_shape(s)) return 1;
+    FlowLayout L(s);
+    return tcflow::supported(L) && fused::supported(L, R) ? fused::chunk_count(L.L) : 1;
+}
+int mhe_flow_bwd_chunk_layers(mhe_flow_shape s, int R, int direction, int chunk, int* first_layer, int* layers) {
+    MHE_REQUIRE(valid_shape(s) && first_layer && layers && chunk >= 0 && chunk < mhe_flow_bwd_chunk_count(s, R), "bwd_chunk_layers: bad args");
+    FlowLayout L(s);
+    if (mhe_flow_bwd_chunk_count(s, R) == 1) { *first_layer = 0; *layers = L.L; return MHE_OK; }
+    fused::chunk_layers(L.L, direction, chunk, first_layer, layers);
+    return MHE_OK;
+}
+int mhe_flow_join_chunk(void* stream, int chunk) { return fused::join_chunk((cudaStream_t)stream, chunk); }
+
 int mhe_flow_pass_bwd_prepare(mhe_flow_shape s, const float* mask, const float* saved, int R, int direction, void* workspace,
                               size_t workspace_bytes, void* stream) {
     MHE_REQUIRE(valid_shape(s) && R >= 0 && direction >= 0 && direction <= 1, "pass_bwd_prepare: bad args");

@@ -1221,9 +1221,10 @@ __global__ void head_start_kernel(unsigned ns) {
 struct BwdAux {
     cudaStream_t stream[7] = {};     // [0..2]: weight gradients (W1, W0 + dcp, W2), [3]: re-planes, [4..6]: conditioning backward
     cudaEvent_t start = nullptr, replaned[kMaxChunks] = {}, chunk_done[kMaxChunks] = {}, dcp_done[kMaxChunks] = {}, gate[kMaxChunks] = {},
-                wgrad_done[6] = {}, dcpp_ready[kMaxChunks] = {};
+                wgrad_done[6] = {}, dcpp_ready[kMaxChunks] = {}, chunk_grads[kMaxChunks][6] = {};
     bool has_pending = false;
     int pending_n = 3;               // how many of wgrad_done[] the pending pass recorded (6 with the conditioning backward)
+    int last_chunks = 0, last_L = 0, last_direction = 0;   // geometry of the last pass (join_chunk / chunk_layers)
     bool ok = false;
 };
 static BwdAux& bwd_aux() {
@@ -1235,7 +1236,7 @@ static BwdAux& bwd_aux() {
         auto ev = [&](cudaEvent_t* e) { ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
         for (int i = 0; i < 7 && ok; ++i) ok = cudaStreamCreateWithFlags(&a.stream[i], cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 6; ++i) ev(&a.wgrad_done[i]);
-        for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); ev(&a.gate[i]); ev(&a.dcpp_ready[i]); }
+        for (int i = 0; i < kMaxChunks; ++i) { ev(&a.replaned[i]); ev(&a.chunk_done[i]); ev(&a.dcp_done[i]); ev(&a.gate[i]); ev(&a.dcpp_ready[i]); for (int k = 0; k < 6; ++k) ev(&a.chunk_grads[i][k]); }
         ev(&a.start);
         a.ok = ok;
     }
@@ -1268,6 +1269,22 @@ static int bwd_chunks(int L) {
         if (n > kMaxChunks) n = kMaxChunks;
     }
     return n < L ? n : L;
+}
+
+int chunk_count(int L) { return bwd_chunks(L); }
+// layers [l0, l0 + nl) of chunk c (the pass walks the steps downwards: chunk 0 holds the LAST steps)
+void chunk_layers(int L, int direction, int c, int* l0, int* nl) {
+    const int n = bwd_chunks(L);
+    const int lo = L - (L * (c + 1)) / n, hi = L - (L * c) / n;
+    *l0 = direction == 0 ? lo : L - hi;
+    *nl = hi - lo;
+}
+int join_chunk(cudaStream_t stream, int c) {
+    BwdAux& ax = bwd_aux();
+    if (!ax.ok || c < 0 || c >= ax.last_chunks) { set_error("join_chunk: no such chunk in the last pass"); return MHE_ERR_INVALID_ARG; }
+    for (int i = 0; i < ax.pending_n; ++i)
+        if (cudaStreamWaitEvent(stream, ax.chunk_grads[c][i], 0) != cudaSuccess) { set_error("join chunk: %s", cudaGetErrorString(cudaGetLastError())); return MHE_ERR_CUDA; }
+    return MHE_OK;
 }
 
 static int g_prepared = 0;
@@ -1426,6 +1443,10 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
             MHE_TRY(tcflow::wgrad_kmajor(ptk(ws.a1b + ao, Rp, L.H, nb), ptk(ws.dpreT + so, Rp, kDp, nb), g, dparams + po + L.oW2, L.H, (long)L.blk, L.D, 1, s2,
                                          "fused wgrad W2"));
         }
+        if (par) {   // "every gradient of this chunk's layers is complete" (join_chunk: bucketed all-reduce)
+            for (int i = 0; i < 3; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.chunk_grads[c][i], ax.stream[i]), "chunk grads"));
+            if (cond) for (int i = 3; i < 6; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.chunk_grads[c][i], ax.stream[i + 1]), "chunk grads"));
+        }
         return MHE_OK;
     };
 
@@ -1455,6 +1476,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
         for (int i = 0; i < 3; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.wgrad_done[i], ax.stream[i]), "join"));
         if (cond) for (int i = 3; i < 6; ++i) MHE_TRY(cuda_ok(cudaEventRecord(ax.wgrad_done[i], ax.stream[i + 1]), "join"));
         ax.pending_n = cond ? 6 : 3;
+        ax.last_chunks = nchunk; ax.last_L = L.L; ax.last_direction = direction;
         // the re-plane stream is joined through the weight-gradient streams (they waited for replaned[c])
         if (async_wgrad()) ax.has_pending = true;    // the caller joins with mhe_flow_join() before reading dparams
         else MHE_TRY(join_pending_on(stream));

@@ -94,6 +94,9 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
 // Asynchronous weight gradients: with set_async_wgrad(1) pass_bwd returns with its weight-gradient GEMMs still running on internal
 // streams; join(stream) makes `stream` wait for them (mhe_flow_set_async / mhe_flow_join in the C ABI).
 void set_async_wgrad(int on);
+int chunk_count(int L);
+void chunk_layers(int L, int direction, int c, int* l0, int* nl);
+int join_chunk(cudaStream_t stream, int c);   // `stream` waits for every gradient of chunk c of the last (async) pass
 void set_wgrad_operands_prepared(int on);
 int pass_bwd_prepare(const FlowLayout& L, const float* mask, const float* saved, int R, int direction, void* workspace, cudaStream_t stream);
 int join(cudaStream_t stream);

@@ -20,7 +20,7 @@ from .losses import MHEntHead
 
 class TrainStep:
     def __init__(self, head: MHEntHead, B: int, S: int, device, want_verts: bool = True, use_graph: bool = True,
-                 prepare_ahead: bool = False, pipelined_cond_bwd: bool = False):
+                 prepare_ahead: bool = False, pipelined_cond_bwd: bool = False, allreduce_group=None, allreduce: bool = False):
         self.head, self.B, self.S, self.R = head, B, S, B * S
         self.dev = torch.device(device)
         flow = head.q_z_giv_i
@@ -72,6 +72,14 @@ class TrainStep:
         # mhe_flow_pass_cond_bwd (conditioning backward pipelined into the chunked pass) instead of the two calls: measured equal
         # within 1 % on one GPU (0.557 vs 0.551 ms); it is what a bucketed gradient all-reduce needs (chunk gradients complete early)
         self.pipelined_cond_bwd = pipelined_cond_bwd or bool(os.environ.get('MHE_ENGINE_PIPELINED_COND_BWD'))
+        # data parallelism: sum-all-reduce of the flat gradient and the loss INSIDE the step, bucketed by backward
+        # chunk - the gradients of a chunk's layers are exchanged while the remaining chunks still run (mhe_flow_join_chunk)
+        self.allreduce = bool(allreduce) and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size(allreduce_group) > 1
+        self.allreduce_group = allreduce_group
+        if self.allreduce:
+            self.pipelined_cond_bwd = self.tc
+            self.comm = torch.cuda.Stream(self.dev)
         self.launches_per_step = None
 
     # ------------------------------------------------------------------
@@ -164,9 +172,48 @@ class TrainStep:
                                           cws, cwsb, s), 'cond_bwd')
         finally:
             check(L.mhe_flow_set_async(0), 'set_async')
+        if self.allreduce:
+            self._enqueue_allreduce(L, shape, R)
         check(L.mhe_flow_join(s), 'flow_join')
         torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
         torch.cuda.current_stream(self.dev).wait_stream(self.side4)    # ... and the loss reductions
+
+    def _enqueue_allreduce(self, L, shape, R):
+        """Bucketed sum-all-reduce on the communication stream: chunk c's gradient segments as soon as its layers are complete."""
+        import ctypes
+        import torch.distributed as dist
+        main = torch.cuda.current_stream(self.dev)
+        self.comm.wait_stream(main)
+        total = L.mhe_flow_param_floats(shape)
+        nlayers = shape.layers
+
+        def off(layer, which):      # float offset of (layer, net 0, which); layer == L gives the end of that region
+            if layer < nlayers:
+                return L.mhe_flow_param_offset(shape, layer, 0, which)
+            return {0: L.mhe_flow_param_offset(shape, 0, 0, 6), 6: L.mhe_flow_param_offset(shape, 0, 0, 7), 7: total}[which]
+
+        nchunks = L.mhe_flow_bwd_chunk_count(shape, R) if self.tc else 1
+        with torch.cuda.stream(self.comm):
+            sp = _lib.stream_ptr(self.dev)
+            for c in range(nchunks):
+                l0, nl = ctypes.c_int(), ctypes.c_int()
+                check(L.mhe_flow_bwd_chunk_layers(shape, R, 0, c, ctypes.byref(l0), ctypes.byref(nl)), 'bwd_chunk_layers')
+                if self.tc and nchunks > 1:
+                    check(L.mhe_flow_join_chunk(sp, c), 'join_chunk')
+                else:
+                    check(L.mhe_flow_join(sp), 'flow_join')
+                # coupling blocks | conditioning weights | conditioning biases of layers [l0, l0 + nl): one grouped NCCL launch
+                segs = [self.dflat[off(l0.value, which):off(l0.value + nl.value, which)] for which in (0, 6, 7)]
+                if os.environ.get('MHE_ENGINE_NO_COALESCE'):
+                    for seg in segs:
+                        dist.all_reduce(seg, group=self.allreduce_group)
+                else:
+                    with dist._coalescing_manager(group=self.allreduce_group, device=self.dev, async_ops=False):
+                        for seg in segs:
+                            dist.all_reduce(seg, group=self.allreduce_group)
+            self.comm.wait_stream(self.side4)            # the loss (reduced on a side stream)
+            dist.all_reduce(self.loss, group=self.allreduce_group)
+        main.wait_stream(self.comm)
 
     def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
         """Copy one batch (host or device tensors) into the static input buffers."""

@@ -11,11 +11,17 @@ from mhentropy_b200.synthetic import synthetic_batch
 
 B, S = int(os.environ.get('B', 64)), int(os.environ.get('S', 10))
 graph = os.environ.get('GRAPH', '1') == '1'
-dev = torch.device('cuda')
+world = int(os.environ.get('WORLD_SIZE', 1))
+rank = int(os.environ.get('RANK', 0))
+if world > 1:      # torchrun: data-parallel step with the in-step bucketed all-reduce
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    dist.init_process_group('nccl')
+dev = torch.device('cuda', torch.cuda.current_device())
 torch.manual_seed(0)
 head = MHEntHead(mano_data=synthetic_mano(0)).to(dev)
 head.q_z_giv_i.precision = os.environ.get('PRECISION', 'bf16x3')
-eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=graph)
+eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=graph, allreduce=world > 1)
 eng.load(**{k: v.to(dev) for k, v in synthetic_batch(B, S, seed=1).items()})
 for _ in range(5):
     eng.run()
@@ -24,6 +30,8 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         eng.run()
     torch.cuda.synchronize()
+if rank != 0:
+    sys.exit(0)
 prof.export_chrome_trace('gpurun_out/trace_step.json')
 tr = json.load(open('gpurun_out/trace_step.json'))
 evs = [e for e in tr['traceEvents'] if e.get('cat') in ('kernel', 'gpu_memset', 'gpu_memcpy')]
