@@ -144,7 +144,7 @@ int mhe_flow_join_chunk(void* stream, int chunk);
  * on the forward pass (re-planed saved activations, masked inputs, zeroed scratch), enqueued on `stream`.  May run on any stream once
  * the forward pass that filled `saved` has completed - e.g. while the loss is computed; the caller orders it before
  * mhe_flow_pass_bwd and sets mhe_flow_set_async bit 3.  Returns MHE_ERR_UNSUPPORTED (and does nothing) when the pass would not take
- * the fused path.  (Validated for eager launches; inside a stream capture keep the default schedule.)                               */
+ * the fused path.                                                                                                                   */
 int mhe_flow_pass_bwd_prepare(mhe_flow_shape s, const float* mask, const float* saved, int R, int direction, void* workspace,
                               size_t workspace_bytes, void* stream);
 /* Zero the slots of a gradient buffer that accumulate even with mhe_flow_set_async bit 1 (the biases); the weight slots are then

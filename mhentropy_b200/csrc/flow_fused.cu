@@ -627,6 +627,7 @@ struct BwdArgs {
     long long* dbg;
     int R, Rp, D, H, L, direction, tiles, two_mma;
     int s_lo, s_hi;                             // the steps [s_lo, s_hi) this launch runs (descending): the pass may be cut into chunks
+    int zero_dpreT;                             // the kernel zeroes its rows of dpreT itself (no memset in front of it)
     size_t blk, ob2;
 };
 
@@ -920,6 +921,18 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
             gs[n * kXs + d] = r < p.R ? p.dout[(size_t)r * D + d] : 0.f;
         }
         if (t < 8) { const int r = r0 + 8 * (int)rank + t; gls[t] = (p.dlogdet && r < p.R) ? p.dlogdet_scale * p.dlogdet[r] : 0.f; }
+        if (p.zero_dpreT) {
+            // dpreT [layer][net][plane][64 dims][Rp]: the owners only write the transformed dims of their rows; this CTA zeroes its 8 rows
+            // of every dim / plane / net of the launch's layers once (16 bytes each), instead of a memset of the whole buffer in front
+            // of the kernel.  Same-CTA stores to the same addresses follow many barriers later.
+            const int nl = p.s_hi - p.s_lo;
+            const int l_first = p.direction == 0 ? p.s_lo : p.L - p.s_hi;
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = t; i < nl * 4 * kDp; i += kWorkers) {      // (layer, net, plane) x dim
+                uint16_t* q = reinterpret_cast<uint16_t*>(p.dpreT) + ((size_t)l_first * 4 * kDp + i) * p.Rp + r0 + 8 * (int)rank;
+                *reinterpret_cast<uint4*>(q) = z4;
+            }
+        }
         zero_dpre_tile();
         worker_sync();
         // every CTA's dpre tile is zeroed before any owner writes into it: cluster-wide rendezvous of the worker warps via bar_part
@@ -1342,7 +1355,7 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     if (st != MHE_OK) return st;
     // only the active dims of dpreT are written by the kernel
     const bool prepared = g_prepared != 0;            // pass_bwd_prepare already ran on this saved block / workspace (caller-ordered)
-    if (!prepared) MHE_TRY(cuda_ok(cudaMemsetAsync(ws.dpreT, 0, (size_t)L.L * 4 * kDp * Rp * 2, stream), "memset dpreT"));
+    a.zero_dpreT = prepared ? 0 : 1;                  // (pass_bwd_prepare memsets the whole buffer)
 
     static bool attr_set = false;
     if (!attr_set) {

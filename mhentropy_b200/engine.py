@@ -66,9 +66,8 @@ class TrainStep:
         self.mws = torch.empty(self.mws_bytes, dtype=torch.uint8, device=dev)
         self.graph = None
         self.use_graph = use_graph
-        # re-plane the weight-gradient operands right after the forward pass (see _enqueue); eager launches only for now: the
-        # extra fork invalidates the stream capture (cause not found yet), and it measured slower anyway
-        self.prepare_ahead = prepare_ahead and not use_graph
+        # re-plane the weight-gradient operands right after the forward pass (see _enqueue); measured slower, off by default
+        self.prepare_ahead = prepare_ahead
         # mhe_flow_pass_cond_bwd (conditioning backward pipelined into the chunked pass) instead of the two calls: measured equal
         # within 1 % on one GPU (0.557 vs 0.551 ms); it is what a bucketed gradient all-reduce needs (chunk gradients complete early)
         self.pipelined_cond_bwd = pipelined_cond_bwd or bool(os.environ.get('MHE_ENGINE_PIPELINED_COND_BWD'))
@@ -175,7 +174,8 @@ class TrainStep:
         if self.allreduce:
             self._enqueue_allreduce(L, shape, R)
         check(L.mhe_flow_join(s), 'flow_join')
-        torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
+        if self.verts is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
         torch.cuda.current_stream(self.dev).wait_stream(self.side4)    # ... and the loss reductions
 
     def _enqueue_allreduce(self, L, shape, R):

@@ -110,7 +110,7 @@ def test_engine_prepare_ahead_matches_default():
     devb = {k: v.to(DEV) for k, v in synthetic_batch(64, 10, seed=5).items()}
     outs = []
     for ahead in (False, True):
-        eng = TrainStep(head, 64, 10, DEV, want_verts=False, use_graph=False, prepare_ahead=ahead)   # (eager: see engine.py)
+        eng = TrainStep(head, 64, 10, DEV, want_verts=False, use_graph=True, prepare_ahead=ahead)
         eng.load(**devb)
         for _ in range(2):
             eng.run()
