@@ -103,3 +103,38 @@ def test_invalid_arguments_return_error_codes():
     assert L.mhe_flow_packed_bytes(shape) > 0 and L.mhe_flow_packed_bytes(_lib.FlowShape(45, 48, 16, 6)) == 0   # hidden % 64
     st = L.mhe_reproj_loss_fwd(ctypes.byref(_lib.LossCfg()), None, None, None, None, None, 7, 2, None, None, None, None, None, None, None)
     assert st == 1
+
+
+def test_load_reference_checkpoint(tmp_path):
+    """A checkpoint in the reference's format (CrossModalHand.py:573-586) loads into MHEntHead without renaming; the backbone entries
+    come back untouched; a different flow configuration fails loudly.  Uses the live reference's MHEnt when /root/reference exists."""
+    from mhentropy_b200.checkpoint import load_reference_checkpoint
+    from oracle import ref_shim
+    if ref_shim.reference_available():
+        src = ref_shim.build_mhent(synthetic_mano(0), seed=3)
+    else:
+        torch.manual_seed(3)
+        src = MHEntHead(mano_data=synthetic_mano(0))
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    sd['feat_extractor.conv1.weight'] = torch.randn(4, 3, 3, 3)
+    path = tmp_path / 'ent_test.pth'
+    torch.save({'decoderPose': {}, 'encoderRGB': sd}, path)
+    torch.manual_seed(99)
+    head = MHEntHead(mano_data=synthetic_mano(1))          # other weights, other MANO constants
+    rest = load_reference_checkpoint(head, str(path))
+    assert set(rest) == {'feat_extractor.conv1.weight'}
+    own = head.state_dict()
+    for k, v in sd.items():
+        if k in own:
+            assert torch.equal(own[k], v), k
+    assert len([k for k in own if k.startswith('q_z_giv_i.')]) == 241
+    # keep the head's own MANO buffers
+    head2 = MHEntHead(mano_data=synthetic_mano(1))
+    keep = head2.state_dict()['mano_dec.mano_layer.th_v_template'].clone()
+    load_reference_checkpoint(head2, {'encoderRGB': sd}, load_mano_buffers=False)
+    assert torch.equal(head2.state_dict()['mano_dec.mano_layer.th_v_template'], keep)
+    assert torch.equal(head2.state_dict()['det_head.2.bias'], sd['det_head.2.bias'])
+    # a different flow depth must not load silently
+    small = MHEntHead(q_z_giv_i_cfg=dict(num_steps=2), mano_data=synthetic_mano(0))
+    with pytest.raises(KeyError):
+        load_reference_checkpoint(small, {'encoderRGB': sd})
