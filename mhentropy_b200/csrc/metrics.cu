@@ -8,7 +8,7 @@ namespace mhe {
 
 constexpr int kMK = 21;          // joints
 constexpr int kMetricRows = 14;  // 2 spaces x (sample, sample_std, vis, vis_std, vis_mean, invis, invis_std)
-constexpr int kMWarps = 4;
+constexpr int kMWarps = 16;      // warps per image: the N hypotheses are strided over them
 
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
@@ -71,7 +71,12 @@ __global__ void __launch_bounds__(kMWarps * 32) hyp_metrics_kernel(const float* 
     // per-joint means over the hypotheses (coordinates), then the centred second pass
     float tot[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) tot[i] = s_sum[0][k][i] + s_sum[1][k][i] + s_sum[2][k][i] + s_sum[3][k][i];
+    for (int i = 0; i < 7; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kMWarps; ++ww) a += s_sum[ww][k][i];
+        tot[i] = a;
+    }
     if (warp == 0 && jt)
         for (int i = 0; i < 5; ++i) s_mean[k][i] = tot[2 + i] / (float)N;
     __syncthreads();
@@ -90,7 +95,12 @@ __global__ void __launch_bounds__(kMWarps * 32) hyp_metrics_kernel(const float* 
     if (warp != 0) return;
     float sd[5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) sd[i] = N > 1 ? sqrtf((s_sq[0][k][i] + s_sq[1][k][i] + s_sq[2][k][i] + s_sq[3][k][i]) / (float)(N - 1)) : 0.f;   // torch.std: unbiased
+    for (int i = 0; i < 5; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kMWarps; ++ww) a += s_sq[ww][k][i];
+        sd[i] = N > 1 ? sqrtf(a / (float)(N - 1)) : 0.f;   // torch.std: unbiased
+    }
     // spread of the hypotheses per joint: geometric mean of the per-axis std times sqrt(D) (criteria.py:153-160)
     const float sp3 = N > 1 ? cbrtf(sd[0] * sd[1] * sd[2]) * sqrtf(3.f) : 0.f;
     const float sp2 = N > 1 ? sqrtf(sd[3] * sd[4]) * sqrtf(2.f) : 0.f;

@@ -1,5 +1,7 @@
 """Secondary workloads of BASELINE.json through the drop-in API on one GPU (not bench lines; for the record in profiles/):
-config 3: inference sampling B=256 x S=100 (flow sample + MANO mesh + reprojection), config 4: NLL scoring of 16384 poses."""
+config 3: inference sampling B=256 x S=100 (flow sample + MANO mesh + reprojection), config 4: NLL scoring of 16384 poses; plus the
+SURVEY 8f-1 evaluation kernels at the reference's evaluation size (200 hypotheses per image, CrossModalHand.py:357-361): top-k selection and
+the MHEntLoss metrics, with their achieved bandwidth (they read the (N, B, .) outputs once: HBM / launch bound)."""
 import json
 import os
 import sys
@@ -62,4 +64,20 @@ def nll():
 ms = timeit(nll)
 assert torch.isfinite(res['lp']).all()
 out['config4_nll_scoring'] = {'rows': R, 'ms': ms, 'poses_per_s': R / (ms * 1e-3)}
+# ---- section 8f-1: hypothesis selection + multi-hypothesis metrics, N = 200 hypotheses x B = 256 images
+from mhentropy_b200 import hypothesis_metrics, topk_hypotheses  # noqa: E402
+N, Bm = 200, 256
+pose3d = torch.randn(Bm, 63, device=dev)
+xyz = pose3d[None] + 0.3 * torch.randn(N, Bm, 63, device=dev)
+crop_uv = torch.rand(Bm, 42, device=dev) * 2 - 1
+uv = (crop_uv[None] + 1) / 2 * 256 + 8. * torch.randn(N, Bm, 42, device=dev)
+scale = 0.05 + 0.1 * torch.rand(Bm, device=dev)
+vis = (torch.rand(Bm, 21, device=dev) < 0.7).float()
+log_q = torch.randn(N, Bm, device=dev)
+ms = timeit(lambda: res.__setitem__('m', hypothesis_metrics(xyz, uv, pose3d, scale, crop_uv, vis)), n=20)
+nbytes = 2 * N * Bm * (63 + 42) * 4          # two passes over xyz / uv (error terms, then the centred second moment)
+out['metrics_8f1'] = {'N': N, 'B': Bm, 'ms': ms, 'algorithmic_bytes': nbytes, 'GB_per_s': nbytes / (ms * 1e-3) / 1e9,
+                      'hypotheses_per_s': N * Bm / (ms * 1e-3)}
+ms = timeit(lambda: res.__setitem__('k', topk_hypotheses(log_q, 20)), n=20)
+out['topk_8f1'] = {'N': N, 'B': Bm, 'k': 20, 'ms': ms, 'hypotheses_per_s': N * Bm / (ms * 1e-3)}
 print(json.dumps(out))
