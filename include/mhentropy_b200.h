@@ -189,6 +189,7 @@ typedef struct mhe_mano_consts {
     const float* jt;
     const float* js;
     const float* pose_tables;   /* optional (may be NULL): mhe_mano_pose_tables_floats() floats filled by mhe_mano_pack_pose_tables() */
+    const void* posedirs_planes; /* optional (may be NULL): mhe_mano_posedirs_planes_bytes() bytes filled by mhe_mano_pack_posedirs_planes() */
 } mhe_mano_consts;
 
 /* The pose / joints kernels stage the small tables they need (PCA basis, joint regressors, the blend-shape rows and skinning
@@ -196,6 +197,13 @@ typedef struct mhe_mano_consts {
  * staging is a coalesced copy; with pose_tables == NULL every block gathers it from the full-size constants instead.          */
 size_t mhe_mano_pose_tables_floats(void);
 int mhe_mano_pack_pose_tables(const mhe_mano_consts* c, float* pose_tables, void* stream);
+
+/* Pose blend shapes on the tensor cores (reference manolayer.py:186-190: th_v_posed = th_v_shaped + posedirs . pose_map): with
+ * posedirs_planes set - posedirs as split half planes, the B operand of a tcgen05 GEMM - the mesh forward computes the pose offsets of
+ * all rows as ONE [R x 135] . [135 x 2334] contraction (3-pass split precision, fp32 accumulate) instead of a 135-term dot product per
+ * vertex on the CUDA cores; with NULL it takes the latter path.                                                                    */
+size_t mhe_mano_posedirs_planes_bytes(void);
+int mhe_mano_pack_posedirs_planes(const mhe_mano_consts* c, void* posedirs_planes, void* stream);
 
 #define MHE_MANO_VERTS 778
 #define MHE_MANO_JOINTS 21

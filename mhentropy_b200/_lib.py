@@ -20,7 +20,8 @@ class FlowShape(Structure):
 
 class ManoConsts(Structure):
     _fields_ = [(n, c_void_p) for n in
-                ('comps', 'hands_mean', 'v_template', 'shapedirs', 'posedirs_t', 'jreg', 'weights', 'jt', 'js', 'pose_tables')]
+                ('comps', 'hands_mean', 'v_template', 'shapedirs', 'posedirs_t', 'jreg', 'weights', 'jt', 'js', 'pose_tables',
+                 'posedirs_planes')]
 
 
 class LossCfg(Structure):
@@ -66,6 +67,8 @@ _SIGNATURES = {
     'mhe_std_normal_logp_bwd': (c_int, [_P, _P, c_int, c_int, _P, _P]),
     'mhe_mano_pose_tables_floats': (c_size_t, []),
     'mhe_mano_pack_pose_tables': (c_int, [POINTER(ManoConsts), _P, _P]),
+    'mhe_mano_posedirs_planes_bytes': (c_size_t, []),
+    'mhe_mano_pack_posedirs_planes': (c_int, [POINTER(ManoConsts), _P, _P]),
     'mhe_mano_workspace_bytes': (c_size_t, [c_int, c_int]),
     'mhe_mano_fwd': (c_int, [POINTER(ManoConsts), _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     'mhe_mano_bwd': (c_int, [POINTER(ManoConsts), _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int,

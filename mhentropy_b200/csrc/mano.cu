@@ -4,6 +4,7 @@
 #include "gemm_simt.cuh"
 #include "loss_rows.cuh"
 #include "mano_math.cuh"
+#include "tc_gemm.cuh"
 
 namespace mhe {
 using namespace mano;
@@ -32,17 +33,21 @@ constexpr int kWsRowFwd = kWsPm + kWsA + kWsCen;            // 332
 constexpr int kWsRowBwd = 192 + 136 + 12 + 4;               // 344
 constexpr int kWsRowMesh = 3 * 2336;                        // vp, dvt, dvp
 
+// tensor-core pose blend: pose-map planes [2][R][kPmK] (half), pose offsets [R][kOffLd] fp32
+constexpr int kPmK = 192;            // 135 pose-map entries padded to three 64-deep k-blocks
+constexpr int kOffLd = 2336;         // 2334 vertex coordinates padded to a 16-byte multiple of 16-bit elements
 struct ManoWs {
-    float *pm, *A, *cen, *dA, *dpm, *dbv, *dcen, *vp, *dvt, *dvp;
+    float *pm, *A, *cen, *dA, *dpm, *dbv, *dcen, *vp, *dvt, *dvp, *pmp, *poff;
     ManoWs(float* base, int R, bool mesh) {
         auto take = [&](size_t n) { float* p = base; base += (n + 63) / 64 * 64; return p; };
         pm = take((size_t)R * kWsPm); A = take((size_t)R * kWsA); cen = take((size_t)R * kWsCen);
         dA = take((size_t)R * 192); dpm = take((size_t)R * 136); dbv = take((size_t)R * 12); dcen = take((size_t)R * 4);
         vp = dvt = dvp = nullptr;
         if (mesh) { vp = take((size_t)R * 2336); dvt = take((size_t)R * 2336); dvp = take((size_t)R * 2336); }
+        pmp = take((size_t)R * kPmK); poff = take((size_t)R * kOffLd);      // (2 half planes of kPmK = kPmK floats per row)
     }
     static size_t floats(int R, bool mesh) {
-        return (size_t)R * (kWsRowFwd + kWsRowBwd + (mesh ? kWsRowMesh : 0)) + 10 * 64;
+        return (size_t)R * (kWsRowFwd + kWsRowBwd + (mesh ? kWsRowMesh : 0) + kPmK + kOffLd) + 12 * 64;
     }
 };
 
@@ -242,9 +247,10 @@ __device__ __forceinline__ void skin_vertex(const mhe_mano_consts& c, int v, con
 template <int RT>
 __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, const float* __restrict__ beta, int ld_beta, int R, int order,
                                                             const float* __restrict__ pm_g, const float* __restrict__ A_g, const float* __restrict__ cen_g,
-                                                            float* __restrict__ verts, float* __restrict__ jtr, float* __restrict__ vp_out) {
+                                                            float* __restrict__ verts, float* __restrict__ jtr, float* __restrict__ vp_out,
+                                                            const float* __restrict__ pose_off) {
     __shared__ float s_pm[RT][kWsPm];
-    __shared__ float s_A[RT][kWsA];
+    __shared__ __align__(16) float s_A[RT][kWsA];
     __shared__ float s_beta[RT][12];
     __shared__ float s_cen[RT][4];
     const int r0 = blockIdx.y * RT;
@@ -266,6 +272,14 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
             for (int b = 0; b < kShape; ++b) acc = fmaf(__ldg(c.shapedirs + (v * 3 + cc) * kShape + b), s_beta[rr][b], acc);
             vp[rr][cc] = acc;
         }
+    if (pose_off) {   // pose offsets of every row from the tensor-core GEMM
+#pragma unroll
+        for (int rr = 0; rr < RT; ++rr)
+            if (rr < nr) {
+                const float* po = pose_off + (long)(r0 + rr) * kOffLd + v * 3;
+                vp[rr][0] += po[0]; vp[rr][1] += po[1]; vp[rr][2] += po[2];
+            }
+    } else
     for (int k = 0; k < kPoseMap; ++k) {
         const float p0 = __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 0);
         const float p1 = __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 1);
@@ -295,9 +309,13 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
         for (int i = 0; i < 12; ++i) T[i] = 0.f;
 #pragma unroll
         for (int k = 0; k < kJ; ++k) {
-            if (w[k] != 0.f)
-#pragma unroll
-                for (int i = 0; i < 12; ++i) T[i] = fmaf(w[k], s_A[rr][k * 12 + i], T[i]);
+            if (w[k] != 0.f) {   // (the joint's 3 x 4 transform as three 16-byte shared-memory loads: this loop is LDS-bound)
+                const float4* a4 = reinterpret_cast<const float4*>(&s_A[rr][k * 12]);
+                const float4 a0 = a4[0], a1 = a4[1], a2 = a4[2];
+                T[0] = fmaf(w[k], a0.x, T[0]); T[1] = fmaf(w[k], a0.y, T[1]); T[2] = fmaf(w[k], a0.z, T[2]); T[3] = fmaf(w[k], a0.w, T[3]);
+                T[4] = fmaf(w[k], a1.x, T[4]); T[5] = fmaf(w[k], a1.y, T[5]); T[6] = fmaf(w[k], a1.z, T[6]); T[7] = fmaf(w[k], a1.w, T[7]);
+                T[8] = fmaf(w[k], a2.x, T[8]); T[9] = fmaf(w[k], a2.y, T[9]); T[10] = fmaf(w[k], a2.z, T[10]); T[11] = fmaf(w[k], a2.w, T[11]);
+            }
         }
         float o[3];
 #pragma unroll
@@ -602,11 +620,31 @@ __global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_ma
     for (int i = lane; i < loss::kZ; i += 32) dz[(long)r * loss::kZ + i] = dzr[i];
 }
 
+// epilogue of the pose-blend GEMM: row = hypothesis (TMEM lane), 32 consecutive vertex coordinates -> pose offsets [R][kOffLd]
+struct EpiPoseOffsets {
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
+    float* out;
+    __device__ void operator()(int, int, int row, int col0, float* v, const tc::GemmShape&) const {
+        float4* o = reinterpret_cast<float4*>(out + (long)row * kOffLd + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __device__ void elem(int, int, int, int, float, const tc::GemmShape&) const {}
+};
+
 }  // namespace mhe
 
 using namespace mhe;
 
 extern "C" {
+
+size_t mhe_mano_posedirs_planes_bytes(void) { return (size_t)2 * kPmK * kOffLd * 2; }
+
+int mhe_mano_pack_posedirs_planes(const mhe_mano_consts* c, void* posedirs_planes, void* stream) {
+    MHE_REQUIRE(c && c->posedirs_t && posedirs_planes && ((uintptr_t)posedirs_planes & 15) == 0, "mano_pack_posedirs_planes: bad args");
+    // posedirs_t [135][2334] (k-major) -> half planes [2][192][2336], zero padded: the MN-major B operand of the pose-blend GEMM
+    return tc::split_planes(c->posedirs_t, kVC, 0, kPoseMap, kVC, nullptr, (__nv_bfloat16*)posedirs_planes, kPmK, kOffLd, 2, 1, true, (cudaStream_t)stream);
+}
 
 size_t mhe_mano_pose_tables_floats(void) { return sizeof(PoseTables) / sizeof(float); }
 
@@ -635,12 +673,25 @@ int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
                                                                                  verts ? ws.pm : nullptr, verts ? ws.A : nullptr, verts ? ws.cen : nullptr, jtr);
     MHE_TRY(check_launch("mano pose fwd"));
     if (verts) {
+        const float* poff = nullptr;
+        if (c->posedirs_planes) {   // pose blend of all rows as one tensor-core GEMM: [R x 135] . [135 x 2334] -> pose offsets
+            MHE_TRY(tc::split_planes(ws.pm, kWsPm, 0, R, kPoseMap, nullptr, (__nv_bfloat16*)ws.pmp, R, kPmK, 2, 1, true, stream));
+            tc::PlaneTensor A, Bp;
+            A.base = (const __nv_bfloat16*)ws.pmp; A.cols = kPmK; A.rows = R; A.planes = 2; A.batches = 1;
+            A.row_pitch = kPmK; A.plane_stride = (long)R * kPmK; A.batch_stride = (long)2 * R * kPmK;
+            Bp.base = (const __nv_bfloat16*)c->posedirs_planes; Bp.cols = kOffLd; Bp.rows = kPmK; Bp.planes = 2; Bp.batches = 1;
+            Bp.row_pitch = kOffLd; Bp.plane_stride = (long)kPmK * kOffLd; Bp.batch_stride = (long)2 * kPmK * kOffLd;
+            tc::GemmShape g{R, kOffLd, kPmK, 1, 1, 1, 1};
+            EpiPoseOffsets e{ws.poff};
+            MHE_TRY((tc::launch_tc_gemm<128, false, true, 3, true>(A, Bp, g, e, stream, "mano pose blend")));
+            poff = ws.poff;
+        }
         if (R >= 512) {
             dim3 grid(cdiv(kV, 128), cdiv(R, 8));
-            mano_skin_fwd_kernel<8><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr);
+            mano_skin_fwd_kernel<8><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, poff);
         } else {
             dim3 grid(cdiv(kV, 128), cdiv(R, 2));
-            mano_skin_fwd_kernel<2><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr);
+            mano_skin_fwd_kernel<2><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, poff);
         }
         MHE_TRY(check_launch("mano skin fwd"));
         if (joints2) {
@@ -669,7 +720,7 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
                                                                                      ws.cen, nullptr);
         MHE_TRY(check_launch("mano pose recompute"));
         dim3 grid(cdiv(kV, 128), cdiv(R, 2));
-        mano_skin_fwd_kernel<2><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, nullptr, nullptr, ws.vp);
+        mano_skin_fwd_kernel<2><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, nullptr, nullptr, ws.vp, nullptr);
         MHE_TRY(check_launch("mano vposed recompute"));
         mano_dverts_total_kernel<<<cdiv(R * kV, 256), 256, 0, stream>>>(*c, dverts, djtr, djoints2, R, joint_order, ws.dvt);
         MHE_TRY(check_launch("mano dverts total"));

@@ -122,11 +122,16 @@ class ManoCore(nn.Module):
                 'js': torch.einsum('jv,vck->jck', jreg, d(self.th_shapedirs)).float(),
             }
             tensors = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in pack.items()}
-            c = ManoConsts(**{k: v.data_ptr() for k, v in tensors.items()}, pose_tables=None)
+            c = ManoConsts(**{k: v.data_ptr() for k, v in tensors.items()}, pose_tables=None, posedirs_planes=None)
             if torch.device(device).type == 'cuda':   # gather the small pose / tip tables once (coalesced staging in the kernels)
                 tensors['pose_tables'] = torch.empty(lib().mhe_mano_pose_tables_floats(), device=device, dtype=torch.float32)
                 check(lib().mhe_mano_pack_pose_tables(c, ptr(tensors['pose_tables']), stream_ptr(torch.device(device))), 'mhe_mano_pack_pose_tables')
                 c.pose_tables = tensors['pose_tables'].data_ptr()
+                # posedirs as split half planes: the pose blend of the mesh forward runs as one tcgen05 GEMM over all rows
+                tensors['posedirs_planes'] = torch.empty(lib().mhe_mano_posedirs_planes_bytes(), device=device, dtype=torch.uint8)
+                check(lib().mhe_mano_pack_posedirs_planes(c, ptr(tensors['posedirs_planes']), stream_ptr(torch.device(device))),
+                      'mhe_mano_pack_posedirs_planes')
+                c.posedirs_planes = tensors['posedirs_planes'].data_ptr()
             self._packed = (key, tensors, c)
         return self._packed[2]
 
