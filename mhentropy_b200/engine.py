@@ -67,7 +67,7 @@ class TrainStep:
         self.graph = None
         self.use_graph = use_graph
         # re-plane the weight-gradient operands right after the forward pass (see _enqueue); measured slower, off by default
-        self.prepare_ahead = prepare_ahead
+        self.prepare_ahead = prepare_ahead or bool(os.environ.get('MHE_ENGINE_PREPARE_AHEAD'))
         # mhe_flow_pass_cond_bwd (conditioning backward pipelined into the chunked pass) instead of the two calls: measured equal
         # within 1 % on one GPU (0.557 vs 0.551 ms); it is what a bucketed gradient all-reduce needs (chunk gradients complete early)
         self.pipelined_cond_bwd = pipelined_cond_bwd or bool(os.environ.get('MHE_ENGINE_PIPELINED_COND_BWD'))
