@@ -245,7 +245,7 @@ typedef struct mhe_loss_cfg {
 
 /* z = combine(x_flow [R][45], z_det [B][16] = th3|bt|logs|t)  (network.py:703-717, 747) */
 int mhe_combine_z_fwd(const float* x_flow, const float* z_det, int R, int B, float* z, void* stream);
-/* dz [R][61] -> dx_flow [R][45] (overwritten), dz_det [B][16] (overwritten: sum over the hypotheses) */
+/* dz [R][61] -> dx_flow [R][45] (overwritten; may be NULL), dz_det [B][16] (overwritten: sum over the hypotheses) */
 int mhe_combine_z_bwd(const float* dz, int R, int B, float* dx_flow, float* dz_det, void* stream);
 
 /* joints [R][21][3] (RHD order, mm), z [R][61], crop_uv [B][42], vis [B][21], log_q [R] ->
@@ -271,11 +271,13 @@ int mhe_image_loss_reduce(const float* row_log_p, const float* log_q, int R, int
  * manolayer.py:110-274), root / bone normalisation, projection, Laplace(visible) and priors (mhe_reproj_loss_fwd's row part;
  * utils.py:46-66, network.py:497-514, 233-258, 155-165), and the backward of both down to dz (mhe_reproj_loss_bwd + mhe_mano_bwd).
  * The loss is linear in the row terms, so the gradient seed of every row is the constant -dloss / R and nothing waits for a
- * reduction.  z [R][61] (theta = z[:, 0:48], beta = z[:, 48:58]), crop_uv [B][42], vis [B][21] ->
- *   jtr [R][21][3] (may be NULL), uv [R][42] (may be NULL), row_log_p [R], dz [R][61] (overwritten), dlog_q [R] (may be NULL).     */
-int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* crop_uv,
-                                const float* vis, int R, int B, int joint_order, float dloss,
-                                float* jtr, float* uv, float* row_log_p, float* dz, float* dlog_q, void* stream);
+ * reduction.  z [R][61] (theta = z[:, 0:48], beta = z[:, 48:58]) - or z == NULL and its two sources x_flow [R][45], z_det [B][16]
+ * (mhe_combine_z_fwd's inputs: the kernel assembles the row itself) -, crop_uv [B][42], vis [B][21] ->
+ *   jtr [R][21][3] (may be NULL), uv [R][42] (may be NULL), row_log_p [R], dz [R][61] (overwritten), dx_flow [R][45] (may be NULL: the
+ *   flow's columns of dz, what mhe_combine_z_bwd extracts), dlog_q [R] (may be NULL).                                               */
+int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* x_flow,
+                                const float* z_det, const float* crop_uv, const float* vis, int R, int B, int joint_order, float dloss,
+                                float* jtr, float* uv, float* row_log_p, float* dz, float* dx_flow, float* dlog_q, void* stream);
 
 /* xyz / verts normalisation and projection for MHEnt.sample (network.py:466-483, 497-514, 876-877):
  * joints [R][21][3], verts [R][778][3] (NULL ok), logs_t = z[:, 58:61] with row stride ld_z ->

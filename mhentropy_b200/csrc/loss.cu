@@ -17,7 +17,7 @@ __global__ void combine_z_fwd_kernel(const float* __restrict__ x, const float* _
 
 __global__ void combine_z_bwd_kernel(const float* __restrict__ dz, int R, int B, float* __restrict__ dx, float* __restrict__ dzd) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (long)R * 45) {
+    if (dx && i < (long)R * 45) {
         const int r = (int)(i / 45), c = (int)(i % 45);
         dx[i] = dz[(long)r * kZ + 3 + c];
     }
@@ -130,9 +130,9 @@ int mhe_combine_z_fwd(const float* x_flow, const float* z_det, int R, int B, flo
 
 int mhe_combine_z_bwd(const float* dz, int R, int B, float* dx_flow, float* dz_det, void* stream) {
     if (R == 0) return MHE_OK;
-    MHE_REQUIRE(dz && dx_flow && dz_det && R >= 0 && B > 0 && R % B == 0, "combine_z_bwd: bad args");
+    MHE_REQUIRE(dz && dz_det && R >= 0 && B > 0 && R % B == 0, "combine_z_bwd: bad args");
     if (R == 0) return MHE_OK;
-    const long n = (long)R * 45 > (long)B * 16 ? (long)R * 45 : (long)B * 16;
+    const long n = (dx_flow && (long)R * 45 > (long)B * 16) ? (long)R * 45 : (long)B * 16;
     combine_z_bwd_kernel<<<cdiv((int)n, 256), 256, 0, (cudaStream_t)stream>>>(dz, R, B, dx_flow, dz_det);
     return check_launch("combine z bwd");
 }

@@ -570,12 +570,13 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
 // terms, loss = -mean_b mean_n (row_log_p - log_q) (network.py:793-808, criteria.py:55,173), so with dloss = 1 every row's gradient
 // seed is the constant -1 / (B N) and nothing of the backward waits for a reduction.  z [R][61] = th3 | th45 | bt | logs | t.
 __global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_mano_consts c, mhe_loss_cfg cfg, const float* __restrict__ z,
+                                     const float* __restrict__ x_flow, const float* __restrict__ z_det,
                                      const float* __restrict__ crop_uv, const float* __restrict__ vis, int R, int B, int order, float dloss,
                                      float* __restrict__ jtr, float* __restrict__ uv, float* __restrict__ row_lp, float* __restrict__ dz,
-                                     float* __restrict__ dlog_q) {
+                                     float* __restrict__ dx_flow, float* __restrict__ dlog_q) {
     __shared__ WarpPose s_w[kPoseWarps];
     __shared__ PoseTables s_t;
-    __shared__ float s_jo[kPoseWarps][64], s_dz[kPoseWarps][64];
+    __shared__ float s_jo[kPoseWarps][64], s_dz[kPoseWarps][64], s_z[kPoseWarps][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * kPoseWarps + warp;
     stage_pose_tables(c, s_t, true);
@@ -584,8 +585,16 @@ __global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_ma
     WarpPose& W = s_w[warp];
     float* jo = s_jo[warp];
     float* dzr = s_dz[warp];
-    const float* zz = z + (long)r * loss::kZ;
     const int b = r % B;
+    const float* zz;
+    if (z) zz = z + (long)r * loss::kZ;
+    else {   // z = th3 | th45 (flow) | bt | logs | t assembled here (network.py:703-717): no separate z kernel in front of this one
+        float* zr = s_z[warp];
+        for (int i = lane; i < loss::kZ; i += 32)
+            zr[i] = i < 3 ? z_det[b * 16 + i] : (i < 48 ? x_flow[(long)r * 45 + i - 3] : z_det[b * 16 + i - 45]);
+        __syncwarp();
+        zz = zr;
+    }
     pose_fwd_warp(s_t, zz, zz + 48, W, lane);
     // the 21 output joints (chain joints + tip vertices, reordered, centred, millimetres)
     for (int i = lane; i < kNJ * 3; i += 32) {
@@ -618,6 +627,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_ma
     for (int i = lane; i < kPose; i += 32) dzr[i] += pose_dtheta(s_t, W, i);
     __syncwarp();
     for (int i = lane; i < loss::kZ; i += 32) dz[(long)r * loss::kZ + i] = dzr[i];
+    if (dx_flow) for (int i = lane; i < 45; i += 32) dx_flow[(long)r * 45 + i] = dzr[3 + i];     // the flow's share of dz (network.py:703-717)
 }
 
 // epilogue of the pose-blend GEMM: row = hypothesis (TMEM lane), 32 consecutive vertex coordinates -> pose offsets [R][kOffLd]
@@ -745,14 +755,14 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
     return check_launch("mano pose bwd");
 }
 
-int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* crop_uv, const float* vis,
-                                int R, int B, int joint_order, float dloss, float* jtr, float* uv, float* row_log_p, float* dz, float* dlog_q,
-                                void* stream) {
+int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* x_flow, const float* z_det,
+                                const float* crop_uv, const float* vis, int R, int B, int joint_order, float dloss, float* jtr, float* uv,
+                                float* row_log_p, float* dz, float* dx_flow, float* dlog_q, void* stream) {
     if (R == 0) return MHE_OK;
-    MHE_REQUIRE(c && cfg && z && crop_uv && vis && row_log_p && dz, "hypothesis_rows_fwd_bwd: null pointer");
+    MHE_REQUIRE(c && cfg && (z || (x_flow && z_det)) && crop_uv && vis && row_log_p && dz, "hypothesis_rows_fwd_bwd: null pointer");
     MHE_REQUIRE(R > 0 && B > 0 && R % B == 0 && joint_order >= 0 && joint_order <= 1, "hypothesis_rows_fwd_bwd: bad sizes");
-    hypothesis_rows_kernel<<<cdiv(R, kPoseWarps), kPoseWarps * 32, 0, (cudaStream_t)stream>>>(*c, *cfg, z, crop_uv, vis, R, B, joint_order, dloss, jtr,
-                                                                                               uv, row_log_p, dz, dlog_q);
+    hypothesis_rows_kernel<<<cdiv(R, kPoseWarps), kPoseWarps * 32, 0, (cudaStream_t)stream>>>(*c, *cfg, z, x_flow, z_det, crop_uv, vis, R, B, joint_order,
+                                                                                               dloss, jtr, uv, row_log_p, dz, dx_flow, dlog_q);
     return check_launch("hypothesis rows fwd+bwd");
 }
 

@@ -143,8 +143,12 @@ class TrainStep:
             self.dflat.zero_()
             self.dcp.zero_()
         # ---- MANO joints + reprojection / priors forward AND backward (dloss = 1) of every hypothesis: one kernel
-        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), ptr(self.crop_uv), ptr(self.vis), R, B, 1, 1.0,
-                                            ptr(self.jtr), ptr(self.uv), ptr(self.row_lp), ptr(self.dz), ptr(self.dlog_q), s), 'hypothesis_rows')
+        # (the kernel can also assemble its row of z from x / z_det and emit the flow's share of dz itself, which takes both combine_z
+        # kernels off this chain - measured slower, 0.549 vs 0.537 ms: the backward's cluster kernel needs entirely free SMs and cannot
+        # start before the mesh skinning has drained anyway, and an earlier per-row kernel collides with the pose-blend GEMM)
+        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), None, None, ptr(self.crop_uv), ptr(self.vis), R, B, 1, 1.0,
+                                            ptr(self.jtr), ptr(self.uv), ptr(self.row_lp), ptr(self.dz), None, ptr(self.dlog_q), s),
+              'hypothesis_rows')
         self.side4.wait_stream(main)
         with torch.cuda.stream(self.side4):
             check(L.mhe_image_loss_reduce(ptr(self.row_lp), ptr(self.log_q), R, B, ptr(self.log_p), ptr(self.h), ptr(self.qlp),

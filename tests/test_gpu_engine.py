@@ -90,8 +90,20 @@ def test_hypothesis_rows_kernel_matches_separate_kernels(R, B):
     check(L.mhe_mano_bwd(consts, theta, 61, beta, 61, R, 1, None, ptr(dj0), None, dz0.data_ptr(), 61, dz0.data_ptr() + 48 * 4, 61, 1,
                          ptr(ws), wsb, s), 'mano_bwd')
     jtr1, uv1, lp1, dz1, dlq1 = f(R, 21, 3), f(R, 42), f(R), f(R, 61), f(R)
-    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(z), ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr1), ptr(uv1), ptr(lp1), ptr(dz1),
-                                        ptr(dlq1), s), 'rows')
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(z), None, None, ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr1), ptr(uv1), ptr(lp1),
+                                        ptr(dz1), None, ptr(dlq1), s), 'rows')
+    # the same from z's two sources, with the flow's share of dz as an extra output
+    x_flow, z_det = z[:, 3:48].contiguous(), torch.cat([z[:B, :3], z[:B, 48:]], 1).contiguous()
+    zc = torch.empty_like(z)
+    check(L.mhe_combine_z_fwd(ptr(x_flow), ptr(z_det), R, B, ptr(zc), s), 'combine')
+    jtr2, uv2, lp2, dz2, dx2 = f(R, 21, 3), f(R, 42), f(R), f(R, 61), f(R, 45)
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, None, ptr(x_flow), ptr(z_det), ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr2), ptr(uv2),
+                                        ptr(lp2), ptr(dz2), ptr(dx2), None, s), 'rows from sources')
+    jtr3, lp3, dz3 = f(R, 21, 3), f(R), f(R, 61)
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(zc), None, None, ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr3), None, ptr(lp3),
+                                        ptr(dz3), None, None, s), 'rows from combined z')
+    torch.cuda.synchronize()
+    assert torch.equal(jtr2, jtr3) and torch.equal(lp2, lp3) and torch.equal(dz2, dz3) and torch.equal(dx2, dz2[:, 3:48])
     logp1, loss1 = f(B), f(1)
     check(L.mhe_image_loss_reduce(ptr(lp1), ptr(log_q), R, B, ptr(logp1), None, None, ptr(loss1), s), 'reduce')
     torch.cuda.synchronize()
