@@ -1,4 +1,5 @@
 set -x
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r1v3_smoke.log 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r1v3_pytest_gpu.log
 python bench.py --steps 50 --warmup 5 > gpurun_out/r1v3_bench.json 2> gpurun_out/r1v3_bench.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r1v3_ref.json 2> gpurun_out/r1v3_ref.err
