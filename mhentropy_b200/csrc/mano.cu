@@ -255,8 +255,13 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
     __shared__ float s_cen[RT][4];
     const int r0 = blockIdx.y * RT;
     const int nr = min(RT, R - r0);
-    for (int i = threadIdx.x; i < RT * kWsPm; i += blockDim.x) { const int rr = i / kWsPm; s_pm[rr][i % kWsPm] = rr < nr ? pm_g[(long)(r0 + rr) * kWsPm + i % kWsPm] : 0.f; }
-    for (int i = threadIdx.x; i < RT * kWsA; i += blockDim.x) { const int rr = i / kWsA; s_A[rr][i % kWsA] = rr < nr ? A_g[(long)(r0 + rr) * kWsA + i % kWsA] : 0.f; }
+    if (!pose_off)   // (the pose map is only read by the in-kernel pose blend)
+        for (int i = threadIdx.x; i < RT * kWsPm; i += blockDim.x) { const int rr = i / kWsPm; s_pm[rr][i % kWsPm] = rr < nr ? pm_g[(long)(r0 + rr) * kWsPm + i % kWsPm] : 0.f; }
+    {   // the tile's joint transforms are one contiguous block of nr * 192 floats: 16-byte copies, no index arithmetic
+        const float4* src = reinterpret_cast<const float4*>(A_g + (long)r0 * kWsA);
+        float4* dst = reinterpret_cast<float4*>(&s_A[0][0]);
+        for (int i = threadIdx.x; i < RT * kWsA / 4; i += blockDim.x) dst[i] = i < nr * kWsA / 4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int i = threadIdx.x; i < RT * kShape; i += blockDim.x) { const int rr = i / kShape; s_beta[rr][i % kShape] = rr < nr ? beta[(long)(r0 + rr) * ld_beta + i % kShape] : 0.f; }
     for (int i = threadIdx.x; i < RT * 3; i += blockDim.x) { const int rr = i / 3; s_cen[rr][i % 3] = rr < nr ? cen_g[(long)(r0 + rr) * kWsCen + i % 3] : 0.f; }
     __syncthreads();
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
         for (int i = 0; i < 12; ++i) T[i] = 0.f;
 #pragma unroll
         for (int k = 0; k < kJ; ++k) {
-            if (w[k] != 0.f) {   // (the joint's 3 x 4 transform as three 16-byte shared-memory loads: this loop is LDS-bound)
+            if (w[k] != 0.f) {   // real MANO skinning weights have <= 4 non-zeros per vertex   // (the joint's 3 x 4 transform as three 16-byte shared-memory loads: this loop is LDS-bound)
                 const float4* a4 = reinterpret_cast<const float4*>(&s_A[rr][k * 12]);
                 const float4 a0 = a4[0], a1 = a4[1], a2 = a4[2];
                 T[0] = fmaf(w[k], a0.x, T[0]); T[1] = fmaf(w[k], a0.y, T[1]); T[2] = fmaf(w[k], a0.z, T[2]); T[3] = fmaf(w[k], a0.w, T[3]);

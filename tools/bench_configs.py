@@ -64,6 +64,27 @@ def nll():
 ms = timeit(nll)
 assert torch.isfinite(res['lp']).all()
 out['config4_nll_scoring'] = {'rows': R, 'ms': ms, 'poses_per_s': R / (ms * 1e-3)}
+# ---- MANO mesh alone at the config-3 row count: pose kernel + pose-blend GEMM (tensor cores) + shape blend / LBS (HBM-bound part)
+from mhentropy_b200._lib import check, lib, ptr, stream_ptr  # noqa: E402
+Rm = B * S
+consts = head.mano_dec.mano_layer._consts(dev)
+zz = torch.cat([0.5 * torch.randn(Rm, 3), 1.0 * torch.randn(Rm, 45), 0.02 * torch.randn(Rm, 10), torch.zeros(Rm, 3)], 1).to(dev).contiguous()
+verts, jtr = torch.empty(Rm, 778, 3, device=dev), torch.empty(Rm, 21, 3, device=dev)
+mwsb = lib().mhe_mano_workspace_bytes(Rm, 0)
+mws = torch.empty(mwsb, dtype=torch.uint8, device=dev)
+
+
+def mesh():
+    check(lib().mhe_mano_fwd(consts, zz.data_ptr(), 61, zz.data_ptr() + 48 * 4, 61, Rm, 1, ptr(verts), ptr(jtr), None, ptr(mws), mwsb,
+                             stream_ptr(dev)), 'mano_fwd')
+
+
+ms = timeit(mesh, n=10)
+lbs_bytes = Rm * (9336 + 9344)            # vertices written + pose offsets read per row
+out['mano_mesh_fwd'] = {'rows': Rm, 'ms': ms, 'rows_per_s': Rm / (ms * 1e-3), 'lbs_algorithmic_bytes': lbs_bytes,
+                        'GB_per_s_whole_mesh_path': lbs_bytes / (ms * 1e-3) / 1e9,
+                        'pose_blend_gflop': Rm * 630180 / 1e9, 'note': 'whole mesh path (pose kernel + split + pose-blend GEMM + skinning) timed '
+                        'together; the LBS bytes over that time is a lower bound of the skinning kernel\'s own bandwidth'}
 # ---- section 8f-1: hypothesis selection + multi-hypothesis metrics, N = 200 hypotheses x B = 256 images
 from mhentropy_b200 import hypothesis_metrics, topk_hypotheses  # noqa: E402
 N, Bm = 200, 256
