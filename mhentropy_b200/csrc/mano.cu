@@ -36,8 +36,11 @@ constexpr int kWsRowMesh = 3 * 2336;                        // vp, dvt, dvp
 // tensor-core pose blend: pose-map planes [2][R][kPmK] (half), pose offsets [R][kOffLd] fp32
 constexpr int kPmK = 192;            // 135 pose-map entries padded to three 64-deep k-blocks
 constexpr int kOffLd = 2336;         // 2334 vertex coordinates padded to a 16-byte multiple of 16-bit elements
+constexpr int kLbsN = 16;            // the 12 entries of a 3 x 4 transform padded to 16 GEMM columns per row
+constexpr int kVp = 896;             // 778 vertices padded to 7 tiles of 128
+constexpr int kBlendRows = kPoseMap + kShape + 1;   // contraction of the blend GEMM: 135 pose-map entries | 10 betas | 1 (template)
 struct ManoWs {
-    float *pm, *A, *cen, *dA, *dpm, *dbv, *dcen, *vp, *dvt, *dvp, *pmp, *poff;
+    float *pm, *A, *cen, *dA, *dpm, *dbv, *dcen, *vp, *dvt, *dvp, *pmp, *poff, *lbsb;
     ManoWs(float* base, int R, bool mesh) {
         auto take = [&](size_t n) { float* p = base; base += (n + 63) / 64 * 64; return p; };
         pm = take((size_t)R * kWsPm); A = take((size_t)R * kWsA); cen = take((size_t)R * kWsCen);
@@ -45,9 +48,10 @@ struct ManoWs {
         vp = dvt = dvp = nullptr;
         if (mesh) { vp = take((size_t)R * 2336); dvt = take((size_t)R * 2336); dvp = take((size_t)R * 2336); }
         pmp = take((size_t)R * kPmK); poff = take((size_t)R * kOffLd);      // (2 half planes of kPmK = kPmK floats per row)
+        lbsb = take((size_t)R * kLbsN * 64);                                // 2 half planes [R * 16][64]
     }
     static size_t floats(int R, bool mesh) {
-        return (size_t)R * (kWsRowFwd + kWsRowBwd + (mesh ? kWsRowMesh : 0) + kPmK + kOffLd) + 12 * 64;
+        return (size_t)R * (kWsRowFwd + kWsRowBwd + (mesh ? kWsRowMesh : 0) + kPmK + kOffLd + kLbsN * 64) + 13 * 64;
     }
 };
 
@@ -269,6 +273,13 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
     if (v >= kV) return;
 
     float vp[RT][3];
+    if (pose_off) {   // template + shape blend + pose blend of every row: the tensor-core blend GEMM's output
+#pragma unroll
+        for (int rr = 0; rr < RT; ++rr) {
+            const float* po = pose_off + (long)(r0 + (rr < nr ? rr : 0)) * kOffLd + v * 3;
+            vp[rr][0] = po[0]; vp[rr][1] = po[1]; vp[rr][2] = po[2];
+        }
+    } else {
 #pragma unroll
     for (int rr = 0; rr < RT; ++rr)
 #pragma unroll
@@ -277,14 +288,6 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
             for (int b = 0; b < kShape; ++b) acc = fmaf(__ldg(c.shapedirs + (v * 3 + cc) * kShape + b), s_beta[rr][b], acc);
             vp[rr][cc] = acc;
         }
-    if (pose_off) {   // pose offsets of every row from the tensor-core GEMM
-#pragma unroll
-        for (int rr = 0; rr < RT; ++rr)
-            if (rr < nr) {
-                const float* po = pose_off + (long)(r0 + rr) * kOffLd + v * 3;
-                vp[rr][0] += po[0]; vp[rr][1] += po[1]; vp[rr][2] += po[2];
-            }
-    } else
     for (int k = 0; k < kPoseMap; ++k) {
         const float p0 = __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 0);
         const float p1 = __ldg(c.posedirs_t + (long)k * kVC + v * 3 + 1);
@@ -296,6 +299,7 @@ __global__ void __launch_bounds__(128) mano_skin_fwd_kernel(mhe_mano_consts c, c
             vp[rr][1] = fmaf(p1, p, vp[rr][1]);
             vp[rr][2] = fmaf(p2, p, vp[rr][2]);
         }
+    }
     }
     float w[kJ];
 #pragma unroll
@@ -635,6 +639,89 @@ __global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_ma
     if (dx_flow) for (int i = lane; i < 45; i += 32) dx_flow[(long)r * 45 + i] = dzr[3 + i];     // the flow's share of dz (network.py:703-717)
 }
 
+// ---- tensor-core mesh path ----------------------------------------------------------------------------------------------
+// (1) blend GEMM   vp[r][v*3+c] = sum_k P[r][k] Bd[k][v*3+c],  P = [pose map | beta | 1],  Bd = [posedirs ; shapedirs^T ; v_template]
+// (2) skinning GEMM T[v][(r, e)] = sum_j weights[v][j] A[r][j][e]  (e < 12: the 3 x 4 transform), epilogue: verts = T . vp - centre
+// Operands are split half planes (3-pass split precision, fp32 accumulate), K padded to the 64-deep k-block of the GEMM kernel.
+__global__ void __launch_bounds__(256) mano_pack_blend_planes_kernel(mhe_mano_consts c, uint16_t* __restrict__ bd, uint16_t* __restrict__ wp) {
+    const long nbd = (long)kPmK * kOffLd, nw = (long)kVp * 64;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nbd + nw; i += (long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        uint16_t* dst;
+        long plane;
+        if (i < nbd) {
+            const int k = (int)(i / kOffLd), col = (int)(i % kOffLd);
+            if (col < kVC) {
+                if (k < kPoseMap) v = c.posedirs_t[(long)k * kVC + col];
+                else if (k < kPoseMap + kShape) v = c.shapedirs[(long)col * kShape + (k - kPoseMap)];
+                else if (k == kPoseMap + kShape) v = c.v_template[col];
+            }
+            dst = bd + i; plane = nbd;
+        } else {
+            const long j = i - nbd;
+            const int vtx = (int)(j / 64), k = (int)(j % 64);
+            if (vtx < kV && k < kJ) v = c.weights[vtx * kJ + k];
+            dst = wp + j; plane = nw;
+        }
+        const uint16_t h = tc::to16<true>(v);
+        dst[0] = h;
+        dst[plane] = tc::to16<true>(v - tc::from16<true>(h));
+    }
+}
+// per-row operands: P planes [2][R][192] and the transposed transforms [2][R*16][64] (element (r*16 + e, j) = A[r][j][e])
+__global__ void __launch_bounds__(256) mano_mesh_operands_kernel(const float* __restrict__ pm, const float* __restrict__ A, const float* __restrict__ beta,
+                                                                 int ld_beta, int R, uint16_t* __restrict__ pmp, uint16_t* __restrict__ lbsb) {
+    const long np = (long)R * kPmK, nl = lbsb ? (long)R * kLbsN * 64 : 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < np + nl; i += (long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        uint16_t* dst;
+        long plane;
+        if (i < np) {
+            const int r = (int)(i / kPmK), k = (int)(i % kPmK);
+            if (k < kPoseMap) v = pm[(long)r * kWsPm + k];
+            else if (k < kPoseMap + kShape) v = beta[(long)r * ld_beta + k - kPoseMap];
+            else if (k == kPoseMap + kShape) v = 1.f;
+            dst = pmp + i; plane = np;
+        } else {
+            const long j = i - np;
+            const int k = (int)(j % 64), e = (int)((j / 64) % kLbsN), r = (int)(j / (64 * kLbsN));
+            if (k < kJ && e < 12) v = A[(long)r * kWsA + k * 12 + e];
+            dst = lbsb + j; plane = nl;
+        }
+        const uint16_t h = tc::to16<true>(v);
+        dst[0] = h;
+        dst[plane] = tc::to16<true>(v - tc::from16<true>(h));
+    }
+}
+// epilogue of the skinning GEMM: thread = vertex (TMEM lane), 32 columns = the padded transforms of two consecutive rows
+struct EpiSkin {
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
+    const float* vp; const float* cen; float* verts; float* jtr; int R, order;
+    __device__ void operator()(int, int, int vtx, int col0, float* t, const tc::GemmShape&) const {
+        int tip = -1;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) if (c_tip_vert[q] == vtx) tip = q;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = (col0 >> 4) + h;
+            if (r >= R) continue;
+            const float* T = t + 16 * h;
+            const float* p = vp + (long)r * kOffLd + vtx * 3;
+            const float p0 = p[0], p1 = p[1], p2 = p[2];
+            const float* cc = cen + (long)r * kWsCen;
+            float o[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) o[i] = (T[i * 3 + 0] * p0 + T[i * 3 + 1] * p1 + T[i * 3 + 2] * p2 + T[9 + i] - cc[i]) * kMM;
+            float* d = verts + ((long)r * kV + vtx) * 3;
+            d[0] = o[0]; d[1] = o[1]; d[2] = o[2];
+            if (tip >= 0 && jtr)
+                for (int i = 0; i < kNJ; ++i)
+                    if (c_jtr_src[order][i] == kJ + tip) { float* dj = jtr + ((long)r * kNJ + i) * 3; dj[0] = o[0]; dj[1] = o[1]; dj[2] = o[2]; }
+        }
+    }
+    __device__ void elem(int, int, int, int, float, const tc::GemmShape&) const {}
+};
+
 // epilogue of the pose-blend GEMM: row = hypothesis (TMEM lane), 32 consecutive vertex coordinates -> pose offsets [R][kOffLd]
 struct EpiPoseOffsets {
     static constexpr bool kDirect = true, kStaged = false, kRmw = false;
@@ -653,12 +740,16 @@ using namespace mhe;
 
 extern "C" {
 
-size_t mhe_mano_posedirs_planes_bytes(void) { return (size_t)2 * kPmK * kOffLd * 2; }
+size_t mhe_mano_posedirs_planes_bytes(void) { return ((size_t)2 * kPmK * kOffLd + (size_t)2 * kVp * 64) * 2; }
 
 int mhe_mano_pack_posedirs_planes(const mhe_mano_consts* c, void* posedirs_planes, void* stream) {
-    MHE_REQUIRE(c && c->posedirs_t && posedirs_planes && ((uintptr_t)posedirs_planes & 15) == 0, "mano_pack_posedirs_planes: bad args");
-    // posedirs_t [135][2334] (k-major) -> half planes [2][192][2336], zero padded: the MN-major B operand of the pose-blend GEMM
-    return tc::split_planes(c->posedirs_t, kVC, 0, kPoseMap, kVC, nullptr, (__nv_bfloat16*)posedirs_planes, kPmK, kOffLd, 2, 1, true, (cudaStream_t)stream);
+    MHE_REQUIRE(c && c->posedirs_t && c->shapedirs && c->v_template && c->weights && posedirs_planes && ((uintptr_t)posedirs_planes & 15) == 0,
+                "mano_pack_posedirs_planes: bad args");
+    // [posedirs ; shapedirs^T ; v_template] as half planes [2][192][2336] (the MN-major B operand of the blend GEMM), then the skinning
+    // weights as half planes [2][896][64] (the A operand of the skinning GEMM), zero padded
+    uint16_t* bd = (uint16_t*)posedirs_planes;
+    mano_pack_blend_planes_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(*c, bd, bd + (size_t)2 * kPmK * kOffLd);
+    return check_launch("mano pack blend planes");
 }
 
 size_t mhe_mano_pose_tables_floats(void) { return sizeof(PoseTables) / sizeof(float); }
@@ -688,27 +779,47 @@ int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
                                                                                  verts ? ws.pm : nullptr, verts ? ws.A : nullptr, verts ? ws.cen : nullptr, jtr);
     MHE_TRY(check_launch("mano pose fwd"));
     if (verts) {
-        const float* poff = nullptr;
-        if (c->posedirs_planes) {   // pose blend of all rows as one tensor-core GEMM: [R x 135] . [135 x 2334] -> pose offsets
-            MHE_TRY(tc::split_planes(ws.pm, kWsPm, 0, R, kPoseMap, nullptr, (__nv_bfloat16*)ws.pmp, R, kPmK, 2, 1, true, stream));
+        if (c->posedirs_planes) {   // both contractions of the mesh on the tensor cores (see above)
+            const uint16_t* bd = (const uint16_t*)c->posedirs_planes;
+            const uint16_t* wp = bd + (size_t)2 * kPmK * kOffLd;
+            static const bool tc_skin = getenv("MHE_MANO_TC_SKIN") != nullptr;
+            const long nel = (long)R * (kPmK + (tc_skin ? kLbsN * 64 : 0));
+            const int nblk = (int)((nel + 255) / 256 < 1184 ? (nel + 255) / 256 : 1184);      // grid-stride beyond 8 blocks per SM
+            mano_mesh_operands_kernel<<<nblk, 256, 0, stream>>>(ws.pm, ws.A, beta, ld_beta, R, (uint16_t*)ws.pmp, tc_skin ? (uint16_t*)ws.lbsb : nullptr);
+            MHE_TRY(check_launch("mano mesh operands"));
             tc::PlaneTensor A, Bp;
             A.base = (const __nv_bfloat16*)ws.pmp; A.cols = kPmK; A.rows = R; A.planes = 2; A.batches = 1;
             A.row_pitch = kPmK; A.plane_stride = (long)R * kPmK; A.batch_stride = (long)2 * R * kPmK;
-            Bp.base = (const __nv_bfloat16*)c->posedirs_planes; Bp.cols = kOffLd; Bp.rows = kPmK; Bp.planes = 2; Bp.batches = 1;
+            Bp.base = (const __nv_bfloat16*)bd; Bp.cols = kOffLd; Bp.rows = kPmK; Bp.planes = 2; Bp.batches = 1;
             Bp.row_pitch = kOffLd; Bp.plane_stride = (long)kPmK * kOffLd; Bp.batch_stride = (long)2 * kPmK * kOffLd;
             tc::GemmShape g{R, kOffLd, kPmK, 1, 1, 1, 1};
             EpiPoseOffsets e{ws.poff};
-            MHE_TRY((tc::launch_tc_gemm<128, false, true, 3, true>(A, Bp, g, e, stream, "mano pose blend")));
-            poff = ws.poff;
-        }
+            MHE_TRY((tc::launch_tc_gemm<128, false, true, 3, true>(A, Bp, g, e, stream, "mano blend")));
+            if (!tc_skin) {   // skinning on the CUDA cores from the GEMM's vertices: the one-tile-per-CTA GEMM kernel's fixed cost per
+                // 128 x 128 tile makes the K = 16 skinning GEMM below no faster yet (measured 0.544 vs 0.536 ms/step)
+                if (R >= 512) mano_skin_fwd_kernel<8><<<dim3(cdiv(kV, 128), cdiv(R, 8)), 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, ws.poff);
+                else mano_skin_fwd_kernel<2><<<dim3(cdiv(kV, 128), cdiv(R, 2)), 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, ws.poff);
+                MHE_TRY(check_launch("mano skin fwd"));
+            } else {
+            tc::PlaneTensor Wt, Tr;
+            Wt.base = (const __nv_bfloat16*)wp; Wt.cols = 64; Wt.rows = kVp; Wt.planes = 2; Wt.batches = 1;
+            Wt.row_pitch = 64; Wt.plane_stride = (long)kVp * 64; Wt.batch_stride = (long)2 * kVp * 64;
+            Tr.base = (const __nv_bfloat16*)ws.lbsb; Tr.cols = 64; Tr.rows = R * kLbsN; Tr.planes = 2; Tr.batches = 1;
+            Tr.row_pitch = 64; Tr.plane_stride = (long)R * kLbsN * 64; Tr.batch_stride = (long)2 * R * kLbsN * 64;
+            tc::GemmShape gs{kV, R * kLbsN, 64, 1, 1, 1, 1};
+            EpiSkin es{ws.poff, ws.cen, verts, jtr, R, joint_order};
+            MHE_TRY((tc::launch_tc_gemm<128, false, false, 3, true>(Wt, Tr, gs, es, stream, "mano skinning")));
+            }
+        } else
         if (R >= 512) {
             dim3 grid(cdiv(kV, 128), cdiv(R, 8));
-            mano_skin_fwd_kernel<8><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, poff);
+            mano_skin_fwd_kernel<8><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, nullptr);
+            MHE_TRY(check_launch("mano skin fwd"));
         } else {
             dim3 grid(cdiv(kV, 128), cdiv(R, 2));
-            mano_skin_fwd_kernel<2><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, poff);
+            mano_skin_fwd_kernel<2><<<grid, 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, nullptr);
+            MHE_TRY(check_launch("mano skin fwd"));
         }
-        MHE_TRY(check_launch("mano skin fwd"));
         if (joints2) {
             mano_joints2_fwd_kernel<<<R, 256, 0, stream>>>(*c, verts, R, joint_order, joints2);
             MHE_TRY(check_launch("mano joints2 fwd"));
