@@ -317,7 +317,9 @@ def run_ours(args):
         if fused:
             ms_f, n_f = probe(b'fused flow fwd')
             ms_b, n_b = probe(b'fused flow bwd')
-        else:
+            if n_f == 0 or n_b == 0:     # row count above the cluster-fused path (MHE_FUSED_MAX_ROWS): the per-GEMM tensor-core path ran
+                fused = False
+        if not fused:
             ms_f, n_f = probe(b'flow G1')
             ms_b, n_b = probe(b'dgrad G1')
         L.mhe_probe_configure(None, 0)
@@ -325,7 +327,9 @@ def run_ours(args):
         # a pass may be cut into several launches of the same kernel (chunks of consecutive layers): FLOPs per launch scale with it
         lpp_f, lpp_b = max(n_f, 1) / PROBE_RUNS, max(n_b, 1) / PROBE_RUNS
         us_f, us_b = ms_f / max(n_f, 1) * 1e3, ms_b / max(n_b, 1) * 1e3
-        ach_f, ach_b = flop_pass / lpp_f / (us_f * 1e-6) / 1e12, flop_pass / lpp_b / (us_b * 1e-6) / 1e12
+        # (fused: FLOW_PASS_FLOP covers a whole pass = lpp launches; per-GEMM path: flop_pass already is ONE G1 launch of both nets)
+        fl_f, fl_b = (flop_pass / lpp_f, flop_pass / lpp_b) if fused else (flop_pass, flop_pass)
+        ach_f, ach_b = fl_f / max(us_f, 1e-9) * 1e6 / 1e12, fl_b / max(us_b, 1e-9) * 1e6 / 1e12
         step_us = total_ms / args.steps * 1e3
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'r1_fused_bwd_traffic.json')
@@ -334,11 +338,12 @@ def run_ours(args):
                 traffic = json.load(fh).get('dram_bytes_per_launch')
         roof = {'bound': 'tensor',
                 'kernel': ('flow_bwd_fused_kernel (cluster-fused data-gradient pass over all 12 coupling layers: tcgen05 split-bf16x3, TMA '
-                           'weight ring, DSMEM exchanges)' if fused else 'sgemm_kernel (fp32 CUDA cores), dgrad G1'),
+                           'weight ring, DSMEM exchanges)' if fused else ('tc_gemm_kernel (tcgen05 split precision), dgrad G1 of one layer' if args.precision == 'bf16x3'
+                                                             else 'sgemm_kernel (fp32 CUDA cores), dgrad G1')),
                 'achieved': ach_b, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': ach_b / peaks['bf16_tflops_sustained'],
                 'traffic': traffic, 'peak_source': f'{peaks["source"]} bf16 dense sustained',
                 'launches_timed': n_b, 'avg_launch_us': us_b, 'launches_per_step': lpp_b, 'share_of_step': us_b * lpp_b / step_us,
-                'algorithmic_flop_per_launch': flop_pass / lpp_b,
+                'algorithmic_flop_per_launch': fl_b,
                 'second_kernel': {'kernel': 'flow_fwd_fused_kernel (cluster-fused sampling pass, same mapping)' if fused else 'flow G1',
                                   'achieved': ach_f, 'frac': ach_f / peaks['bf16_tflops_sustained'], 'avg_launch_us': us_f,
                                   'launches_per_step': lpp_f, 'share_of_step': us_f * lpp_f / step_us, 'launches_timed': n_f},

@@ -8,6 +8,10 @@
 #include <vector>
 #include "tc_gemm.cuh"
 
+#ifndef MHE_TC_PERSISTENT_DEFAULT
+#define MHE_TC_PERSISTENT_DEFAULT "1"
+#endif
+
 namespace mhe {
 namespace tc {
 
@@ -91,6 +95,25 @@ const CUtensorMap* cached_map_f32(const float* base, int cols, int rows, int bat
     cache.emplace(key, map);
     *status = MHE_OK;
     return map;
+}
+
+// MHE_TC_PERSISTENT: unset / "0" = one tile per CTA everywhere; "1" = persistent kernel everywhere; otherwise a comma-separated list of
+// launch-label substrings that take the persistent kernel
+bool tc_persistent_enabled(const char* what) {
+    static std::string spec;
+    static bool parsed = false;
+    if (!parsed) { parsed = true; if (const char* e = getenv("MHE_TC_PERSISTENT")) spec = e; else spec = MHE_TC_PERSISTENT_DEFAULT; }
+    if (spec.empty() || spec == "0") return false;
+    if (spec == "1") return true;
+    size_t pos = 0;
+    while (pos < spec.size()) {
+        size_t end = spec.find(',', pos);
+        if (end == std::string::npos) end = spec.size();
+        const std::string item = spec.substr(pos, end - pos);
+        if (!item.empty() && what && strstr(what, item.c_str())) return true;
+        pos = end + 1;
+    }
+    return false;
 }
 
 int stages_for(const char* what, int requested, int max_stages) {

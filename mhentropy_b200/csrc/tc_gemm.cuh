@@ -85,6 +85,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -328,6 +329,191 @@ const CUtensorMap* cached_map_f32(const float* base, int cols, int rows, int bat
 // ring depth of a launch: the caller's choice, overridden by MHE_TC_STAGES="label=n,label=n" (substring match on the launch label)
 int stages_for(const char* what, int requested, int max_stages);
 
+// Persistent variant: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (N tiles fastest), the operand ring keeps running
+// across tiles, and the accumulator is DOUBLE-BUFFERED in TMEM: the epilogue of tile i (TMEM -> registers -> global) overlaps the loads
+// and MMAs of tile i + 1.  Short contractions with large outputs (K = 64 weight gradients, the MANO skinning / blend GEMMs) are
+// dominated by the per-CTA fixed cost (barrier init, TMEM allocation, first TMA round trip, epilogue drain) in the one-tile kernel.
+template <int BN, bool A_MN, bool B_MN, int NPAIR, bool F16, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi,
+                          int tiles_n, int tiles_m, int tiles_total) {
+    constexpr int NPL = NPAIR == 1 ? 1 : 2;
+    using Plan = SmemPlan<BN, NPL>;
+    constexpr int NSmax = Plan::kStages;
+    const int NS = g.stages;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[NSmax], bar_empty[NSmax], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_stage[Epi::kStaged ? 4 : 1][32][33];
+
+    pdl_launch_dependents();
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_total = (g.K + BK - 1) / BK;
+    const int kb_per = (kb_total + g.ksplit - 1) / g.ksplit;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+    pdl_wait();
+
+    auto stage_a = [&](int s, int p) { return smem0 + s * Plan::kStageBytes + p * Plan::kABytes; };
+    auto stage_b = [&](int s, int p) { return smem0 + s * Plan::kStageBytes + NPL * Plan::kABytes + p * Plan::kBBytes; };
+    // tile -> (n0, m0, batch, split, k-block range); every role walks the same sequence
+    struct Tile { int n0, m0, batch, split, kb_begin, nkb1, nkb; };
+    auto tile_of = [&](int t) {
+        Tile T;
+        T.n0 = (t % tiles_n) * BN;
+        T.m0 = ((t / tiles_n) % tiles_m) * BM;
+        const int z = t / (tiles_n * tiles_m);
+        T.batch = z / g.ksplit; T.split = z % g.ksplit;
+        T.kb_begin = T.split * kb_per;
+        const int kb_end = min(kb_total, T.kb_begin + kb_per);
+        T.nkb1 = max(kb_end - T.kb_begin, 0);
+        T.nkb = T.nkb1 * g.kfold;
+        return T;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+                const Tile T = tile_of(t);
+                for (int i = 0; i < T.nkb; ++i, ++q) {
+                    const int s = q % NS;
+                    mbar_wait(smem_u32(&bar_empty[s]), ((q / NS) & 1) ^ 1);
+                    const uint32_t full = smem_u32(&bar_full[s]);
+                    mbar_expect_tx(full, Plan::kStageBytes);
+                    const int k0 = (T.kb_begin + i % T.nkb1) * BK;
+                    const int bsrc = T.batch * g.kfold + i / T.nkb1;
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) {
+                        if (!A_MN) tma_load_4d(stage_a(s, p), &mapA, full, k0, T.m0, p, bsrc * g.a_batch_mul);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, &mapA, full, T.m0 + 64 * j, k0, p, bsrc * g.a_batch_mul);
+                        }
+                        if (!B_MN) tma_load_4d(stage_b(s, p), &mapB, full, k0, T.n0, p, bsrc * g.b_batch_mul);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, &mapB, full, T.n0 + 64 * j, k0, p, bsrc * g.b_batch_mul);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(BN, A_MN, B_MN, F16, F16);
+            constexpr uint32_t kHi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+            constexpr uint32_t kLoA = A_MN ? ((8192u >> 4) << 16) : ((16u >> 4) << 16);
+            constexpr uint32_t kLoB = B_MN ? ((8192u >> 4) << 16) : ((16u >> 4) << 16);
+            constexpr uint32_t kStepA = A_MN ? (2048u >> 4) : (32u >> 4);
+            constexpr uint32_t kStepB = B_MN ? (2048u >> 4) : (32u >> 4);
+            uint32_t q = 0, tl = 0;
+            for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++tl) {
+                const Tile T = tile_of(t);
+                const uint32_t buf = tl & 1;
+                mbar_wait(smem_u32(&bar_acc_empty[buf]), ((tl >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_d + buf * BN;
+                uint32_t accumulate = 0;
+                for (int i = 0; i < T.nkb; ++i, ++q) {
+                    const int s = q % NS;
+                    mbar_wait(smem_u32(&bar_full[s]), (q / NS) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_lo0 = kLoA | (stage_a(s, 0) >> 4), b_lo0 = kLoB | (stage_b(s, 0) >> 4);
+#pragma unroll
+                    for (int pr = 0; pr < NPAIR; ++pr) {
+                        const uint32_t a_lo = a_lo0 + ((pr == 2) ? (uint32_t)(Plan::kABytes >> 4) : 0u);
+                        const uint32_t b_lo = b_lo0 + ((pr == 1) ? (uint32_t)(Plan::kBBytes >> 4) : 0u);
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                            umma_bf16_lohi(acc, a_lo + ks * kStepA, b_lo + ks * kStepB, kHi, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    tcgen05_commit(smem_u32(&bar_empty[s]));
+                }
+                tcgen05_commit(smem_u32(&bar_acc_full[buf]));
+            }
+        }
+    } else {
+        const int qd = warp & 3;
+        uint32_t tl = 0;
+        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++tl) {
+            const Tile T = tile_of(t);
+            const uint32_t buf = tl & 1;
+            const int row = T.m0 + qd * 32 + lane;
+            mbar_wait(smem_u32(&bar_acc_full[buf]), (tl >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t acc = tmem_d + buf * BN + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(acc + c0, v);
+                if (c0 + 32 >= BN) {   // last chunk read: hand the accumulator back before the (long) global stores of this chunk
+                    tcgen05_fence_before();
+                    mbar_arrive_cta(smem_u32(&bar_acc_empty[buf]));
+                }
+                if (T.n0 + c0 >= g.N) continue;
+                if constexpr (Epi::kDirect) {
+                    if (row < g.M) epi(T.batch, T.split, row, T.n0 + c0, v, g);
+                }
+                if constexpr (Epi::kStaged) {
+                    float (*st)[33] = s_stage[warp - 2];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) st[lane][j] = v[j];
+                    __syncwarp();
+                    const int col = T.n0 + c0 + lane;
+                    const int rows = min(32, g.M - (T.m0 + qd * 32));
+                    if constexpr (Epi::kRmw) {
+                        long stride;
+                        float* p0 = epi.rmw_ptr(T.batch, T.m0 + qd * 32, col, stride);
+                        if (p0 && rows > 0) {
+                            if (epi.atomic) {
+                                for (int rr = 0; rr < rows; ++rr) atomicAdd(p0 + rr * stride, st[rr][lane]);
+                            } else if (epi.overwrite) {
+#pragma unroll
+                                for (int rr = 0; rr < 32; ++rr) if (rr < rows) p0[rr * stride] = st[rr][lane];
+                            } else {
+                                float old[32];
+#pragma unroll
+                                for (int rr = 0; rr < 32; ++rr) old[rr] = rr < rows ? p0[rr * stride] : 0.f;
+#pragma unroll
+                                for (int rr = 0; rr < 32; ++rr) if (rr < rows) p0[rr * stride] = old[rr] + st[rr][lane];
+                            }
+                        }
+                    } else {
+                        if (col < g.N)
+                            for (int rr = 0; rr < rows; ++rr) epi.elem(T.batch, T.split, T.m0 + qd * 32 + rr, col, st[rr][lane], g);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(2 * BN) : "memory");
+    }
+}
+
+bool tc_persistent_enabled(const char* what);
+
 // launch helper: builds (cached) tensor maps and launches.  A: rows = M (K-major) or K (MN-major), etc.
 const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status);
 
@@ -359,6 +545,29 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
         if (gs.stages > kb_per) gs.stages = kb_per > 0 ? kb_per : 1;
     }
     const size_t smem = (size_t)gs.stages * Plan::kStageBytes + 1024;
+    const int kb_check = cdiv(g.K, BK);
+    const int tiles_total = (int)(grid.x * grid.y * grid.z);
+    if (tc_persistent_enabled(what) && g.K > 0 && tiles_total > 0 && (g.ksplit == 1 || kb_check % g.ksplit == 0)) {   // (no empty k-ranges)
+        auto pkern = tc_gemm_persistent_kernel<BN, A_MN, B_MN, NPAIR, F16, Epi>;
+        static bool pattr_set = false;
+        if (!pattr_set) {
+            if (cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kBytes) != cudaSuccess) {
+                set_error("%s: cannot raise dynamic shared memory to %d", what, Plan::kBytes);
+                return MHE_ERR_CUDA;
+            }
+            pattr_set = true;
+        }
+        // CTAs per SM: shared memory (the ring) and TMEM (2 x BN of 512 columns per CTA)
+        int per_sm = (int)((220 * 1024) / (smem + 4096));
+        if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
+        if (per_sm < 1) per_sm = 1;
+        const int nctas = tiles_total < 148 * per_sm ? tiles_total : 148 * per_sm;
+        if (launch_chain(pkern, dim3(nctas), dim3(kThreads), smem, stream, *ma, *mb, gs, epi, (int)grid.x, (int)grid.y, tiles_total) != cudaSuccess) {
+            set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+            return MHE_ERR_CUDA;
+        }
+        return check_launch(what);
+    }
     if (launch_chain(kern, grid, dim3(kThreads), smem, stream, *ma, *mb, gs, epi) != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
         return MHE_ERR_CUDA;
