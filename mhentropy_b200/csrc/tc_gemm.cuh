@@ -26,6 +26,7 @@ constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kThreadsP = 320; // persistent kernel: eight epilogue warps (2-9), two per TMEM lane quadrant
 
 // ---- host: tensor maps ----------------------------------------------------------------------------
 struct PlaneTensor {          // [batches][planes][rows][cols] bf16, element strides
@@ -334,7 +335,7 @@ int stages_for(const char* what, int requested, int max_stages);
 // and MMAs of tile i + 1.  Short contractions with large outputs (K = 64 weight gradients, the MANO skinning / blend GEMMs) are
 // dominated by the per-CTA fixed cost (barrier init, TMEM allocation, first TMA round trip, epilogue drain) in the one-tile kernel.
 template <int BN, bool A_MN, bool B_MN, int NPAIR, bool F16, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsP, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi,
                           int tiles_n, int tiles_m, int tiles_total) {
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
@@ -344,7 +345,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[NSmax], bar_empty[NSmax], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_stage[Epi::kStaged ? 4 : 1][32][33];
+    __shared__ float s_stage[Epi::kStaged ? 8 : 1][32][33];     // one transpose buffer per epilogue warp
 
     pdl_launch_dependents();
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -354,7 +355,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -451,7 +452,9 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             }
         }
     } else {
-        const int qd = warp & 3;
+        // eight epilogue warps: TMEM lane quadrant = warp id % 4 (hardware rule), column half = the warp's group of four
+        const int qd = warp & 3, half = (warp - 2) >> 2;
+        constexpr int kCols = BN / 2;
         uint32_t tl = 0;
         for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++tl) {
             const Tile T = tile_of(t);
@@ -461,10 +464,10 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             tcgen05_fence_after();
             const uint32_t acc = tmem_d + buf * BN + ((uint32_t)(qd * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * kCols; c0 < (half + 1) * kCols; c0 += 32) {
                 float v[32];
                 tmem_ld32(acc + c0, v);
-                if (c0 + 32 >= BN) {   // last chunk read: hand the accumulator back before the (long) global stores of this chunk
+                if (c0 + 32 >= (half + 1) * kCols) {   // last chunk read: hand the accumulator back before the (long) global stores of this chunk
                     tcgen05_fence_before();
                     mbar_arrive_cta(smem_u32(&bar_acc_empty[buf]));
                 }
@@ -562,7 +565,7 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
         if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
         if (per_sm < 1) per_sm = 1;
         const int nctas = tiles_total < 148 * per_sm ? tiles_total : 148 * per_sm;
-        if (launch_chain(pkern, dim3(nctas), dim3(kThreads), smem, stream, *ma, *mb, gs, epi, (int)grid.x, (int)grid.y, tiles_total) != cudaSuccess) {
+        if (launch_chain(pkern, dim3(nctas), dim3(kThreadsP), smem, stream, *ma, *mb, gs, epi, (int)grid.x, (int)grid.y, tiles_total) != cudaSuccess) {
             set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
             return MHE_ERR_CUDA;
         }
