@@ -237,16 +237,31 @@ __global__ void __launch_bounds__(256) coupling_bwd_kernel(const float* __restri
     }
 }
 
-// half planes -> bfloat16 planes of the same values (for the backward GEMMs): n elements per plane, batches of [2 planes][n]
-__global__ void replane_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long n, int batches) {
+// half planes -> bfloat16 planes of the same values (for the backward GEMMs): n elements per plane (a multiple of 8), batches of
+// [2 planes][n]; 8 values per thread, 16-byte loads and stores
+__global__ void __launch_bounds__(256) replane_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long n, int batches) {
     pdl_launch_dependents();
     pdl_wait();
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * batches) return;
-    const long b = i / n, k = i % n;
-    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + b * 2 * n;
-    const float v = from16<true>(s16[k]) + from16<true>(s16[n + k]);
-    put_planes<false>(dst + b * 2 * n + k, n, v);
+    const long i8 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i8 >= n * batches) return;
+    const long b = i8 / n, k = i8 % n;
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + b * 2 * n + k;
+    uint16_t* d16 = reinterpret_cast<uint16_t*>(dst) + b * 2 * n + k;
+    const uint4 h4 = *reinterpret_cast<const uint4*>(s16), l4 = *reinterpret_cast<const uint4*>(s16 + n);
+    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[q])), c = __half22float2(*reinterpret_cast<const __half2*>(&lw[q]));
+        const float v0 = a.x + c.x, v1 = a.y + c.y;
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+        const float2 hf = __bfloat1622float2(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+        oh[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        ol[q] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(d16) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(d16 + n) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
 }
 
 // grid (cp_ld / 256, 8): block row y sums images y, y + 8, ... and adds its share (the slots accumulate anyway)
@@ -589,11 +604,11 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
             MHE_TRY((gemm<false, true, false>(dh0, w0, s, e, stream, "tc dgrad G0")));
         }
         // the saved activations are half planes; the side streams re-plane them to bfloat16 for their GEMMs
-        replane_kernel<<<cdiv((int)(2 * RH), 256), 256, 0, wstream>>>(S.a0(step), ws.a0b, RH, 2);
+        replane_kernel<<<cdiv((int)(2 * RH / 8), 256), 256, 0, wstream>>>(S.a0(step), ws.a0b, RH, 2);
         MHE_TRY(check_launch("replane a0"));
-        replane_kernel<<<cdiv((int)(2 * RH), 256), 256, 0, wstream2>>>(S.a1(step), ws.a1b, RH, 2);
+        replane_kernel<<<cdiv((int)(2 * RH / 8), 256), 256, 0, wstream2>>>(S.a1(step), ws.a1b, RH, 2);
         MHE_TRY(check_launch("replane a1"));
-        replane_kernel<<<cdiv((int)RD, 256), 256, 0, wstream2>>>(S.xm(step), ws.xmb, RD, 1);
+        replane_kernel<<<cdiv((int)(RD / 8), 256), 256, 0, wstream2>>>(S.xm(step), ws.xmb, RD, 1);
         MHE_TRY(check_launch("replane xm"));
         {   // dW1 [out][in] += dh1^T a0
             GemmShape s{L.H, L.H, R, 2, ks, 1, 1};
