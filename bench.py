@@ -206,12 +206,12 @@ def run_ours(args):
     ar_inside = world > 1 and bool(os.environ.get('MHE_BENCH_ALLREDUCE_INSIDE'))
 
     def allreduce(engine):
-        if world > 1 and not engine.allreduce:
-            dist.all_reduce(engine.dflat)
-            dist.all_reduce(engine.loss)
+        if world > 1:
+            engine.exchange_gradients()      # factored exchange (MHE_BENCH_DENSE_ALLREDUCE=1: one dense all-reduce of the 80 MB)
 
     # ---------------- value: inputs resident in HBM, fused engine (CUDA graph) ----------------
-    eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=not args.no_graph, allreduce=ar_inside)
+    eng = TrainStep(head, B, S, dev, want_verts=True, use_graph=not args.no_graph, allreduce=ar_inside,
+                    factored_exchange=world > 1 and not os.environ.get('MHE_BENCH_DENSE_ALLREDUCE'))
     eng.load(**devb)
     for _ in range(max(args.warmup, 3)):
         flush.zero_()

@@ -131,6 +131,14 @@ int mhe_flow_pass_cond_bwd(mhe_flow_shape s, const float* params, const void* pa
                            float* din, float* dparams, float* dcp, const float* feat, float* dfeat,
                            void* workspace, size_t workspace_bytes, void* cond_workspace, size_t cond_workspace_bytes, void* stream);
 
+/* The conditioning weight gradient alone, from its two factors: dparams Cw slots (+)= dcp[:, idx, :]^T feat over Bt rows (tensor-core
+ * path; workspace of mhe_flow_cond_workspace_bytes(s, Bt)).  It is the same contraction mhe_flow_cond_bwd runs with the local batch.
+ * Data parallelism: this gradient has rank <= (images) per weight matrix, so the ranks exchange the FACTORS (all-gather of dcp
+ * [B][L*4*H] and feat [B][C]: 6.4 MB per rank at 64 images) and each computes the global gradient with Bt = world x B, instead of
+ * all-reducing the dense 50 MB; the remaining 30 MB of the flat gradient are all-reduced as before.                               */
+int mhe_flow_cond_wgrad(mhe_flow_shape s, const float* feat, const float* dcp, int Bt, float* dparams, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* Bucketed gradient exchange.  On the fused tensor-core path the backward pass runs as mhe_flow_bwd_chunk_count() chunks of consecutive
  * layers (1 on the other paths), chunk 0 first (it holds the layers the backward reaches first); mhe_flow_bwd_chunk_layers() gives
  * chunk c's layers.  After an asynchronous mhe_flow_pass_cond_bwd (mhe_flow_set_async bit 0), mhe_flow_join_chunk(stream, c) makes
@@ -158,6 +166,8 @@ int mhe_flow_zero_bias_grads(mhe_flow_shape s, float* dparams, void* stream);
  *          captured graph ends.
  *   bit 1  the caller promises that the WEIGHT slots of dparams (W0, W1, W2, Cw) are zero when mhe_flow_pass_bwd /
  *          mhe_flow_cond_bwd run: their epilogues then store instead of read-modify-write (bias slots always accumulate).
+ *   bit 4  mhe_flow_cond_bwd skips the conditioning WEIGHT gradient (Cw slots): the caller computes it with mhe_flow_cond_wgrad, e.g.
+ *          from factors gathered over the data-parallel ranks (tensor-core path only).
  *   bit 3  the caller has run mhe_flow_pass_bwd_prepare on the same saved block / workspace and ordered it before mhe_flow_pass_bwd.
  *   bit 2  the caller promises that dfeat is zero when mhe_flow_cond_bwd runs on the tensor-core path (it is accumulated into with
  *          atomics there): the memset that would otherwise sit on the critical path is skipped.                                 */

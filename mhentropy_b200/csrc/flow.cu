@@ -422,6 +422,16 @@ int mhe_flow_pass_cond_bwd(mhe_flow_shape s, const float* params, const void* pa
     return mhe_flow_cond_bwd(s, params, packed, feat, dcp, B, dparams, dfeat, cond_workspace, cond_workspace_bytes, stream_);
 }
 
+int mhe_flow_cond_wgrad(mhe_flow_shape s, const float* feat, const float* dcp, int Bt, float* dparams, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    MHE_REQUIRE(valid_shape(s) && feat && dcp && dparams && workspace && Bt >= 0, "cond_wgrad: bad args");
+    if (Bt == 0) return MHE_OK;
+    FlowLayout L(s);
+    if (!tcflow::supported(L)) { set_error("cond_wgrad: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
+    if (workspace_bytes < tcflow::cond_ws_bytes(L, Bt)) { set_error("cond_wgrad: workspace too small"); return MHE_ERR_WORKSPACE; }
+    return tcflow::cond_wgrad(L, feat, dcp, Bt, dparams, workspace, (cudaStream_t)stream);
+}
+
 int mhe_flow_bwd_chunk_count(mhe_flow_shape s, int R) {
     if (!valid_shape(s)) return 1;
     FlowLayout L(s);
@@ -547,6 +557,7 @@ int mhe_flow_set_async(int on) {
     tcflow::set_grads_are_zero((on >> 1) & 1);
     tcflow::set_dfeat_is_zero((on >> 2) & 1);
     fused::set_wgrad_operands_prepared((on >> 3) & 1);
+    tcflow::set_skip_cond_wgrad((on >> 4) & 1);
     return MHE_OK;
 }
 int mhe_flow_join(void* stream) { return fused::join((cudaStream_t)stream); }

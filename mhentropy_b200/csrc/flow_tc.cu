@@ -316,7 +316,8 @@ int zero_bias_grads(const FlowLayout& L, float* dparams, cudaStream_t stream) {
     return check_launch("zero bias grads");
 }
 
-static int g_grads_zero = 0, g_dfeat_zero = 0;
+static int g_grads_zero = 0, g_dfeat_zero = 0, g_skip_cond_wgrad = 0;
+void set_skip_cond_wgrad(int on) { g_skip_cond_wgrad = on; }
 void set_grads_are_zero(int on) { g_grads_zero = on; }
 bool grads_are_zero() { return g_grads_zero != 0; }
 void set_dfeat_is_zero(int on) { g_dfeat_zero = on; }
@@ -416,7 +417,7 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         MHE_TRY(check_launch("cond bias grad"));
         if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[1][0], bstream), "join cond bias grad"));
     }
-    {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat      (A MN-major: cols = h, rows = b; B MN-major: cols = c, rows = b)
+    if (!g_skip_cond_wgrad) {   // dCw[idx] [H][C] += dcp[:, idx, :]^T feat      (A MN-major: cols = h, rows = b; B MN-major: cols = c, rows = b)
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
@@ -441,6 +442,22 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         MHE_TRY(cuda_ok(cudaStreamWaitEvent(stream, aux.done[1][0], 0), "join cond bias grad"));
     }
     return MHE_OK;
+}
+
+// The conditioning weight gradient alone, from its two factors: dCw[idx] (+)= dcp[:, idx, :]^T feat over Bt rows.  Data parallelism uses
+// it with the factors GATHERED from all ranks (Bt = world x B): the gradient of the 50 MB of conditioning weights has rank <= Bt per
+// (layer, net, j), so exchanging dcp (B x L*4*H) and feat (B x C) is far less traffic than all-reducing the dense gradient.
+int cond_wgrad(const FlowLayout& L, const float* feat, const float* dcp, int Bt, float* dparams, void* ws_, cudaStream_t stream) {
+    const long cp_ld = (long)L.L * 4 * L.H;
+    bf16* featp = (bf16*)ws_;
+    bf16* dcpp = featp + (((size_t)2 * Bt * L.C + 511) / 512) * 512;
+    MHE_TRY(split_planes(feat, L.C, 0, Bt, L.C, nullptr, featp, Bt, L.C, 2, 1, false, stream));
+    MHE_TRY(split_planes(dcp, cp_ld, 0, Bt, (int)cp_ld, nullptr, dcpp, Bt, (int)cp_ld, 2, 1, false, stream));
+    PlaneTensor A = pt(dcpp, L.H, Bt, cp_ld, (long)Bt * cp_ld, L.L * 4, L.H);
+    PlaneTensor Bt_ = pt(featp, L.C, Bt, L.C, (long)Bt * L.C, 1, 0);
+    GemmShape g{L.H, L.C, Bt, L.L * 4, 1, 1, 0};
+    EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
+    return gemm<true, true, false>(A, Bt_, g, e, stream, "tc cond wgrad");
 }
 
 // ---- conditioning backward by layer range (the chunked fused pass pipelines it behind each chunk's dcp sums) ----------------

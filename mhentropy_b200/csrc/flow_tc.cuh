@@ -90,6 +90,8 @@ inline size_t cond_ws_bytes(const FlowLayout& L, int B) {
 bool cond_direct_supported(const FlowLayout& L, int B);
 int cond_fwd_direct(const FlowLayout& L, const float* params, const float* feat, int B, float* cp, void* ws, cudaStream_t stream);
 int zero_bias_grads(const FlowLayout& L, float* dparams, cudaStream_t stream);
+void set_skip_cond_wgrad(int on);
+int cond_wgrad(const FlowLayout& L, const float* feat, const float* dcp, int Bt, float* dparams, void* ws, cudaStream_t stream);
 int cond_bwd_feat_planes(const FlowLayout& L, const float* feat, int B, void* ws, cudaStream_t stream);
 int cond_bwd_dcp_planes(const FlowLayout& L, const float* dcp, int B, void* ws, int l0, int nl, cudaStream_t stream);
 int cond_bwd_layers(const FlowLayout& L, const void* packed, const float* dcp, int B, float* dparams, float* dfeat, void* ws, int l0, int nl,

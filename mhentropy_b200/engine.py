@@ -20,7 +20,8 @@ from .losses import MHEntHead
 
 class TrainStep:
     def __init__(self, head: MHEntHead, B: int, S: int, device, want_verts: bool = True, use_graph: bool = True,
-                 prepare_ahead: bool = False, pipelined_cond_bwd: bool = False, allreduce_group=None, allreduce: bool = False):
+                 prepare_ahead: bool = False, pipelined_cond_bwd: bool = False, allreduce_group=None, allreduce: bool = False,
+                 factored_exchange: bool = False):
         self.head, self.B, self.S, self.R = head, B, S, B * S
         self.dev = torch.device(device)
         flow = head.q_z_giv_i
@@ -79,6 +80,18 @@ class TrainStep:
         if self.allreduce:
             self.pipelined_cond_bwd = self.tc
             self.comm = torch.cuda.Stream(self.dev)
+        # data parallelism, the default exchange (exchange_gradients(), after the step): the conditioning weight gradient (50 of the 80 MB)
+        # has rank <= images per weight matrix, so the ranks all-gather its FACTORS (dcp, feat: 6.4 MB per rank) and each computes the
+        # global gradient with mhe_flow_cond_wgrad; only the other 30 MB are all-reduced.  The step itself then skips that GEMM.
+        self.factored_exchange = bool(factored_exchange) and self.tc and not self.allreduce and torch.distributed.is_available() \
+            and torch.distributed.is_initialized() and torch.distributed.get_world_size(allreduce_group) > 1
+        if self.factored_exchange:
+            world = torch.distributed.get_world_size(allreduce_group)
+            self.comm = torch.cuda.Stream(self.dev)
+            self.dcp_all = torch.empty(world * B, cpf, device=dev)
+            self.feat_all = torch.empty(world * B, flow.cond_dim, device=dev)
+            self.xws_bytes = L.mhe_flow_cond_workspace_bytes(self.shape, world * B)
+            self.xws = torch.empty(self.xws_bytes, dtype=torch.uint8, device=dev)
         self.launches_per_step = None
 
     # ------------------------------------------------------------------
@@ -161,7 +174,7 @@ class TrainStep:
         #  bit 2: so was dfeat)
         if self.tc and self.prepare_ahead:
             torch.cuda.current_stream(self.dev).wait_stream(self.side5)
-        check(L.mhe_flow_set_async((7 if self.tc else 3) | (8 if self.prepared else 0)), 'set_async')
+        check(L.mhe_flow_set_async((7 if self.tc else 3) | (8 if self.prepared else 0) | (16 if self.factored_exchange else 0)), 'set_async')
         try:
             if self.tc and self.pipelined_cond_bwd:
                 # ONE call: the conditioning backward is pipelined into the chunked pass
@@ -181,6 +194,47 @@ class TrainStep:
         if self.verts is not None:
             torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
         torch.cuda.current_stream(self.dev).wait_stream(self.side4)    # ... and the loss reductions
+
+    def exchange_gradients(self):
+        """Data-parallel gradient exchange after run() (sum over the ranks, like one all-reduce of dflat and loss): all-gather of the
+        conditioning factors + local mhe_flow_cond_wgrad for the conditioning weights, all-reduce of the rest."""
+        import torch.distributed as dist
+        L, shape, grp = lib(), self.shape, self.allreduce_group
+        if not self.factored_exchange:
+            if dist.is_initialized() and dist.get_world_size(grp) > 1 and not self.allreduce:
+                dist.all_reduce(self.dflat, group=grp)
+                dist.all_reduce(self.loss, group=grp)
+            return
+        main = torch.cuda.current_stream(self.dev)
+        cw0, cw1 = L.mhe_flow_param_offset(shape, 0, 0, 6), L.mhe_flow_param_offset(shape, 0, 0, 7)
+        # factors first (small), then the dense remainder on the communication stream while the GEMM below runs
+        # (grouped NCCL launches: one for the two gathers, one for the three reductions - each separate call costs ~15-20 us)
+        coalesce = not os.environ.get('MHE_ENGINE_NO_COALESCE')
+        if coalesce:
+            with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
+                dist.all_gather_into_tensor(self.dcp_all, self.dcp, group=grp)
+                dist.all_gather_into_tensor(self.feat_all, self.feat, group=grp)
+        else:
+            dist.all_gather_into_tensor(self.dcp_all, self.dcp, group=grp)
+            dist.all_gather_into_tensor(self.feat_all, self.feat, group=grp)
+        self.comm.wait_stream(main)
+        with torch.cuda.stream(self.comm):
+            if coalesce:
+                with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
+                    dist.all_reduce(self.dflat[:cw0], group=grp)
+                    dist.all_reduce(self.dflat[cw1:], group=grp)
+                    dist.all_reduce(self.loss, group=grp)
+            else:
+                dist.all_reduce(self.dflat[:cw0], group=grp)
+                dist.all_reduce(self.dflat[cw1:], group=grp)
+                dist.all_reduce(self.loss, group=grp)
+        check(L.mhe_flow_set_async(2), 'set_async')          # the Cw slots are overwritten (they were never written this step)
+        try:
+            check(L.mhe_flow_cond_wgrad(shape, ptr(self.feat_all), ptr(self.dcp_all), self.dcp_all.shape[0], ptr(self.dflat), ptr(self.xws),
+                                        self.xws_bytes, _lib.stream_ptr(self.dev)), 'cond_wgrad')
+        finally:
+            check(L.mhe_flow_set_async(0), 'set_async')
+        main.wait_stream(self.comm)
 
     def _enqueue_allreduce(self, L, shape, R):
         """Bucketed sum-all-reduce on the communication stream: chunk c's gradient segments as soon as its layers are complete."""
