@@ -372,7 +372,9 @@ def run_ours(args):
             'dtype': 'f32 (bf16x3 split on tcgen05, fp32 accumulate)' if args.precision == 'bf16x3' else 'f32', 'data': 'synthetic',
             'config': {'workload': f'training step B={B} x S={S} hypotheses per GPU (BASELINE configs[1]): flow sample+log_prob, '
                                    'MANO (778-vertex mesh fwd), visible-2D + entropy loss, fwd+bwd'
-                                   + (', NCCL allreduce of the flat gradient' if world > 1 else ''),
+                                   + ((', gradient exchange: NCCL all-gather of the conditioning factors + local weight-gradient GEMM, '
+                                       'NCCL all-reduce of the other 30 MB' if eng.factored_exchange else ', NCCL allreduce of the flat gradient')
+                                      if world > 1 else ''),
                        'images_per_gpu': B, 'hypotheses': S, 'rows_per_gpu': R, 'l2': 'flushed (256 MiB write) before every timed step',
                        'launch': 'CUDA graph' if not args.no_graph else 'stream', 'parallelism': f'dp{world}'},
             'clocks': clocks.summary(),
