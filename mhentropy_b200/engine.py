@@ -21,7 +21,7 @@ from .losses import MHEntHead
 class TrainStep:
     def __init__(self, head: MHEntHead, B: int, S: int, device, want_verts: bool = True, use_graph: bool = True,
                  prepare_ahead: bool = False, pipelined_cond_bwd: bool = False, allreduce_group=None, allreduce: bool = False,
-                 factored_exchange: bool = False):
+                 factored_exchange: bool = False, exchange_in_graph: bool = False):
         self.head, self.B, self.S, self.R = head, B, S, B * S
         self.dev = torch.device(device)
         flow = head.q_z_giv_i
@@ -85,9 +85,14 @@ class TrainStep:
         # global gradient with mhe_flow_cond_wgrad; only the other 30 MB are all-reduced.  The step itself then skips that GEMM.
         self.factored_exchange = bool(factored_exchange) and self.tc and not self.allreduce and torch.distributed.is_available() \
             and torch.distributed.is_initialized() and torch.distributed.get_world_size(allreduce_group) > 1
+        # exchange_in_graph (EXPERIMENTAL, off): the factored exchange is enqueued inside the (captured) step, so the gather and the global
+        # conditioning GEMM run beside the last weight gradients instead of after the step - 0.638 vs 0.670 ms/step on 2 GPUs in bench.py, but
+        # tools/check_factored_exchange.py hung with it (two engines in one process); not the default until that is understood
+        self.exchange_in_graph = bool(exchange_in_graph or os.environ.get('MHE_ENGINE_EXCHANGE_IN_GRAPH')) and self.factored_exchange
         if self.factored_exchange:
             world = torch.distributed.get_world_size(allreduce_group)
             self.comm = torch.cuda.Stream(self.dev)
+            self.comm2 = torch.cuda.Stream(self.dev)
             self.dcp_all = torch.empty(world * B, cpf, device=dev)
             self.feat_all = torch.empty(world * B, flow.cond_dim, device=dev)
             self.xws_bytes = L.mhe_flow_cond_workspace_bytes(self.shape, world * B)
@@ -174,7 +179,8 @@ class TrainStep:
         #  bit 2: so was dfeat)
         if self.tc and self.prepare_ahead:
             torch.cuda.current_stream(self.dev).wait_stream(self.side5)
-        check(L.mhe_flow_set_async((7 if self.tc else 3) | (8 if self.prepared else 0) | (16 if self.factored_exchange else 0)), 'set_async')
+        flags = (7 if self.tc else 3) | (8 if self.prepared else 0) | (16 if self.factored_exchange else 0)
+        check(L.mhe_flow_set_async(flags), 'set_async')
         try:
             if self.tc and self.pipelined_cond_bwd:
                 # ONE call: the conditioning backward is pipelined into the chunked pass
@@ -184,6 +190,8 @@ class TrainStep:
             else:
                 check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
                                           ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(self.dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
+                if self.exchange_in_graph:      # dcp is complete here (stream order): gather the factors, global conditioning GEMM
+                    self._enqueue_factor_exchange(L, shape, flags)
                 check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), pk, ptr(self.feat), ptr(self.dcp), B, ptr(self.dflat), ptr(self.dfeat),
                                           cws, cwsb, s), 'cond_bwd')
         finally:
@@ -191,35 +199,44 @@ class TrainStep:
         if self.allreduce:
             self._enqueue_allreduce(L, shape, R)
         check(L.mhe_flow_join(s), 'flow_join')
+        if self.exchange_in_graph:              # every local gradient is complete: reduce the dense remainder
+            self._enqueue_dense_remainder(L, shape)
         if self.verts is not None:
             torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
         torch.cuda.current_stream(self.dev).wait_stream(self.side4)    # ... and the loss reductions
 
-    def exchange_gradients(self):
-        """Data-parallel gradient exchange after run() (sum over the ranks, like one all-reduce of dflat and loss): all-gather of the
-        conditioning factors + local mhe_flow_cond_wgrad for the conditioning weights, all-reduce of the rest."""
+    def _enqueue_factor_exchange(self, L, shape, flags):
+        """All-gather of the conditioning factors and the global conditioning weight gradient, on the communication stream."""
         import torch.distributed as dist
-        L, shape, grp = lib(), self.shape, self.allreduce_group
-        if not self.factored_exchange:
-            if dist.is_initialized() and dist.get_world_size(grp) > 1 and not self.allreduce:
-                dist.all_reduce(self.dflat, group=grp)
-                dist.all_reduce(self.loss, group=grp)
-            return
-        main = torch.cuda.current_stream(self.dev)
-        cw0, cw1 = L.mhe_flow_param_offset(shape, 0, 0, 6), L.mhe_flow_param_offset(shape, 0, 0, 7)
-        # factors first (small), then the dense remainder on the communication stream while the GEMM below runs
-        # (grouped NCCL launches: one for the two gathers, one for the three reductions - each separate call costs ~15-20 us)
-        coalesce = not os.environ.get('MHE_ENGINE_NO_COALESCE')
-        if coalesce:
-            with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
-                dist.all_gather_into_tensor(self.dcp_all, self.dcp, group=grp)
-                dist.all_gather_into_tensor(self.feat_all, self.feat, group=grp)
-        else:
-            dist.all_gather_into_tensor(self.dcp_all, self.dcp, group=grp)
-            dist.all_gather_into_tensor(self.feat_all, self.feat, group=grp)
+        grp, main = self.allreduce_group, torch.cuda.current_stream(self.dev)
         self.comm.wait_stream(main)
         with torch.cuda.stream(self.comm):
-            if coalesce:
+            # (grouped NCCL launch: each separate call costs ~15-20 us)
+            if not os.environ.get('MHE_ENGINE_NO_COALESCE'):
+                with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
+                    dist.all_gather_into_tensor(self.dcp_all, self.dcp, group=grp)
+                    dist.all_gather_into_tensor(self.feat_all, self.feat, group=grp)
+            else:
+                dist.all_gather_into_tensor(self.dcp_all, self.dcp, group=grp)
+                dist.all_gather_into_tensor(self.feat_all, self.feat, group=grp)
+            self.gathered = torch.cuda.Event()
+            self.gathered.record(self.comm)
+        # the GEMM on its own stream (the reductions that follow on the communication stream must not wait for it)
+        self.comm2.wait_event(self.gathered)
+        with torch.cuda.stream(self.comm2):
+            check(L.mhe_flow_set_async(flags), 'set_async')     # (bit 1: the Cw slots are overwritten - they were never written this step)
+            check(L.mhe_flow_cond_wgrad(shape, ptr(self.feat_all), ptr(self.dcp_all), self.dcp_all.shape[0], ptr(self.dflat), ptr(self.xws),
+                                        self.xws_bytes, _lib.stream_ptr(self.dev)), 'cond_wgrad')
+
+    def _enqueue_dense_remainder(self, L, shape):
+        """All-reduce of everything but the conditioning weights (+ the loss) on the communication stream; joins both streams."""
+        import torch.distributed as dist
+        grp, main = self.allreduce_group, torch.cuda.current_stream(self.dev)
+        cw0, cw1 = L.mhe_flow_param_offset(shape, 0, 0, 6), L.mhe_flow_param_offset(shape, 0, 0, 7)
+        self.comm.wait_stream(main)
+        self.comm.wait_stream(self.side4)           # the loss (reduced on a side stream)
+        with torch.cuda.stream(self.comm):
+            if not os.environ.get('MHE_ENGINE_NO_COALESCE'):
                 with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
                     dist.all_reduce(self.dflat[:cw0], group=grp)
                     dist.all_reduce(self.dflat[cw1:], group=grp)
@@ -228,13 +245,27 @@ class TrainStep:
                 dist.all_reduce(self.dflat[:cw0], group=grp)
                 dist.all_reduce(self.dflat[cw1:], group=grp)
                 dist.all_reduce(self.loss, group=grp)
-        check(L.mhe_flow_set_async(2), 'set_async')          # the Cw slots are overwritten (they were never written this step)
+        main.wait_stream(self.comm)
+        main.wait_stream(self.comm2)
+
+    def exchange_gradients(self):
+        """Data-parallel gradient exchange after run() (sum over the ranks, like one all-reduce of dflat and loss): all-gather of the
+        conditioning factors + local mhe_flow_cond_wgrad for the conditioning weights, all-reduce of the rest.  A no-op when the
+        exchange already ran inside the step (exchange_in_graph / allreduce)."""
+        import torch.distributed as dist
+        L, shape, grp = lib(), self.shape, self.allreduce_group
+        if not self.factored_exchange:
+            if dist.is_initialized() and dist.get_world_size(grp) > 1 and not self.allreduce:
+                dist.all_reduce(self.dflat, group=grp)
+                dist.all_reduce(self.loss, group=grp)
+            return
+        if self.exchange_in_graph:
+            return
         try:
-            check(L.mhe_flow_cond_wgrad(shape, ptr(self.feat_all), ptr(self.dcp_all), self.dcp_all.shape[0], ptr(self.dflat), ptr(self.xws),
-                                        self.xws_bytes, _lib.stream_ptr(self.dev)), 'cond_wgrad')
+            self._enqueue_factor_exchange(L, shape, 2 | 16)
         finally:
             check(L.mhe_flow_set_async(0), 'set_async')
-        main.wait_stream(self.comm)
+        self._enqueue_dense_remainder(L, shape)
 
     def _enqueue_allreduce(self, L, shape, R):
         """Bucketed sum-all-reduce on the communication stream: chunk c's gradient segments as soon as its layers are complete."""
