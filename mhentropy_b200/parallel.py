@@ -42,3 +42,24 @@ def allreduce_step(flat_grad: torch.Tensor, loss: torch.Tensor, local_images: in
         dist.all_reduce(flat_grad, group=group)
         dist.all_reduce(loss, group=group)
     return flat_grad, loss
+
+
+def gather_cond_factors(dcp: torch.Tensor, feat: torch.Tensor, group=None):
+    """Factored exchange of the conditioning weight gradient: ``dCw[idx] = dcp[:, idx, :]^T feat`` has rank <= images
+    per weight matrix, so the ranks all-gather the factors - ``dcp`` (B, L*4*H) and ``feat`` (B, C), equal B on every rank - instead of
+    all-reducing the dense gradient.  Returns ``(dcp_all, feat_all)`` with world*B rows; ``mhe_flow_cond_wgrad`` (or
+    :func:`cond_wgrad_from_factors` on the CPU) turns them into the global gradient."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return dcp, feat
+    world = dist.get_world_size(group)
+    dcp_all = dcp.new_empty(world * dcp.shape[0], dcp.shape[1])
+    feat_all = feat.new_empty(world * feat.shape[0], feat.shape[1])
+    dist.all_gather_into_tensor(dcp_all, dcp.contiguous(), group=group)
+    dist.all_gather_into_tensor(feat_all, feat.contiguous(), group=group)
+    return dcp_all, feat_all
+
+
+def cond_wgrad_from_factors(dcp_all: torch.Tensor, feat_all: torch.Tensor, hidden: int) -> torch.Tensor:
+    """Plain-PyTorch statement of ``mhe_flow_cond_wgrad``: (L*4, H, C) conditioning weight gradients from the (gathered) factors."""
+    Bt = dcp_all.shape[0]
+    return torch.einsum('bih,bc->ihc', dcp_all.reshape(Bt, -1, hidden), feat_all)

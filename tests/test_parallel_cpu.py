@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from mhentropy_b200.mano_assets import synthetic_mano
-from mhentropy_b200.parallel import allreduce_step, image_range, shard_batch
+from mhentropy_b200.parallel import allreduce_step, cond_wgrad_from_factors, gather_cond_factors, image_range, shard_batch
 from mhentropy_b200.synthetic import synthetic_batch
 from oracle import flow_oracle as fo
 from oracle import loss_oracle as lo
@@ -82,3 +82,40 @@ def test_two_rank_step_matches_single_process():
     assert abs(float(loss2[0]) - float(loss1)) < 1e-4 * abs(float(loss1))
     err = float((torch.from_numpy(flat2) - flat1).norm() / flat1.norm())
     assert err < 1e-4, err
+
+
+def _factor_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    g = torch.Generator().manual_seed(50 + rank)
+    Bl, L4, H, C = 3, 8, 16, 12
+    dcp, feat = torch.randn(Bl, L4 * H, generator=g, dtype=torch.float64), torch.randn(Bl, C, generator=g, dtype=torch.float64)
+    dense = cond_wgrad_from_factors(dcp, feat, H)             # the local gradient ...
+    dist.all_reduce(dense)                                     # ... all-reduced: the dense exchange
+    dcp_all, feat_all = gather_cond_factors(dcp, feat)         # the factored exchange
+    fact = cond_wgrad_from_factors(dcp_all, feat_all, H)
+    if rank == 0:
+        q.put((dense.numpy(), fact.numpy(), tuple(dcp_all.shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_factored_cond_exchange_equals_dense_allreduce():
+    """The data-parallel exchange of the conditioning weight gradient by its factors (all-gather of dcp / feat, then one local contraction)
+    equals the all-reduce of the local dense gradients (gloo, world size 2)."""
+    import numpy as np
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_factor_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    dense, fact, shape = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert shape == (6, 8 * 16)
+    np.testing.assert_allclose(fact, dense, rtol=1e-12, atol=1e-12)
