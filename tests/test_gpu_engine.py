@@ -152,3 +152,42 @@ def test_engine_pipelined_cond_bwd_matches_default():
         assert torch.equal(outs[0][0], outs[1][0])
         for a, b in zip(outs[0][1:], outs[1][1:]):
             assert rel(a, b) < 1e-5
+
+
+def test_cond_wgrad_matches_cond_bwd():
+    """mhe_flow_cond_wgrad (the conditioning weight gradient from its factors, used by the factored data-parallel exchange) writes exactly
+    what mhe_flow_cond_bwd writes into the Cw slots; with mhe_flow_set_async bit 4 cond_bwd leaves those slots alone."""
+    from mhentropy_b200 import RealNVP, _lib
+    from mhentropy_b200._lib import check, lib, ptr
+    torch.manual_seed(3)
+    flow = RealNVP(dim=45, tsfm_on=512, h_dims=[512, 512], num_steps=6).to(DEV)
+    flow.precision = 'bf16x3'
+    L, shape = lib(), flow._shape
+    flat, packed = flow.flat_parameters(torch.device(DEV)), flow.packed_weights(torch.device(DEV))
+    s = _lib.stream_ptr(torch.device(DEV))
+    cw0, cw1 = L.mhe_flow_param_offset(shape, 0, 0, 6), L.mhe_flow_param_offset(shape, 0, 0, 7)
+    for B in (64, 5):
+        feat = torch.randn(B, 512, device=DEV)
+        dcp = 1e-3 * torch.randn(B, L.mhe_flow_cp_floats_per_image(shape), device=DEV)
+        wsb = L.mhe_flow_cond_workspace_bytes(shape, B)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+        ga, gb = torch.zeros_like(flat), torch.zeros_like(flat)
+        dfa, dfb = torch.empty(B, 512, device=DEV), torch.empty(B, 512, device=DEV)
+        check(L.mhe_flow_cond_bwd(shape, ptr(flat), ptr(packed), ptr(feat), ptr(dcp), B, ptr(ga), ptr(dfa), ptr(ws), wsb, s), 'cond_bwd')
+        check(L.mhe_flow_set_async(16), 'set_async')
+        try:
+            check(L.mhe_flow_cond_bwd(shape, ptr(flat), ptr(packed), ptr(feat), ptr(dcp), B, ptr(gb), ptr(dfb), ptr(ws), wsb, s), 'cond_bwd skip')
+        finally:
+            check(L.mhe_flow_set_async(0), 'set_async')
+        torch.cuda.synchronize()
+        assert float(gb[cw0:cw1].abs().max()) == 0.0                      # Cw slots untouched
+        assert rel(gb[:cw0], ga[:cw0]) < 1e-5 and rel(gb[cw1:], ga[cw1:]) < 1e-5        # biases as before (atomic sums: order may differ)
+        assert rel(dfb, dfa) < 1e-5
+        check(L.mhe_flow_cond_wgrad(shape, ptr(feat), ptr(dcp), B, ptr(gb), ptr(ws), wsb, s), 'cond_wgrad')
+        torch.cuda.synchronize()
+        assert torch.equal(gb[cw0:cw1], ga[cw0:cw1])
+        # and against plain PyTorch (fp64)
+        from mhentropy_b200.parallel import cond_wgrad_from_factors
+        ref = cond_wgrad_from_factors(dcp.double().cpu(), feat.double().cpu(), 512)
+        got = torch.stack([ga[L.mhe_flow_param_offset(shape, i // 4, (i // 2) % 2, 6 + 2 * (i % 2)):][:512 * 512].view(512, 512) for i in range(48)])
+        assert rel(got, ref) < 1e-3      # gradients travel as bfloat16 split planes (16 significant bits): the north-star gradient bar
