@@ -174,6 +174,16 @@ int mhe_flow_zero_bias_grads(mhe_flow_shape s, float* dparams, void* stream);
 int mhe_flow_set_async(int on);
 int mhe_flow_join(void* stream);
 
+/* Optimizer step on the flat buffer (reference hand/CrossModalHand.py:201 torch.optim.Adam with default betas / eps, :462-470
+ * clip_grad_norm_ then optimizer.step()).  exp_avg / exp_avg_sq: Adam state, same layout as params.  step >= 1 is the step count AFTER
+ * this update.  grad_scale multiplies the gradient first: the reference clips by the global norm over the whole encoder (CNN backbone
+ * included), so the caller combines mhe_flow_grad_sqnorm() with its other modules' terms and passes min(1, max_norm / norm).  When
+ * packed != NULL the split planes mhe_flow_pack_weights() would produce (half and bfloat16, every family) are refreshed in the same
+ * call - the two dense families straight from the update's registers -, so the next step needs no re-pack.                         */
+int mhe_flow_grad_sqnorm(mhe_flow_shape s, const float* dparams, double* sqnorm_out /* device, 1 double */, void* stream);
+int mhe_flow_adam_step(mhe_flow_shape s, float* params, const float* dparams, float* exp_avg, float* exp_avg_sq, void* packed, int step,
+                       double lr, double beta1, double beta2, double eps, double grad_scale, void* stream);
+
 /* log N(z; 0, I) + logdet per row (flows.py:320) and its gradient seeds:
  *   fwd: logp[r] = -0.5|z_r|^2 - 0.5 D ln(2 pi) + logdet_sign*logdet[r]   (logdet may be NULL)
  *   bwd: dz[r][:] = -z[r][:] * dlogp[r]                                                          */

@@ -16,5 +16,6 @@ from .mano import ManoCore, ManoLayer  # noqa: F401
 from .losses import MHEntHead, default_loss_cfg  # noqa: F401
 from .metrics import MHEntLoss, hypothesis_metrics, topk_hypotheses  # noqa: F401
 from .checkpoint import load_reference_checkpoint  # noqa: F401
+from .optim import FlatAdam  # noqa: F401
 
-__all__ = ['RealNVP', 'ManoLayer', 'ManoCore', 'MHEntHead', 'default_loss_cfg', 'MHEntLoss', 'hypothesis_metrics', 'topk_hypotheses', 'load_reference_checkpoint']
+__all__ = ['RealNVP', 'ManoLayer', 'ManoCore', 'MHEntHead', 'default_loss_cfg', 'MHEntLoss', 'hypothesis_metrics', 'topk_hypotheses', 'load_reference_checkpoint', 'FlatAdam']

@@ -254,6 +254,8 @@ class RealNVP(nn.Module):
     def flat_parameters(self, device=None) -> torch.Tensor:
         """The flat fp32 parameter buffer the kernels read (adopting the parameters if needed)."""
         device = torch.device(device) if device is not None else self.mask.device
+        if device.type == 'cuda' and device.index is None:      # 'cuda' == the current device: tensors always report an index
+            device = torch.device('cuda', torch.cuda.current_device())
         if not self._flat_is_current(device):
             self._adopt(device)
         return self._flat

@@ -191,3 +191,41 @@ def test_cond_wgrad_matches_cond_bwd():
         ref = cond_wgrad_from_factors(dcp.double().cpu(), feat.double().cpu(), 512)
         got = torch.stack([ga[L.mhe_flow_param_offset(shape, i // 4, (i // 2) % 2, 6 + 2 * (i % 2)):][:512 * 512].view(512, 512) for i in range(48)])
         assert rel(got, ref) < 1e-3      # gradients travel as bfloat16 split planes (16 significant bits): the north-star gradient bar
+
+
+def test_flat_adam_matches_torch_adam_and_refreshes_planes():
+    """mhe_flow_adam_step == torch.optim.Adam on the flat buffer (reference CrossModalHand.py:201, clip scale :462-470), and the split
+    planes it leaves behind are byte-identical to a fresh mhe_flow_pack_weights of the updated parameters."""
+    from mhentropy_b200 import RealNVP, _lib
+    from mhentropy_b200._lib import check, lib, ptr
+    from mhentropy_b200.optim import FlatAdam
+    torch.manual_seed(8)
+    dev = torch.device(DEV)
+    flow = RealNVP(dim=45, tsfm_on=512, h_dims=[512, 512], num_steps=6).to(dev)
+    flow.precision = 'bf16x3'
+    L, shape = lib(), flow._shape
+    flat = flow.flat_parameters(dev)
+    packed = flow.packed_weights(dev)
+    ref_p = torch.nn.Parameter(flat.detach().clone())
+    ref_opt = torch.optim.Adam([ref_p], lr=2e-3)
+    opt = FlatAdam(flow, lr=2e-3)
+    for it in range(3):
+        g = torch.zeros_like(flat)                                   # like a real flat gradient: zero on the padding between tensors
+        for _, off, n, _ in flow._slots:
+            g[off:off + n] = 1e-2 * torch.randn(n, device=dev)
+        sq = opt.grad_sqnorm(g)
+        assert abs(float(sq) - float(g.double().pow(2).sum())) < 1e-9 * float(sq)
+        scale = min(1.0, 1.0 / (float(sq) ** 0.5 + 1e-6))             # clip_grad_norm_(…, 1.)
+        ref_p.grad = g * scale
+        ref_opt.step()
+        opt.step(g, grad_scale=scale)
+    torch.cuda.synchronize()
+    err = rel(flow.flat_parameters(dev), ref_p)
+    assert err < 2e-6, err
+    fresh = packed.clone()             # (same padding bytes between the plane families; the data regions are re-packed below)
+    check(L.mhe_flow_pack_weights(shape, ptr(flow.flat_parameters(dev)), ptr(fresh), 3, _lib.stream_ptr(dev)), 'pack_weights')
+    torch.cuda.synchronize()
+    # compare the plane regions only (padding between them is never written)
+    nb = L.mhe_flow_packed_bytes(shape)
+    a, b = packed[:nb].view(torch.int16), fresh[:nb].view(torch.int16)
+    assert int((a != b).sum()) == 0
