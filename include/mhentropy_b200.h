@@ -66,6 +66,11 @@ typedef struct mhe_flow_shape {
     int hidden;
     int cond;
     int layers;
+    /* Largest number of transformed (mask == 0) or conditioning (mask == 1) dims of any coupling layer, computed by the caller from
+     * its {0,1} mask (reference flows.py:152-155 builds dim/2 | dim - dim/2 splits; RealNVP also accepts a user mask, :131).
+     * 0 = the reference's default alternating half masks.  The cluster-fused kernels exchange at most 24 dims per layer and side:
+     * larger splits run on the per-GEMM tensor-core path.  Masks that are not exactly {0,1} are outside every kernel path.      */
+    int max_split;
 } mhe_flow_shape;
 
 size_t mhe_flow_param_floats(mhe_flow_shape s);

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'libmhentropy_b200.so')
 
 
 class FlowShape(Structure):
-    _fields_ = [('dim', c_int), ('hidden', c_int), ('cond', c_int), ('layers', c_int)]
+    _fields_ = [('dim', c_int), ('hidden', c_int), ('cond', c_int), ('layers', c_int), ('max_split', c_int)]
 
 
 class ManoConsts(Structure):

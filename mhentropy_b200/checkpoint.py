@@ -30,7 +30,7 @@ def load_reference_checkpoint(head, checkpoint, module: str = 'encoderRGB', load
     ``load_state_dict``), so a checkpoint of a different flow configuration fails loudly.
     """
     if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, '__fspath__'):
-        checkpoint = torch.load(checkpoint, map_location='cpu', weights_only=False)
+        checkpoint = torch.load(checkpoint, map_location='cpu', weights_only=True)   # state dicts are plain tensors: no unpickling of code
     sd = checkpoint[module] if module in checkpoint and isinstance(checkpoint[module], dict) else checkpoint
     hot, rest = split_reference_state_dict(sd)
     if not load_mano_buffers:
@@ -42,7 +42,13 @@ def load_reference_checkpoint(head, checkpoint, module: str = 'encoderRGB', load
         raise KeyError(f'reference checkpoint does not match the head: missing {missing[:5]}{"..." if len(missing) > 5 else ""}, '
                        f'unexpected {unexpected[:5]}{"..." if len(unexpected) > 5 else ""}')
     head.load_state_dict(hot, strict=load_mano_buffers)
+    # derived state follows the loaded tensors: the flow's split weight planes and the MANO kernels' packed constants are rebuilt on
+    # next use (both modules also invalidate themselves in _load_from_state_dict; an engine built BEFORE the load must be rebuilt -
+    # TrainStep bakes the constants' pointers into its CUDA graph)
     flow = getattr(head, 'q_z_giv_i', None)
-    if flow is not None and hasattr(flow, '_packed'):
-        flow._packed = None          # packed weight planes are derived state: rebuilt on next use
+    if flow is not None and hasattr(flow, 'mark_parameters_changed'):
+        flow.mark_parameters_changed()
+    mano = getattr(getattr(head, 'mano_dec', None), 'mano_layer', None)
+    if mano is not None and hasattr(mano, '_packed'):
+        mano._packed = None
     return rest

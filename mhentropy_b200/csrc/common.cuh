@@ -60,9 +60,10 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // flat parameter layout (see include/mhentropy_b200.h)
 struct FlowLayout {
     int D, H, C, L;
+    int max_split;                             // largest per-layer count of transformed / conditioning dims (see mhe_flow_shape)
     size_t oW0, ob0, oW1, ob1, oW2, ob2, blk;  // offsets inside a (layer, net) block
     size_t cw_base, cw_stride, cb_base, cb_stride, total;
-    explicit FlowLayout(mhe_flow_shape s) : D(s.dim), H(s.hidden), C(s.cond), L(s.layers) {
+    explicit FlowLayout(mhe_flow_shape s) : D(s.dim), H(s.hidden), C(s.cond), L(s.layers), max_split(s.max_split > 0 ? s.max_split : (s.dim + 1) / 2) {
         oW0 = 0;
         ob0 = oW0 + pad_seg((size_t)H * D);
         oW1 = ob0 + pad_seg(H);
@@ -82,7 +83,7 @@ struct FlowLayout {
 };
 
 inline bool valid_shape(mhe_flow_shape s) {
-    return s.dim >= 2 && s.dim <= 64 && s.hidden >= 1 && s.cond >= 1 && s.layers >= 1 && s.layers <= 64;
+    return s.dim >= 2 && s.dim <= 64 && s.hidden >= 1 && s.cond >= 1 && s.layers >= 1 && s.layers <= 64 && s.max_split >= 0 && s.max_split <= s.dim;
 }
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------------

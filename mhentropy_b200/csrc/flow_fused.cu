@@ -33,7 +33,7 @@ bool supported(const FlowLayout& L, int R) {
         const char* e = getenv("MHE_FUSED_MAX_ROWS");
         max_rows = e ? atoi(e) : 4096;
     }
-    return L.D <= 46 && L.D >= 4 && L.H == 512 && L.C % 8 == 0 && L.L <= 16 && R <= max_rows;
+    return L.D <= 46 && L.D >= 4 && L.H == 512 && L.C % 8 == 0 && L.L <= 16 && L.max_split <= kActMax && R <= max_rows;
 }
 
 // ---- cluster / barrier primitives -----------------------------------------------------------------------------

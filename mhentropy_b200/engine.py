@@ -9,6 +9,7 @@ kernel launches on preallocated buffers, so it can be captured in a CUDA graph. 
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -18,13 +19,46 @@ from ._lib import check, lib, ptr
 from .losses import MHEntHead
 
 
+def factored_exchange_pays(shape, B: int, world: int) -> bool:
+    """Factored vs dense exchange of the conditioning weight gradient: the factors all-gathered per rank are
+    world x B x (L*4*H + C) floats, the dense gradient L*4*H*C.  The gather also feeds a contraction over world x B images on every
+    rank, so it only pays while the factors are well below the dense size: 2 and 4 ranks at 64 images, not 8."""
+    factors = world * B * (shape.layers * 4 * shape.hidden + shape.cond)
+    dense = shape.layers * 4 * shape.hidden * shape.cond
+    return factors <= 0.6 * dense
+
+
+@contextlib.contextmanager
+def _nvtx(name: str):
+    """NVTX range around a phase of the step (shows up in Nsight Systems / ncu --nvtx; free when no tool is attached)."""
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
 class TrainStep:
+    """planes: ``'step'`` re-packs the split weight planes from the fp32 parameters inside every step (weights may have been changed by
+    anything); ``'optimizer'`` reads the flow's own plane set (``RealNVP.packed_weights``), which ``FlatAdam.step`` refreshes in the
+    same pass as the update - no conversion kernel runs inside the step.
+    exchange: ``'auto'`` picks the factored or the dense gradient exchange by size (:func:`factored_exchange_pays`).
+    average_over_ranks: with several ranks the loss and every gradient are the GLOBAL-batch mean (each rank seeds its backward with
+    1 / (B * world) and the exchange sums), so a sharded step equals the single-process step on the concatenated batch."""
+
     def __init__(self, head: MHEntHead, B: int, S: int, device, want_verts: bool = True, use_graph: bool = True,
                  prepare_ahead: bool = False, pipelined_cond_bwd: bool = False, allreduce_group=None, allreduce: bool = False,
-                 factored_exchange: bool = False, exchange_in_graph: bool = False):
+                 factored_exchange: bool | None = None, exchange_in_graph: bool = False, planes: str = 'step',
+                 exchange: str = 'auto', average_over_ranks: bool = True):
         self.head, self.B, self.S, self.R = head, B, S, B * S
         self.dev = torch.device(device)
         flow = head.q_z_giv_i
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.world = torch.distributed.get_world_size(allreduce_group) if dist_on else 1
+        self.dloss = 1.0 / self.world if average_over_ranks else 1.0
+        if planes not in ('step', 'optimizer'):
+            raise ValueError("planes must be 'step' or 'optimizer'")
+        self.planes = planes
         self.shape = flow._shape
         self.flat = flow.flat_parameters(self.dev)
         self.mask = flow.mask
@@ -52,7 +86,9 @@ class TrainStep:
         self.saved = torch.empty(L.mhe_flow_saved_bytes(self.shape, R, int(self.tc)), dtype=torch.uint8, device=dev)
         self.packed = None
         if self.tc:
-            self.packed = torch.empty(L.mhe_flow_packed_bytes(self.shape), dtype=torch.uint8, device=dev)
+            # 'optimizer': the flow's own plane set (packed now if stale; FlatAdam.step keeps it current from then on)
+            self.packed = flow.packed_weights(dev) if planes == 'optimizer' else \
+                torch.empty(L.mhe_flow_packed_bytes(self.shape), dtype=torch.uint8, device=dev)
         self.cws_bytes = L.mhe_flow_cond_workspace_bytes(self.shape, B) if self.tc else 0
         self.cws = torch.empty(max(self.cws_bytes, 16), dtype=torch.uint8, device=dev)
         self.ws_bytes = max(L.mhe_flow_workspace_bytes(self.shape, R, int(self.tc)), L.mhe_mano_workspace_bytes(R, 0))
@@ -83,14 +119,15 @@ class TrainStep:
         # data parallelism, the default exchange (exchange_gradients(), after the step): the conditioning weight gradient (50 of the 80 MB)
         # has rank <= images per weight matrix, so the ranks all-gather its FACTORS (dcp, feat: 6.4 MB per rank) and each computes the
         # global gradient with mhe_flow_cond_wgrad; only the other 30 MB are all-reduced.  The step itself then skips that GEMM.
-        self.factored_exchange = bool(factored_exchange) and self.tc and not self.allreduce and torch.distributed.is_available() \
-            and torch.distributed.is_initialized() and torch.distributed.get_world_size(allreduce_group) > 1
+        if factored_exchange is None:
+            factored_exchange = exchange == 'factored' or (exchange == 'auto' and factored_exchange_pays(self.shape, B, self.world))
+        self.factored_exchange = bool(factored_exchange) and self.tc and not self.allreduce and self.world > 1
         # exchange_in_graph (EXPERIMENTAL, off): the factored exchange is enqueued inside the (captured) step, so the gather and the global
         # conditioning GEMM run beside the last weight gradients instead of after the step - 0.638 vs 0.670 ms/step on 2 GPUs in bench.py, but
         # tools/check_factored_exchange.py hung with it (two engines in one process); not the default until that is understood
         self.exchange_in_graph = bool(exchange_in_graph or os.environ.get('MHE_ENGINE_EXCHANGE_IN_GRAPH')) and self.factored_exchange
         if self.factored_exchange:
-            world = torch.distributed.get_world_size(allreduce_group)
+            world = self.world
             self.comm = torch.cuda.Stream(self.dev)
             self.comm2 = torch.cuda.Stream(self.dev)
             self.dcp_all = torch.empty(world * B, cpf, device=dev)
@@ -107,29 +144,37 @@ class TrainStep:
         theta, beta = z.data_ptr(), z.data_ptr() + 48 * 4
         pk, cws, cwsb = ptr(self.packed), ptr(self.cws), self.cws_bytes
         # ---- forward
-        if self.tc:   # weights change between steps: refresh their split planes inside the step.  Only the conditioning planes gate
-            # the first GEMM; the coupling planes are converted on a side stream meanwhile, and the bfloat16 copies (read by the
-            # backward only) on another one while the forward runs.
+        torch.cuda.nvtx.range_push('mhe.step.prologue')
+        repack = self.tc and self.planes == 'step'
+        if self.tc:   # weights change between steps.  planes == 'step': refresh their split planes inside the step - only the conditioning
+            # planes gate the first GEMM; the coupling planes are converted on a side stream meanwhile, and the bfloat16 copies (read by the
+            # backward only) on another one while the forward runs.  planes == 'optimizer': FlatAdam.step wrote them with the update.
             main = torch.cuda.current_stream(self.dev)
             self.side.wait_stream(main)
-            if L.mhe_flow_cond_fwd_uses_planes(shape, B):  # (at <= 128 images the conditioning GEMM streams the fp32 weights itself)
+            if repack and L.mhe_flow_cond_fwd_uses_planes(shape, B):  # (at <= 128 images the conditioning GEMM streams the fp32 weights itself)
                 check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 4, s), 'pack_weights')
-            self.side3.wait_stream(main)               # after the conditioning planes: those gate the first GEMM
-            with torch.cuda.stream(self.side3):
-                check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 8, _lib.stream_ptr(self.dev)), 'pack_weights')
+            if repack:
+                self.side3.wait_stream(main)               # after the conditioning planes: those gate the first GEMM
+                with torch.cuda.stream(self.side3):
+                    check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 8, _lib.stream_ptr(self.dev)), 'pack_weights')
             with torch.cuda.stream(self.side):
-                self.side.wait_stream(self.side3)      # the forward-critical conversions get the memory system first
-                # bfloat16 planes (read by the backward only)
-                check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 2, _lib.stream_ptr(self.dev)), 'pack_weights')
+                if repack:
+                    self.side.wait_stream(self.side3)      # the forward-critical conversions get the memory system first
+                    # bfloat16 planes (read by the backward only)
+                    check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 2, _lib.stream_ptr(self.dev)), 'pack_weights')
                 # the weight slots of dflat are stored (not accumulated) by the backward: only the bias slots need zeroing
                 check(L.mhe_flow_zero_bias_grads(shape, ptr(self.dflat), _lib.stream_ptr(self.dev)), 'zero_bias_grads')
                 self.dcp.zero_()
                 self.dfeat.zero_()
         check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
-        if self.tc:
+        if repack:
             torch.cuda.current_stream(self.dev).wait_stream(self.side3)
+        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_push('mhe.step.flow_forward')
         check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
                                   ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
+        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_push('mhe.step.hypothesis_rows')
         main = torch.cuda.current_stream(self.dev)
         # (Re-planing the saved activations for the weight gradients right here (mhe_flow_pass_bwd_prepare) and converting the
         # bfloat16 conditioning planes in this window were measured: they delay the per-row kernel and collide with the first
@@ -164,14 +209,18 @@ class TrainStep:
         # (the kernel can also assemble its row of z from x / z_det and emit the flow's share of dz itself, which takes both combine_z
         # kernels off this chain - measured slower, 0.549 vs 0.537 ms: the backward's cluster kernel needs entirely free SMs and cannot
         # start before the mesh skinning has drained anyway, and an earlier per-row kernel collides with the pose-blend GEMM)
-        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), None, None, ptr(self.crop_uv), ptr(self.vis), R, B, 1, 1.0,
+        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), None, None, ptr(self.crop_uv), ptr(self.vis), R, B, 1, self.dloss,
                                             ptr(self.jtr), ptr(self.uv), ptr(self.row_lp), ptr(self.dz), None, ptr(self.dlog_q), s),
               'hypothesis_rows')
         self.side4.wait_stream(main)
         with torch.cuda.stream(self.side4):
             check(L.mhe_image_loss_reduce(ptr(self.row_lp), ptr(self.log_q), R, B, ptr(self.log_p), ptr(self.h), ptr(self.qlp),
                                           ptr(self.loss), _lib.stream_ptr(self.dev)), 'image_loss_reduce')
+            if self.dloss != 1.0:
+                self.loss.mul_(self.dloss)              # this rank's share of the global-batch mean (the exchange sums)
         check(L.mhe_combine_z_bwd(ptr(self.dz), R, B, ptr(self.dx), ptr(self.dz_det), s), 'combine_z_bwd')
+        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_push('mhe.step.flow_backward')
         # log_q = log N(z0) - logdet  ->  dL/dlogdet = -dL/dlog_q
         # the weight-gradient GEMMs of the pass keep running on the library's streams while the conditioning backward (which only
         # needs dcp) is enqueued; mhe_flow_join() brings them back before the step ends
@@ -196,6 +245,8 @@ class TrainStep:
                                           cws, cwsb, s), 'cond_bwd')
         finally:
             check(L.mhe_flow_set_async(0), 'set_async')
+        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_push('mhe.step.join')
         if self.allreduce:
             self._enqueue_allreduce(L, shape, R)
         check(L.mhe_flow_join(s), 'flow_join')
@@ -204,6 +255,7 @@ class TrainStep:
         if self.verts is not None:
             torch.cuda.current_stream(self.dev).wait_stream(self.side2)    # mesh skinning joins here
         torch.cuda.current_stream(self.dev).wait_stream(self.side4)    # ... and the loss reductions
+        torch.cuda.nvtx.range_pop()
 
     def _enqueue_factor_exchange(self, L, shape, flags):
         """All-gather of the conditioning factors and the global conditioning weight gradient, on the communication stream."""
@@ -254,18 +306,24 @@ class TrainStep:
         exchange already ran inside the step (exchange_in_graph / allreduce)."""
         import torch.distributed as dist
         L, shape, grp = lib(), self.shape, self.allreduce_group
-        if not self.factored_exchange:
-            if dist.is_initialized() and dist.get_world_size(grp) > 1 and not self.allreduce:
-                dist.all_reduce(self.dflat, group=grp)
-                dist.all_reduce(self.loss, group=grp)
-            return
-        if self.exchange_in_graph:
-            return
-        try:
-            self._enqueue_factor_exchange(L, shape, 2 | 16)
-        finally:
-            check(L.mhe_flow_set_async(0), 'set_async')
-        self._enqueue_dense_remainder(L, shape)
+        with _nvtx('mhe.step.exchange_gradients'):
+            if not self.factored_exchange:
+                if self.world > 1 and not self.allreduce:
+                    if os.environ.get('MHE_ENGINE_NO_COALESCE'):
+                        dist.all_reduce(self.dflat, group=grp)
+                        dist.all_reduce(self.loss, group=grp)
+                    else:       # one grouped NCCL launch for the 80 MB and the scalar
+                        with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
+                            dist.all_reduce(self.dflat, group=grp)
+                            dist.all_reduce(self.loss, group=grp)
+                return
+            if self.exchange_in_graph:
+                return
+            try:
+                self._enqueue_factor_exchange(L, shape, 2 | 16)
+            finally:
+                check(L.mhe_flow_set_async(0), 'set_async')
+            self._enqueue_dense_remainder(L, shape)
 
     def _enqueue_allreduce(self, L, shape, R):
         """Bucketed sum-all-reduce on the communication stream: chunk c's gradient segments as soon as its layers are complete."""
@@ -316,7 +374,8 @@ class TrainStep:
         """One forward+backward on the loaded batch: ``loss`` (1,), ``dflat``, ``dfeat``, ``dz_det`` are updated."""
         if not self.use_graph:
             n0 = lib().mhe_kernel_launch_count()
-            self._enqueue()
+            with _nvtx('mhe.step'):
+                self._enqueue()
             self.launches_per_step = lib().mhe_kernel_launch_count() - n0
             return self.loss
         if self.graph is None:
@@ -332,7 +391,8 @@ class TrainStep:
                 self._enqueue()
             self.launches_per_step = lib().mhe_kernel_launch_count() - n0
             self.graph = g
-        self.graph.replay()
+        with _nvtx('mhe.step (graph replay)'):
+            self.graph.replay()
         return self.loss
 
     def flow_grads(self) -> dict:

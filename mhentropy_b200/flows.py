@@ -56,25 +56,29 @@ _WHICH = {('l', 0, 'weight'): 0, ('l', 0, 'bias'): 1, ('l', 1, 'weight'): 2, ('l
           ('c', 1, 'weight'): 8, ('c', 1, 'bias'): 9}
 
 
-class _GatherFlat(torch.autograd.Function):
-    """Autograd bridge: the 240 reference-named parameters <-> the flat buffer the kernels read."""
+class _FlatAnchor(torch.autograd.Function):
+    """Autograd bridge between the 240 reference-named parameters and the flat buffer the kernels read.
+
+    The flat buffer enters the graph through ONE scalar anchor that requires grad, so the kernels' backward functions run
+    whenever a parameter wants a gradient; they write straight into the flow's persistent flat gradient buffer, of which
+    every parameter's ``.grad`` is a view (``RealNVP.grad_buffer``).  Nothing flows back through this node: routing 240
+    tensors through autograd cost more host time per step than the kernels themselves.
+    """
 
     @staticmethod
-    def forward(ctx, flow, *params):
-        ctx.flow = flow
+    def forward(ctx, anchor, flow):
         return flow._flat.detach()
 
     @staticmethod
     def backward(ctx, gflat):
-        ctx.flow._last_flat_grad = gflat      # the parameters' .grad are views of this buffer (one NCCL all-reduce)
-        return (None, *ctx.flow._split_flat(gflat))
+        return None, None
 
 
 class _CondFn(torch.autograd.Function):
     """cp = hoisted conditioning projections of every layer (``flows.py:107-109``)."""
 
     @staticmethod
-    def forward(ctx, feat, flat, shape, packed):
+    def forward(ctx, feat, flat, shape, packed, flow=None):
         feat = feat.contiguous()
         _lib.require_cuda_f32(feat, flat)
         B = feat.shape[0]
@@ -84,7 +88,7 @@ class _CondFn(torch.autograd.Function):
         ws = _lib.WORKSPACE.get(wsb, dev, 'cond') if wsb else None
         check(lib().mhe_flow_cond_fwd(shape, ptr(flat), ptr(packed), ptr(feat), B, ptr(cp), ptr(ws), wsb, stream_ptr(dev)), 'mhe_flow_cond_fwd')
         ctx.save_for_backward(feat, flat)
-        ctx.shape, ctx.packed = shape, packed
+        ctx.shape, ctx.packed, ctx.flow = shape, packed, flow
         return cp
 
     @staticmethod
@@ -92,21 +96,26 @@ class _CondFn(torch.autograd.Function):
         feat, flat = ctx.saved_tensors
         dcp = dcp.contiguous()
         dev = feat.device
-        dflat = torch.zeros_like(flat)
+        # parameter gradients go straight into the flow's persistent flat gradient buffer (the parameters' .grad are views of it)
+        dflat, store = ctx.flow._grad_target('cond') if ctx.flow is not None else (torch.zeros_like(flat), True)
         dfeat = torch.empty_like(feat) if ctx.needs_input_grad[0] else None
         B = feat.shape[0]
         wsb = lib().mhe_flow_cond_workspace_bytes(ctx.shape, B) if ctx.packed is not None else 0
         ws = _lib.WORKSPACE.get(wsb, dev, 'cond') if wsb else None
-        check(lib().mhe_flow_cond_bwd(ctx.shape, ptr(flat), ptr(ctx.packed), ptr(feat), ptr(dcp), B, ptr(dflat), ptr(dfeat), ptr(ws), wsb,
-                                      stream_ptr(dev)), 'mhe_flow_cond_bwd')
-        return dfeat, dflat, None, None
+        check(lib().mhe_flow_set_async(2 if store else 0), 'mhe_flow_set_async')   # bit 1: the weight slots are zero -> store, no read
+        try:
+            check(lib().mhe_flow_cond_bwd(ctx.shape, ptr(flat), ptr(ctx.packed), ptr(feat), ptr(dcp), B, ptr(dflat), ptr(dfeat), ptr(ws), wsb,
+                                          stream_ptr(dev)), 'mhe_flow_cond_bwd')
+        finally:
+            check(lib().mhe_flow_set_async(0), 'mhe_flow_set_async')
+        return dfeat, (dflat if ctx.flow is None else None), None, None, None
 
 
 class _FlowPassFn(torch.autograd.Function):
     """One pass through the coupling layers; returns (out, logdet)."""
 
     @staticmethod
-    def forward(ctx, inp, cp, flat, mask, shape, direction, B, packed):
+    def forward(ctx, inp, cp, flat, mask, shape, direction, B, packed, flow=None):
         inp = inp.contiguous()
         _lib.require_cuda_f32(inp, cp, flat, mask)
         R, D = inp.shape
@@ -122,7 +131,7 @@ class _FlowPassFn(torch.autograd.Function):
                                       ptr(saved), ptr(ws), wsb, stream_ptr(dev)), 'mhe_flow_pass_fwd')
         if need_grad:
             ctx.save_for_backward(cp, flat, mask, saved)
-        ctx.shape, ctx.direction, ctx.B, ctx.packed, ctx.dims = shape, direction, B, packed, (R, D)
+        ctx.shape, ctx.direction, ctx.B, ctx.packed, ctx.dims, ctx.flow = shape, direction, B, packed, (R, D), flow
         return out, logdet
 
     @staticmethod
@@ -134,14 +143,18 @@ class _FlowPassFn(torch.autograd.Function):
         dout = torch.zeros(R, D, device=dev) if dout is None else dout.contiguous()
         dlogdet = None if dlogdet is None else dlogdet.contiguous()
         din = torch.empty(R, D, device=dev, dtype=torch.float32)
-        dflat = torch.zeros_like(flat)
+        dflat, store = ctx.flow._grad_target('pass') if ctx.flow is not None else (torch.zeros_like(flat), True)
         dcp = torch.zeros_like(cp)
         wsb = lib().mhe_flow_workspace_bytes(shape, R, int(ctx.packed is not None))
         ws = _lib.WORKSPACE.get(wsb, dev)
-        check(lib().mhe_flow_pass_bwd(shape, ptr(flat), ptr(ctx.packed), ptr(mask), ptr(cp), ptr(saved), R, ctx.B, ctx.direction, ptr(dout),
-                                      ptr(dlogdet), 1.0, ptr(din), ptr(dflat), ptr(dcp), ptr(ws), wsb, stream_ptr(dev)),
-              'mhe_flow_pass_bwd')
-        return din, dcp, dflat, None, None, None, None, None
+        check(lib().mhe_flow_set_async(2 if store else 0), 'mhe_flow_set_async')
+        try:
+            check(lib().mhe_flow_pass_bwd(shape, ptr(flat), ptr(ctx.packed), ptr(mask), ptr(cp), ptr(saved), R, ctx.B, ctx.direction, ptr(dout),
+                                          ptr(dlogdet), 1.0, ptr(din), ptr(dflat), ptr(dcp), ptr(ws), wsb, stream_ptr(dev)),
+                  'mhe_flow_pass_bwd')
+        finally:
+            check(lib().mhe_flow_set_async(0), 'mhe_flow_set_async')
+        return din, dcp, (dflat if ctx.flow is None else None), None, None, None, None, None, None
 
 
 class _StdNormalLogpFn(torch.autograd.Function):
@@ -208,16 +221,50 @@ class RealNVP(nn.Module):
         self.scale = 1.
         self.h_dims = h_dims
         self.cond_dim = cond_dim
-        self._kernel_ok = (cond_dim > 0 and len(h_dims) == 2 and h_dims[0] == h_dims[1] and 2 <= dim <= 64
-                           and len(partitioner) == 0 and nets is _nets and nett is _nets)
-        self._shape = FlowShape(dim, h_dims[0], cond_dim, len(mask)) if self._kernel_ok else None
+        self._structure_ok = (cond_dim > 0 and len(h_dims) == 2 and h_dims[0] == h_dims[1] and 2 <= dim <= 64
+                              and len(partitioner) == 0 and nets is _nets and nett is _nets)
         self._flat = None
         self._slots = None
-        self._last_flat_grad = None
+        self._grad_flat = None
+        self._grad_views = None
+        self._grad_writes = {'pass': 0, 'cond': 0}
+        self._fwd_gen = 0
+        self._grad_zero_gen = -1
+        self._anchor = None
         self._packed = None
         self._packed_sig = None
+        self._param_epoch = 0
+        self._refresh_mask_info()
         # 'bf16x3': tcgen05 tensor cores, split-bf16 (hi*hi + hi*lo + lo*hi, fp32 accumulate); 'fp32': CUDA cores, exact
         self.precision = 'bf16x3' if (self._kernel_ok and lib_has_tc(self._shape)) else 'fp32'
+
+    # ------------------------------------------------------------------ coupling masks
+    def _refresh_mask_info(self):
+        """What the kernels need to know about the masks (``flows.py:152-155``; a user may pass any ``mask``, ``:131``).
+
+        The kernels implement the coupling for {0,1} masks only (the reference multiplies by the float mask, so a fractional
+        mask is a different function): anything else is outside the accelerated path.  ``max_split`` - the largest number of
+        transformed or conditioning dims of a layer - travels in the shape: the cluster-fused kernels exchange at most 24 dims per
+        layer and side, larger splits (e.g. 30/15) take the per-GEMM tensor-core path.
+        """
+        m = self.mask.detach().float().cpu()
+        binary = bool(((m == 0) | (m == 1)).all())
+        ones = m.sum(1)
+        max_split = int(max(ones.max().item(), (m.shape[1] - ones).max().item())) if binary and m.numel() else 0
+        self._mask_binary = binary
+        self._kernel_ok = self._structure_ok and binary and m.shape[1] == self.dim
+        self._shape = FlowShape(self.dim, self.h_dims[0], self.cond_dim, m.shape[0], max_split) if self._kernel_ok else None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._refresh_mask_info()           # a checkpoint may carry another mask
+        self.mark_parameters_changed()
+
+    def mark_parameters_changed(self):
+        """Tell the flow that its parameters were modified behind autograd's back (raw-pointer optimizer step, ``.data`` edits): the
+        split weight planes are re-packed before the next tensor-core pass.  ``FlatAdam.step`` calls it; in-place updates through
+        PyTorch bump the tensors' version counters and are noticed without it."""
+        self._param_epoch += 1
 
     # ------------------------------------------------------------------ flat parameter storage
     def _named_flow_params(self):
@@ -241,6 +288,8 @@ class RealNVP(nn.Module):
             p.data = view
             slots.append((p, off, p.numel(), tuple(p.shape)))
         self._flat, self._slots = flat, slots
+        self._grad_flat = self._grad_views = None
+        self._anchor = torch.zeros((), device=device, requires_grad=True)
 
     def _flat_is_current(self, device) -> bool:
         if self._flat is None or self._flat.device != device:
@@ -268,8 +317,7 @@ class RealNVP(nn.Module):
         if self.precision != 'bf16x3':
             raise ValueError(f"precision must be 'fp32' or 'bf16x3', got {self.precision!r}")
         flat = self.flat_parameters(device)
-        ps = self._slots
-        sig = (flat.data_ptr(), flat._version, ps[0][0]._version, ps[len(ps) // 2][0]._version, ps[-1][0]._version)
+        sig = self._packed_signature(flat)
         if self._packed is None or self._packed.device != flat.device or sig != self._packed_sig:
             nbytes = lib().mhe_flow_packed_bytes(self._shape)
             if nbytes == 0:
@@ -280,21 +328,68 @@ class RealNVP(nn.Module):
             self._packed_sig = sig
         return self._packed
 
+    def _packed_signature(self, flat):
+        # every parameter's version counter (in-place updates through PyTorch) + the explicit epoch (raw-pointer updates)
+        return (flat.data_ptr(), flat._version, self._param_epoch, sum(p._version for p, _, _, _ in self._slots))
+
     def _split_flat(self, gflat):
         return [gflat[off:off + n].view(shape) for _, off, n, shape in self._slots]
 
+    def grad_buffer(self, device=None) -> torch.Tensor:
+        """The persistent flat gradient buffer (layout of ``mhe_flow_param_offset``).  After ``backward()`` every parameter's
+        ``.grad`` is a view into it, so a data-parallel exchange is ONE all-reduce of this tensor and ``FlatAdam.step`` consumes it
+        directly."""
+        flat = self.flat_parameters(device)
+        if self._grad_flat is None or self._grad_flat.device != flat.device:
+            self._grad_flat = torch.zeros_like(flat)
+            self._grad_views = self._split_flat(self._grad_flat)
+            self._grad_writes = {'pass': 0, 'cond': 0}
+        return self._grad_flat
+
+    def _grads_attached(self) -> bool:
+        slots, views = self._slots, self._grad_views
+        if views is None:
+            return False
+        for i in (0, len(slots) // 2, len(slots) - 1):      # zero_grad(set_to_none=True) / a foreign .grad detaches all or nothing in practice
+            p = slots[i][0]
+            if p.requires_grad and p.grad is not views[i]:
+                return False
+        return True
+
+    def _grad_target(self, family: str):
+        """Where a backward function accumulates the parameter gradients, and whether it may STORE the weight slots of its family
+        (``'pass'``: W0/W1/W2, ``'cond'``: Cw) instead of read-modify-write.
+
+        ``.grad is None`` (``zero_grad(set_to_none=True)``, the first step) re-attaches the views and zeroes the buffer with one
+        memset; the first writer of each family in that same backward sweep may then store.  Attached views mean the caller
+        accumulates (or has zeroed them in place), so the kernels add."""
+        buf = self.grad_buffer()
+        if not self._grads_attached():
+            buf.zero_()
+            for (p, _, _, _), v in zip(self._slots, self._grad_views):
+                if p.requires_grad:
+                    if p.grad is not None and p.grad is not v:
+                        v.add_(p.grad)                   # a gradient accumulated elsewhere is carried over
+                    p.grad = v
+            self._grad_writes = {'pass': 0, 'cond': 0}
+            self._grad_zero_gen = self._fwd_gen
+        store = self._grad_zero_gen == self._fwd_gen and self._grad_writes[family] == 0
+        self._grad_writes[family] += 1
+        return buf, store
+
     def _flat_for_autograd(self, device):
         flat = self.flat_parameters(device)
-        params = [p for p, _, _, _ in self._slots]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _GatherFlat.apply(self, *params)
+        if torch.is_grad_enabled() and any(p.requires_grad for p, _, _, _ in self._slots):
+            self._fwd_gen += 1                       # a new forward: gradients written after it belong to a new backward sweep
+            return _FlatAnchor.apply(self._anchor, self)
         return flat
 
     def _use_kernels(self, x) -> bool:
         if x.is_cuda:
             if not self._kernel_ok:
-                raise _lib.MheError('this RealNVP configuration is outside the accelerated path; run it on CPU tensors '
-                                    'through the stock implementation or use the shipped configuration')
+                raise _lib.MheError('this RealNVP configuration is outside the accelerated path'
+                                    + ('' if self._mask_binary else ' (the coupling mask is not exactly {0,1})')
+                                    + '; run it on CPU tensors through the stock implementation or use the shipped configuration')
             return True
         return False
 
@@ -302,15 +397,15 @@ class RealNVP(nn.Module):
     def cond_projections(self, cond):
         """Hoisted ``c.{0,1}(cond)`` of all layers, (B, L*4*H); kernel path only."""
         flat = self._flat_for_autograd(cond.device)
-        return _CondFn.apply(cond.float(), flat, self._shape, self.packed_weights(cond.device))
+        return _CondFn.apply(cond.float(), flat, self._shape, self.packed_weights(cond.device), self)
 
     def _pass(self, inp, cond, direction, cp=None, images=None):
         flat = self._flat_for_autograd(inp.device)
         packed = self.packed_weights(inp.device)
         if cp is None:
-            cp = _CondFn.apply(cond.float(), flat, self._shape, packed)
+            cp = _CondFn.apply(cond.float(), flat, self._shape, packed, self)
             images = cond.shape[0]
-        return _FlowPassFn.apply(inp.float(), cp, flat, self.mask, self._shape, direction, images, packed)
+        return _FlowPassFn.apply(inp.float(), cp, flat, self.mask, self._shape, direction, images, packed, self)
 
     def forward_p(self, z, cond=None):
         """z -> x (``flows.py:210-217``)."""
@@ -393,8 +488,8 @@ class RealNVP(nn.Module):
         """
         flat = self._flat_for_autograd(z0.device)
         packed = self.packed_weights(z0.device)
-        cp = _CondFn.apply(feat.float(), flat, self._shape, packed)
-        x, logdet = _FlowPassFn.apply(z0.float(), cp, flat, self.mask, self._shape, 0, feat.shape[0], packed)
+        cp = _CondFn.apply(feat.float(), flat, self._shape, packed, self)
+        x, logdet = _FlowPassFn.apply(z0.float(), cp, flat, self.mask, self._shape, 0, feat.shape[0], packed, self)
         log_q = _StdNormalLogpFn.apply(z0.float(), -logdet)
         return x * self.scale, log_q
 

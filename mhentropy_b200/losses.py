@@ -111,14 +111,17 @@ class MHEntHead(nn.Module):
     """
 
     def __init__(self, q_z_giv_i_cfg: dict | None = None, mano_data: dict | None = None, image_size: int = 256,
-                 feat_dim: int = 512, entropy: bool = True):
+                 feat_dim: int = 512, entropy: bool = True, mano_dir: str = './mano/', synthetic_mano_seed: int | None = None):
+        """``mano_data``: MANO constants (``mano_assets.load_mano_pkl`` / ``synthetic_mano``); otherwise ``<mano_dir>/MANO_RIGHT.pkl``
+        is read as the reference does (``manolayer.py:61-65``).  A synthetic hand is used only when ``synthetic_mano_seed`` is given."""
         super().__init__()
         cfg = dict(dim=45, tsfm_on=feat_dim, kemb=False, jointN=21, h_dims=[512, 512], num_steps=6)   # CrossModalHand.py:67-69
         if q_z_giv_i_cfg:
             cfg.update(q_z_giv_i_cfg)
         self.q_z_giv_i = RealNVP(**cfg)
         self.mano_dec = ManoLayer(skeidx='RHD', flat_hand_mean=False, ncomps=45, use_pca=True, output_size=image_size,
-                                  mask_sz=64, mano_data=mano_data)                                     # network.py:360-363
+                                  mask_sz=64, mano_data=mano_data, MANO_dir=mano_dir,
+                                  synthetic_seed=synthetic_mano_seed)                                  # network.py:360-363
         self.det_head = nn.Sequential(nn.Linear(feat_dim, feat_dim), nn.ReLU(inplace=True), nn.Linear(feat_dim, 16))  # :380-383
         self.image_size = image_size
         self.entropy = entropy
@@ -186,10 +189,15 @@ class MHEntHead(nn.Module):
         else:
             N_quant = N
         B = feat.shape[0]
-        z = self._sample_q_z_giv_i(feat, N=N, temp=temp, z0=z0, z_det=z_det)
-        z = z.reshape(N, B, 61)
+        if N_quant < N and feat.is_cuda:
+            # log q of the samples falls out of the sampling pass itself (log N(z0) - sum s): no second, inverse flow pass
+            # (the reference runs one, network.py:866 -> :669; same value, SURVEY.md section 4 identity)
+            z, log_q = self._sample_q_z_giv_i(feat, N=N, temp=temp, z0=z0, z_det=z_det, return_log_q=True)
+            z, log_q = z.reshape(N, B, 61), log_q.reshape(N, -1)
+        else:
+            z = self._sample_q_z_giv_i(feat, N=N, temp=temp, z0=z0, z_det=z_det).reshape(N, B, 61)
+            log_q = self._reverse_log_q(z.flatten(0, 1), feat).reshape(N, -1) if N_quant < N else None
         if N_quant < N:
-            log_q = self._reverse_log_q(z.flatten(0, 1), feat).reshape(N, -1)
             from .metrics import topk_hypotheses
             idx = (topk_hypotheses(log_q, N_quant) if log_q.is_cuda else torch.topk(log_q, N_quant, dim=0)[1])[..., None].repeat(1, 1, 61)
             z = torch.gather(z, 0, idx)

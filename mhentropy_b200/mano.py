@@ -80,7 +80,7 @@ class ManoCore(nn.Module):
 
     def __init__(self, center_idx=9, flat_hand_mean=False, ncomps=45, side='right', mano_root='mano/models', use_pca=True,
                  root_rot_mode='axisang', joint_rot_mode='axisang', robust_rot=False, mano_data: dict | None = None,
-                 synthetic_seed: int = 0):
+                 synthetic_seed: int | None = None):
         super().__init__()
         if not (use_pca and ncomps == 45 and side == 'right' and root_rot_mode == 'axisang' and center_idx == 9):
             raise NotImplementedError('accelerated MANO path: use_pca=True, ncomps=45, right hand, axis-angle root, center_idx=9')
@@ -109,7 +109,11 @@ class ManoCore(nn.Module):
 
     def _consts(self, device) -> ManoConsts:
         """Pack the buffers into the kernel layouts (once per device; fp64 products for jt / js)."""
-        key = str(device)
+        # derived copies are keyed on the device AND on the buffers' identity / version counters: load_state_dict copies into the
+        # th_* buffers in place, and a stale jt / js / posedirs plane set would silently mix two hands
+        srcs = (self.th_selected_comps, self.th_hands_mean, self.th_v_template, self.th_shapedirs, self.th_posedirs,
+                self.th_J_regressor, self.th_weights)
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in srcs)
         if self._packed is None or self._packed[0] != key:
             d = lambda t: t.detach().double().cpu()  # noqa: E731
             jreg = d(self.th_J_regressor)
@@ -139,6 +143,10 @@ class ManoCore(nn.Module):
         self._packed = None
         return super()._apply(fn, *args, **kwargs)
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._packed = None                  # the kernels' derived constants follow the loaded buffers
+
     def forward(self, th_pose_coeffs, th_betas=None, th_trans=None, root_palm=None, share_betas=None):
         if th_trans is not None and bool(torch.as_tensor(th_trans).abs().sum() != 0):
             raise NotImplementedError('th_trans is outside the accelerated path')
@@ -152,10 +160,10 @@ class ManoLayer(nn.Module):
     """Wrapper equivalent to reference ``hand/ManoLayer.py:10-165``."""
 
     def __init__(self, MANO_dir='./mano/', flat_hand_mean=True, ncomps=45, use_pca=False, n_latent=None, skeidx='FreiHand',
-                 output_size=256, mask_sz=256, mano_data: dict | None = None):
+                 output_size=256, mask_sz=256, mano_data: dict | None = None, synthetic_seed: int | None = None):
         super().__init__()
         self.mano_layer = ManoCore(center_idx=9, flat_hand_mean=flat_hand_mean, ncomps=ncomps, side='right', mano_root=MANO_dir,
-                                   use_pca=use_pca, mano_data=mano_data)
+                                   use_pca=use_pca, mano_data=mano_data, synthetic_seed=synthetic_seed)
         self.Jreg = self.mano_layer.th_J_regressor
         self.n_latent = n_latent
         if n_latent is not None:

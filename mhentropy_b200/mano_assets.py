@@ -102,10 +102,15 @@ def load_mano_pkl(path: str) -> dict:
     return out
 
 
-def resolve_mano(mano_dir: str | None, seed: int = 0) -> tuple[dict, str]:
-    """Real constants when ``<mano_dir>/MANO_RIGHT.pkl`` exists, synthetic otherwise."""
+def resolve_mano(mano_dir: str | None, seed: int | None = None) -> tuple[dict, str]:
+    """Real constants from ``<mano_dir>/MANO_RIGHT.pkl`` (as the reference, ``manolayer.py:61-65``).  A random synthetic hand is
+    used ONLY when the caller asks for one (``seed`` given: tests, benchmarks): silently training on a made-up hand because an
+    asset path was wrong would be a quiet failure, so a missing asset raises."""
     if mano_dir:
         for cand in (os.path.join(mano_dir, 'MANO_RIGHT.pkl'), os.path.join(mano_dir, 'models', 'MANO_RIGHT.pkl')):
             if os.path.isfile(cand):
                 return load_mano_pkl(cand), cand
+    if seed is None:
+        raise FileNotFoundError(f'MANO_RIGHT.pkl not found under {mano_dir!r}: pass mano_data=..., or synthetic_seed=<int> for a '
+                                'synthetic MANO-shaped hand (tests / benchmarks only)')
     return synthetic_mano(seed), f'synthetic(seed={seed})'

@@ -39,3 +39,8 @@ class FlatAdam:
         check(lib().mhe_flow_adam_step(self.flow._shape, ptr(flat), ptr(dflat.contiguous()), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                        ptr(packed) if packed is not None else None, self.step_count, self.lr, self.betas[0], self.betas[1],
                                        self.eps, grad_scale, stream_ptr(dev)), 'mhe_flow_adam_step')
+        # the update went through raw pointers (no version counter moved): with the planes refreshed here the flow's cached set IS
+        # current - record that; without, force a re-pack before the next tensor-core pass
+        self.flow.mark_parameters_changed()
+        if packed is not None:
+            self.flow._packed_sig = self.flow._packed_signature(flat)

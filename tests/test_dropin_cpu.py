@@ -138,3 +138,87 @@ def test_load_reference_checkpoint(tmp_path):
     small = MHEntHead(q_z_giv_i_cfg=dict(num_steps=2), mano_data=synthetic_mano(0))
     with pytest.raises(KeyError):
         load_reference_checkpoint(small, {'encoderRGB': sd})
+
+
+def test_mask_handling_and_fused_limits():
+    """A user mask (reference flows.py:131 accepts any) must never run silently wrong: non-{0,1} masks are outside every kernel path,
+    and splits wider than the cluster-fused kernels' 24-dim exchange travel in the shape so the ABI routes them to the per-GEMM path."""
+    L = _lib.lib()
+    flow = RealNVP(dim=45, tsfm_on=512, h_dims=[512, 512], num_steps=6)
+    assert flow._kernel_ok and flow._shape.max_split == 23
+    m = torch.tensor([[0.] * 15 + [1.] * 30, [1.] * 15 + [0.] * 30] * 6)
+    wide = RealNVP(dim=45, tsfm_on=512, h_dims=[512, 512], num_steps=6, mask=m)
+    assert wide._kernel_ok and wide._shape.max_split == 30
+    # same flat layout / workspace API; the fused path (2 backward chunks) is only offered for the narrow split
+    assert L.mhe_flow_param_floats(wide._shape) == L.mhe_flow_param_floats(flow._shape)
+    assert L.mhe_flow_bwd_chunk_count(flow._shape, 640) == 2 and L.mhe_flow_bwd_chunk_count(wide._shape, 640) == 1
+    assert L.mhe_flow_param_floats(_lib.FlowShape(45, 512, 512, 12, 46)) == 0            # max_split > dim is invalid
+    frac = RealNVP(dim=45, tsfm_on=512, h_dims=[512, 512], num_steps=6, mask=m * 0.5)
+    assert not frac._kernel_ok and frac._shape is None
+    # ... and it still evaluates with the reference's float-mask semantics on CPU tensors
+    x = frac.forward_p(torch.randn(3, 45), cond=torch.randn(3, 512))
+    assert torch.isfinite(x).all()
+    # a checkpoint carrying another mask updates the routing information
+    flow.load_state_dict(wide.state_dict())
+    assert flow._shape.max_split == 30
+
+
+def test_mano_assets_are_explicit(tmp_path):
+    """No silent synthetic hand: a missing MANO_RIGHT.pkl raises unless a synthetic seed is asked for."""
+    with pytest.raises(FileNotFoundError):
+        ManoLayer(MANO_dir=str(tmp_path), flat_hand_mean=False, ncomps=45, use_pca=True)
+    layer = ManoLayer(MANO_dir=str(tmp_path), flat_hand_mean=False, ncomps=45, use_pca=True, synthetic_seed=0)
+    assert layer.mano_layer.mano_source == 'synthetic(seed=0)'
+    # derived kernel constants follow a state-dict load (they are keyed on the buffers' versions)
+    other = ManoLayer(flat_hand_mean=False, ncomps=45, use_pca=True, mano_data=synthetic_mano(1))
+    layer.mano_layer._packed = ('stale',)
+    layer.load_state_dict(other.state_dict())
+    assert layer.mano_layer._packed is None
+    assert torch.equal(layer.mano_layer.th_v_template, other.mano_layer.th_v_template)
+
+
+def test_reference_mhent_runs_with_the_dropin_flow(golden_dir):
+    """INTEGRATION.md section A, executed: the reference's own ``network.MHEnt`` (imported unmodified) with ``RealNVP`` bound to
+    ``mhentropy_b200.flows.RealNVP`` reproduces the golden ``get_loss`` outputs and gradients that the unmodified reference produced
+    (tests/golden/mhent_small.npz).  CPU tensors: the drop-in's stock-op branch; the kernels' parity is the -m gpu suite."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip('needs /root/reference (build container only)')
+    import sys
+    fx = dict(np.load(os.path.join(golden_dir, 'mhent_small.npz')))
+    mano = synthetic_mano(0)
+    cfg = dict(dim=45, tsfm_on=32, kemb=False, jointN=21, h_dims=[64, 64], num_steps=2)
+    network = ref_shim.import_network(mano)
+    ref_flows = sys.modules['flows']
+    saved = (network.RealNVP, ref_flows.RealNVP)
+    network.RealNVP = ref_flows.RealNVP = RealNVP          # the "changed import"
+    try:
+        model = ref_shim.build_mhent(mano, seed=int(fx['seed']), flow_cfg=cfg)
+        assert type(model.q_z_giv_i) is RealNVP
+        model.q_z_giv_i.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in fx.items() if k.startswith('w/')})
+
+        class _ZDet(torch.nn.Module):      # stands in for det_head exactly as tests/golden/make_golden.py does
+            def __init__(self, z):
+                super().__init__()
+                self.z = torch.nn.Parameter(z.clone())
+
+            def forward(self, feat):
+                return self.z
+
+        model.det_head = _ZDet(torch.from_numpy(fx['z_det']))
+        B = fx['feat'].shape[0]
+        y = {'crop_uv': torch.from_numpy(fx['crop_uv']), 'vis': torch.from_numpy(fx['vis']), 'st': torch.zeros(B, 3), 'image': np.zeros(1)}
+        with ref_shim.cpu_mode():
+            feat = torch.from_numpy(fx['feat']).clone().requires_grad_(True)
+            torch.manual_seed(int(fx['seed']) + 2)
+            out = model.get_loss(feat, y, mods=['uv'])
+            (-out['log_p']).mean().backward()
+        rel = lambda a, b: float(np.abs(a.detach().numpy() - b).max() / (np.abs(b).max() + 1e-30))  # noqa: E731
+        assert rel(out['log_p'], fx['log_p']) < 1e-5
+        assert rel(out['h_q_z_giv_i'], fx['h_q_z_giv_i']) < 1e-5
+        assert rel(feat.grad, fx['dfeat']) < 1e-4
+        assert rel(model.det_head.z.grad, fx['dz_det']) < 1e-4
+        for k, p in model.q_z_giv_i.named_parameters():
+            assert rel(p.grad, fx['g/' + k]) < 1e-3, k
+    finally:
+        network.RealNVP, ref_flows.RealNVP = saved

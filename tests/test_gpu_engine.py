@@ -57,7 +57,11 @@ def test_engine_matches_autograd_path_and_oracle(use_graph, B, S, precision):
     ref = lo.reverse_kld(sdg, mo.mano_constants(mano), featc, batch['z_det'], batch['z0'], batch['crop_uv'], batch['vis'], S)
     lo.mhent_loss(ref['log_p']).backward()
     assert rel(eng.log_p, ref['log_p']) < 1e-4
-    assert rel(eng.dfeat, featc.grad) < 5e-3
+    # gradient bar by precision: 1e-3 outright on the exact path; kink-aware on the tensor-core path (tests/_gradcheck.py)
+    from _gradcheck import kink_aware_ok
+    ok, _, n_cross = kink_aware_ok(eng.dfeat, featc.grad)
+    assert ok
+    assert rel(eng.dfeat, featc.grad) < (1e-3 if (precision == 'fp32' or n_cross == 0) else 5e-3)
     # mesh is materialised in the engine exactly as the reference's get_loss does
     dec = mo.mano_wrapper_forward(mo.mano_constants(mano), ref['z'][:, :48].detach(), ref['z'][:, 48:58].detach())
     assert (eng.verts.cpu() - dec['mesh']).abs().max() < 1e-2
@@ -229,3 +233,18 @@ def test_flat_adam_matches_torch_adam_and_refreshes_planes():
     nb = L.mhe_flow_packed_bytes(shape)
     a, b = packed[:nb].view(torch.int16), fresh[:nb].view(torch.int16)
     assert int((a != b).sum()) == 0
+
+
+def test_data_parallel_engine_equals_single_process_step():
+    """TrainStep + exchange_gradients on 2 GPUs == one TrainStep on the concatenated batch (global-batch-mean loss and gradients).
+    Needs two GPUs on the box (the driver's GPU tier has one: it is run with `gpurun --gpus 2`, log under profiles/)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29533', os.path.join(root, 'tools', 'check_engine_dp.py')], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and 'check_engine_dp: OK' in r.stdout

@@ -118,22 +118,24 @@ def test_fused_backward_full_bench_size(flow_and_sd):
     assert relerr(logq, logq_ref) < 1e-4
     assert fro(z0c.grad, dz_ref) < max(1e-3, 2 * fro(dz_32, dz_ref))
     assert fro(featc.grad, df_ref) < max(1e-3, 2 * fro(df_32, df_ref))
-    # Parameter gradients.  Gradients travel as bfloat16 split planes (16 significant bits), so a tensor whose
-    # gradient is a strongly cancelling sum over the 640 rows (late layers' first-layer weights) can sit a little above 1e-3 of its
-    # own (small) norm; the bar is applied to the flat gradient as a whole - what the optimizer and the all-reduce see.
-    worst, worst_name, worst_floor, n_over, num, num32, den = 0.0, '', 0.0, 0, 0.0, 0.0, 0.0
+    # Parameter gradients.  The bar applies to the flat gradient as a whole - what the optimizer and the all-reduce see.  Single
+    # tensors can sit above 1e-3 of their own norm where a leaky-ReLU crossing moved one row's contribution (tests/_gradcheck.py): the
+    # reference's own fp32 arithmetic shows the same on this very input (measured here: `n_over32` tensors), so the per-tensor
+    # allowance is tied to that floor instead of a free constant.
+    worst, worst_name, worst_floor, n_over, n_over32, num, num32, den = 0.0, '', 0.0, 0, 0, 0.0, 0.0, 0.0
     for name, p in flow.named_parameters():
         e, floor = fro(p.grad, gp_ref[name]), fro(gp_32[name], gp_ref[name])
         if e > worst:
             worst, worst_name = e, name
         worst_floor = max(worst_floor, floor)
         n_over += e > 1e-3
+        n_over32 += floor > 1e-3
         num += float((p.grad.detach().cpu().double() - gp_ref[name]).pow(2).sum())
         num32 += float((gp_32[name].double() - gp_ref[name]).pow(2).sum())
         den += float(gp_ref[name].pow(2).sum())
     flat_err, flat_floor = (num / den) ** 0.5, (num32 / den) ** 0.5
     assert flat_err < 1e-3, flat_err                      # north star: gradients within 1e-3 relative
-    assert worst < 1e-2, (worst_name, worst)
-    assert n_over <= 60, n_over
+    assert worst < max(2e-3, 2 * worst_floor), (worst_name, worst, worst_floor)
+    assert n_over <= max(8, 6 * n_over32), (n_over, n_over32)
     print(f'fused fwd+bwd B=64 S=10: flat-gradient error {flat_err:.2e} (reference fp32 vs fp64: {flat_floor:.2e}); worst tensor {worst_name} {worst:.2e} (reference fp32 vs fp64 on the same '
-          f'data: {worst_floor:.2e}); {n_over} of 240 tensors above 1e-3')
+          f'data: {worst_floor:.2e}); {n_over} of 240 tensors above 1e-3 (reference fp32: {n_over32})')

@@ -204,12 +204,20 @@ def test_mhent_loss_against_golden(golden_dir, name, fused, precision):
     assert relerr(out['th_norm'], fx['th_norm']) < 1e-4
     assert relerr(loss, fx['loss']) < 1e-4
     loss.backward()
-    assert relerr(feat.grad, fx['dfeat']) < 5e-3
-    assert relerr(z_det.grad, fx['dz_det']) < 5e-3
+    # Gradient bar, by precision (tests/_gradcheck.py): the exact-fp32 path meets 1e-3 outright; on the tensor-core path a leaky-ReLU
+    # crossing (visible as ONE image's dfeat row off by more than 1e-3) may move that image's share of the gradients - every other image
+    # must meet the bar, and without a crossing everything does.
+    from _gradcheck import kink_aware_ok
+    ok, med, n_cross = kink_aware_ok(feat.grad, T(fx['dfeat']))
+    bar = 1e-3 if (precision == 'fp32' or n_cross == 0) else 5e-3
+    print(f'{precision}: dfeat max-rel {relerr(feat.grad, fx["dfeat"]):.2e} (median image {med:.2e}, {n_cross} images with a crossing); bar {bar:g}')
+    assert ok
+    assert relerr(feat.grad, fx['dfeat']) < bar
+    assert relerr(z_det.grad, fx['dz_det']) < 1e-3
     grads = dict(head.q_z_giv_i.named_parameters())
     if small:
         worst = max(relerr(p.grad, fx['g/' + k]) for k, p in grads.items())
-        assert worst < 5e-3, worst
+        assert worst < bar, worst
         s = head.sample(T(fx['feat']), N=3, temp=0.8, z0=T(fx['z0_sample']), z_det=T(fx['z_det']))
         for k in ('th_bt', 'logs_t', 'xyz', 'uv', 'verts'):
             assert relerr(s[k], fx['sample/' + k]) < 1e-4, k
