@@ -149,6 +149,10 @@ int mhe_flow_cond_wgrad(mhe_flow_shape s, const float* feat, const float* dcp, i
  * chunk c's layers.  After an asynchronous mhe_flow_pass_cond_bwd (mhe_flow_set_async bit 0), mhe_flow_join_chunk(stream, c) makes
  * `stream` wait until EVERY gradient of those layers (coupling and conditioning weights and biases) is complete, so that the caller can
  * all-reduce that part of dparams while the remaining chunks still run.  mhe_flow_join() still ends the pass.                         */
+/* 1 when a tensor-core pass over R rows runs on the cluster-fused kernels (production shape, R <= MHE_FUSED_MAX_ROWS, splits <= 24 dims),
+ * 0 when it runs GEMM by GEMM.  Matters to callers that use mhe_flow_set_async bit 1: only the fused path STORES its weight gradients;
+ * the per-GEMM path always accumulates (its long contractions are split over CTAs), so its dparams must be zeroed by the caller.        */
+int mhe_flow_pass_is_fused(mhe_flow_shape s, int R);
 int mhe_flow_bwd_chunk_count(mhe_flow_shape s, int R);
 int mhe_flow_bwd_chunk_layers(mhe_flow_shape s, int R, int direction, int chunk, int* first_layer, int* layers);
 int mhe_flow_join_chunk(void* stream, int chunk);

@@ -58,6 +58,7 @@ _SIGNATURES = {
     'mhe_flow_grad_sqnorm': (c_int, [FlowShape, _P, _P, _P]),
     'mhe_flow_adam_step': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                    ctypes.c_double, _P]),
+    'mhe_flow_pass_is_fused': (c_int, [FlowShape, c_int]),
     'mhe_flow_bwd_chunk_count': (c_int, [FlowShape, c_int]),
     'mhe_flow_bwd_chunk_layers': (c_int, [FlowShape, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     'mhe_flow_join_chunk': (c_int, [_P, c_int]),

@@ -432,6 +432,11 @@ int mhe_flow_cond_wgrad(mhe_flow_shape s, const float* feat, const float* dcp, i
     return tcflow::cond_wgrad(L, feat, dcp, Bt, dparams, workspace, (cudaStream_t)stream);
 }
 
+int mhe_flow_pass_is_fused(mhe_flow_shape s, int R) {
+    if (!valid_shape(s) || R <= 0) return 0;
+    FlowLayout L(s);
+    return tcflow::supported(L) && fused::supported(L, R) ? 1 : 0;
+}
 int mhe_flow_bwd_chunk_count(mhe_flow_shape s, int R) {
     if (!valid_shape(s)) return 1;
     FlowLayout L(s);

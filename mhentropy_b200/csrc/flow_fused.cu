@@ -107,30 +107,6 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {   // 64 co
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// 8 fp32 -> 8 hi + 8 lo 16-bit values packed as two uint4 (packed two-at-a-time conversions: this runs in every epilogue thread)
-template <bool F16>
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float a = v[2 * j], b = v[2 * j + 1];
-        if (F16) {
-            const __half2 hh = __floats2half2_rn(a, b);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
-        } else {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
-            const float2 hf = __bfloat1622float2(hh);
-            const __nv_bfloat162 ll = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
-            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

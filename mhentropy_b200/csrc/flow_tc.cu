@@ -32,9 +32,20 @@ __device__ __forceinline__ void store_planes32(bf16* hi_ptr, bf16* lo_ptr, const
 
 // ---- epilogues (one call per thread per 32-column chunk of its accumulator row) -----------------------
 struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[batch][plane][row][col]
-    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false, kTile8 = true;
     bf16* out; long ld; long plane_stride; long batch_stride;
     const float* cp; long cp_ld; long cp_off; long cp_bstride; int B;
+    __device__ void tile8(int b, int, int row, int col, float* v, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
+        const float4* c = reinterpret_cast<const float4*>(cp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col);
+        const float4 t0 = __ldg(c), t1 = __ldg(c + 1);
+        v[0] = lrelu(v[0] + t0.x); v[1] = lrelu(v[1] + t0.y); v[2] = lrelu(v[2] + t0.z); v[3] = lrelu(v[3] + t0.w);
+        v[4] = lrelu(v[4] + t1.x); v[5] = lrelu(v[5] + t1.y); v[6] = lrelu(v[6] + t1.z); v[7] = lrelu(v[7] + t1.w);
+        uint4 hi, lo;
+        split8<true>(v, hi, lo);
+        bf16* p = out + (long)b * batch_stride + (long)row * ld + col;
+        *reinterpret_cast<uint4*>(p) = hi;
+        *reinterpret_cast<uint4*>(p + plane_stride) = lo;
+    }
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
         const float4* c = reinterpret_cast<const float4*>(cp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col0);
 #pragma unroll
@@ -65,8 +76,23 @@ struct EpiOutHead {   // st[batch][row][col] = batch == 0 ? tanh(acc + b2) : acc
     }
 };
 struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes.  (dcp = sum over the hypotheses of an image: dcp_from_row_planes_kernel)
-    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false, kTile8 = true;
     bf16* out; const bf16* act_hi; long ld; long plane_stride; long batch_stride; long act_plane_stride; long act_batch_stride;
+    __device__ void tile8(int b, int, int row, int col, float* v, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
+        const uint4 t = *reinterpret_cast<const uint4*>(act_hi + (long)b * act_batch_stride + (long)row * ld + col);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // half > 0  <=>  sign bit clear and magnitude non-zero (the hi plane carries the activation's sign)
+            const uint32_t e0 = w[i] & 0xFFFFu, e1 = w[i] >> 16;
+            v[2 * i] *= ((e0 & 0x8000u) == 0 && (e0 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
+            v[2 * i + 1] *= ((e1 & 0x8000u) == 0 && (e1 & 0x7FFFu) != 0) ? 1.f : kLeakySlope;
+        }
+        uint4 hi, lo;
+        split8<false>(v, hi, lo);
+        const long off = (long)b * batch_stride + (long)row * ld + col;
+        *reinterpret_cast<uint4*>(out + off) = hi;
+        *reinterpret_cast<uint4*>(out + off + plane_stride) = lo;
+    }
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape&) const {
         const uint4* a = reinterpret_cast<const uint4*>(act_hi + (long)b * act_batch_stride + (long)row * ld + col0);
 #pragma unroll
@@ -598,6 +624,10 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
     const long RH = (long)R * L.H, RD = (long)R * kDp;
     const float* g = dout;
     const int ks = R >= 8192 ? 4 : 1;   // wgrad contracts over the rows: split K once it is long
+    // the two thin gradients (dW0, dW2: 512 x 64 outputs per net = 8 tiles in all) need a deeper split to occupy the chip: as many
+    // splits as divide the k-blocks evenly, up to 16 (128 CTAs)
+    int ks_thin = ks;
+    if (R >= 2048) { const int kb = cdiv(R, BK); for (int c = 16; c >= 1; c >>= 1) if (kb % c == 0 && kb / c >= 4) { ks_thin = c; break; } }
     Aux& aux = aux_ctx();
     const bool fork = aux.ok && L.L <= 64;
     cudaStream_t wstream = fork ? aux.stream[0] : stream, wstream2 = fork ? aux.stream[1] : stream;
@@ -663,13 +693,13 @@ int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const
             MHE_TRY((gemm<true, true, false>(dh1, a0, s, e, wstream, "tc wgrad W1")));
         }
         {   // dW0 [out][d] += dh0^T xm
-            GemmShape s{L.H, kDp, R, 2, ks, 1, 0};
-            EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, ks > 1};
+            GemmShape s{L.H, kDp, R, 2, ks_thin, 1, 0};
+            EpiWgrad e{dblk + L.oW0, L.D, (long)L.blk, L.D, ks_thin > 1};
             MHE_TRY((gemm<true, true, false>(dh0, xm, s, e, wstream2, "tc wgrad W0")));
         }
         {   // dW2 [d][h] += dpre^T a1, computed as (a1^T dpre)[h][d] and stored transposed
-            GemmShape s{L.H, kDp, R, 2, ks, 1, 1};
-            EpiWgradT e{dblk + L.oW2, L.H, (long)L.blk, L.D, ks > 1};
+            GemmShape s{L.H, kDp, R, 2, ks_thin, 1, 1};
+            EpiWgradT e{dblk + L.oW2, L.H, (long)L.blk, L.D, ks_thin > 1};
             MHE_TRY((gemm<true, true, false>(a1, dpreK, s, e, wstream2, "tc wgrad W2")));
         }
         if (fork) {

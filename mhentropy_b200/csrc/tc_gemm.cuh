@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace mhe {
@@ -51,6 +52,41 @@ template <bool F16>
 __device__ __forceinline__ float from16(uint16_t u) {
     if (F16) return __half2float(__ushort_as_half(u));
     return __bfloat162float(__ushort_as_bfloat16(u));
+}
+#endif
+
+// Epilogue mode kTile8 (optional member of an Epi): the warp's 32 x 32 accumulator chunk is transposed through shared memory and handed
+// to Epi::tile8(batch, split, row, col, v[8]) as 8 consecutive columns of one row per lane, 4 lanes per row, 8 rows per pass.  Epilogues
+// that read / write ROW-MAJOR 16-bit planes then touch 64 contiguous bytes per row and instruction (8 memory transactions per warp
+// instruction) instead of 32 rows x 16 bytes, 1 KB apart (32 transactions): the plane-writing GEMMs of the long-batch flow path are
+// bound by exactly that.
+template <class E, class = void> struct epi_tile8 : std::false_type {};
+template <class E> struct epi_tile8<E, std::void_t<decltype(E::kTile8)>> : std::bool_constant<E::kTile8> {};
+
+#if defined(__CUDACC__)
+// 8 fp32 -> 8 hi + 8 lo 16-bit values packed as two uint4 (packed two-at-a-time conversions)
+template <bool F16>
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        if (F16) {
+            const __half2 hh = __floats2half2_rn(a, b);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        } else {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 #endif
 
@@ -172,7 +208,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[NSmax], bar_empty[NSmax], bar_accum;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_stage[Epi::kStaged ? 4 : 1][32][33];   // epilogue transpose buffers, one per epilogue warp
+    __shared__ float s_stage[(Epi::kStaged || epi_tile8<Epi>::value) ? 4 : 1][32][33];   // epilogue transpose buffers, one per epilogue warp
 
     pdl_launch_dependents();   // let the next kernel of the chain start its prologue; it blocks in pdl_wait()
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -278,6 +314,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
             if (n0 + c0 >= g.N) continue;                  // warp-uniform
+            if constexpr (epi_tile8<Epi>::value) {
+                float (*st)[33] = s_stage[warp - 2];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) st[lane][j] = v[j];
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = i * 8 + (lane >> 2), cl = (lane & 3) * 8;
+                    float w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) w[k] = st[rl][cl + k];
+                    if (m0 + q * 32 + rl < g.M) epi.tile8(batch, split, m0 + q * 32 + rl, n0 + c0 + cl, w, g);
+                }
+                __syncwarp();
+            } else
             if constexpr (Epi::kDirect) {
                 // lane = accumulator row: each thread owns 32 consecutive columns (vector stores)
                 if (row < g.M) epi(batch, split, row, n0 + c0, v, g);
@@ -345,7 +396,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[NSmax], bar_empty[NSmax], bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_stage[Epi::kStaged ? 8 : 1][32][33];     // one transpose buffer per epilogue warp
+    __shared__ float s_stage[(Epi::kStaged || epi_tile8<Epi>::value) ? 8 : 1][32][33];     // one transpose buffer per epilogue warp
 
     pdl_launch_dependents();
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -472,6 +523,21 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                     mbar_arrive_cta(smem_u32(&bar_acc_empty[buf]));
                 }
                 if (T.n0 + c0 >= g.N) continue;
+                if constexpr (epi_tile8<Epi>::value) {
+                    float (*st)[33] = s_stage[warp - 2];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) st[lane][j] = v[j];
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rl = i * 8 + (lane >> 2), cl = (lane & 3) * 8;
+                        float w[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) w[k] = st[rl][cl + k];
+                        if (T.m0 + qd * 32 + rl < g.M) epi.tile8(T.batch, T.split, T.m0 + qd * 32 + rl, T.n0 + c0 + cl, w, g);
+                    }
+                    __syncwarp();
+                } else
                 if constexpr (Epi::kDirect) {
                     if (row < g.M) epi(T.batch, T.split, row, T.n0 + c0, v, g);
                 }

@@ -83,6 +83,9 @@ class TrainStep:
         self.djtr, self.dz, self.dlog_q = f(R, 21, 3), f(R, 61), f(R)
         self.dx, self.dz_det, self.dz0, self.dfeat = f(R, D), f(B, 16), f(R, D), f(B, flow.cond_dim)
         self.tc = flow.precision != 'fp32'
+        # only the cluster-fused path STORES its weight gradients (mhe_flow_set_async bit 1); the per-GEMM path (long batches, wide
+        # masks) accumulates, so the whole gradient buffer is zeroed for it every step
+        self.fused = bool(self.tc and L.mhe_flow_pass_is_fused(self.shape, R))
         self.saved = torch.empty(L.mhe_flow_saved_bytes(self.shape, R, int(self.tc)), dtype=torch.uint8, device=dev)
         self.packed = None
         if self.tc:
@@ -162,8 +165,10 @@ class TrainStep:
                     self.side.wait_stream(self.side3)      # the forward-critical conversions get the memory system first
                     # bfloat16 planes (read by the backward only)
                     check(L.mhe_flow_pack_weights(shape, ptr(self.flat), pk, 2, _lib.stream_ptr(self.dev)), 'pack_weights')
-                # the weight slots of dflat are stored (not accumulated) by the backward: only the bias slots need zeroing
-                check(L.mhe_flow_zero_bias_grads(shape, ptr(self.dflat), _lib.stream_ptr(self.dev)), 'zero_bias_grads')
+                if self.fused:   # the weight slots of dflat are stored (not accumulated) by the backward: only the bias slots need zeroing
+                    check(L.mhe_flow_zero_bias_grads(shape, ptr(self.dflat), _lib.stream_ptr(self.dev)), 'zero_bias_grads')
+                else:
+                    self.dflat.zero_()
                 self.dcp.zero_()
                 self.dfeat.zero_()
         check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
@@ -228,7 +233,7 @@ class TrainStep:
         #  bit 2: so was dfeat)
         if self.tc and self.prepare_ahead:
             torch.cuda.current_stream(self.dev).wait_stream(self.side5)
-        flags = (7 if self.tc else 3) | (8 if self.prepared else 0) | (16 if self.factored_exchange else 0)
+        flags = ((7 if self.fused else 5) if self.tc else 3) | (8 if self.prepared else 0) | (16 if self.factored_exchange else 0)
         check(L.mhe_flow_set_async(flags), 'set_async')
         try:
             if self.tc and self.pipelined_cond_bwd:

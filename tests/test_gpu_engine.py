@@ -248,3 +248,32 @@ def test_data_parallel_engine_equals_single_process_step():
                         '--master-port', '29533', os.path.join(root, 'tools', 'check_engine_dp.py')], capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and 'check_engine_dp: OK' in r.stdout
+
+
+def test_engine_long_batch_replay_matches_autograd_path():
+    """Above the cluster-fused row limit the engine runs the per-GEMM path, whose weight gradients ACCUMULATE (split contractions): the
+    step must zero the whole gradient buffer itself, or a replayed step would add to the previous one (found in round 2)."""
+    head = MHEntHead(mano_data=synthetic_mano(0))
+    head.q_z_giv_i.load_state_dict(fo.init_state_dict(seed=0))
+    head.q_z_giv_i.precision = 'bf16x3'
+    head = head.to(DEV)
+    B, S = 66, 65
+    devb = {k: v.to(DEV) for k, v in synthetic_batch(B, S, seed=17).items()}
+    eng = TrainStep(head, B, S, DEV, want_verts=False, use_graph=True)
+    assert not eng.fused
+    eng.load(**devb)
+    for _ in range(3):
+        loss = eng.run()
+    torch.cuda.synchronize()
+    feat = devb['feat'].clone().requires_grad_(True)
+    z_det = devb['z_det'].clone().requires_grad_(True)
+    for p in head.parameters():
+        p.requires_grad_(True)
+    head.zero_grad(set_to_none=True)
+    out = head.get_loss(feat, {'crop_uv': devb['crop_uv'], 'vis': devb['vis']}, z0=devb['z0'], z_det=z_det, N=S)
+    (-out['log_p']).mean().backward()
+    assert rel(loss, (-out['log_p']).mean()) < 1e-6
+    assert rel(eng.dfeat, feat.grad) < 1e-4 and rel(eng.dz_det, z_det.grad) < 1e-4
+    g_eng = eng.flow_grads()
+    for k, p in head.q_z_giv_i.named_parameters():
+        assert rel(g_eng[k], p.grad) < 1e-4, k
