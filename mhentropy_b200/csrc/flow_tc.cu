@@ -35,9 +35,13 @@ struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[ba
     static constexpr bool kDirect = true, kStaged = false, kRmw = false, kTile8 = true;
     bf16* out; long ld; long plane_stride; long batch_stride;
     const float* cp; long cp_ld; long cp_off; long cp_bstride; int B;
-    __device__ void tile8(int b, int, int row, int col, float* v, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
+    struct Pre { float4 a, b; };                         // the row's 8 conditioning terms, loaded ahead of the accumulator
+    __device__ void pre8(int b, int row, int col, Pre& p) const {
         const float4* c = reinterpret_cast<const float4*>(cp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col);
-        const float4 t0 = __ldg(c), t1 = __ldg(c + 1);
+        p.a = __ldg(c); p.b = __ldg(c + 1);
+    }
+    __device__ void tile8(int b, int, int row, int col, float* v, const Pre& pr, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
+        const float4 t0 = pr.a, t1 = pr.b;
         v[0] = lrelu(v[0] + t0.x); v[1] = lrelu(v[1] + t0.y); v[2] = lrelu(v[2] + t0.z); v[3] = lrelu(v[3] + t0.w);
         v[4] = lrelu(v[4] + t1.x); v[5] = lrelu(v[5] + t1.y); v[6] = lrelu(v[6] + t1.z); v[7] = lrelu(v[7] + t1.w);
         uint4 hi, lo;
@@ -78,8 +82,12 @@ struct EpiOutHead {   // st[batch][row][col] = batch == 0 ? tanh(acc + b2) : acc
 struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes.  (dcp = sum over the hypotheses of an image: dcp_from_row_planes_kernel)
     static constexpr bool kDirect = true, kStaged = false, kRmw = false, kTile8 = true;
     bf16* out; const bf16* act_hi; long ld; long plane_stride; long batch_stride; long act_plane_stride; long act_batch_stride;
-    __device__ void tile8(int b, int, int row, int col, float* v, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
-        const uint4 t = *reinterpret_cast<const uint4*>(act_hi + (long)b * act_batch_stride + (long)row * ld + col);
+    struct Pre { uint4 a; };                             // hi plane of the 8 saved activations (their signs)
+    __device__ void pre8(int b, int row, int col, Pre& p) const {
+        p.a = __ldg(reinterpret_cast<const uint4*>(act_hi + (long)b * act_batch_stride + (long)row * ld + col));
+    }
+    __device__ void tile8(int b, int, int row, int col, float* v, const Pre& pr, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
+        const uint4 t = pr.a;
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {   // half > 0  <=>  sign bit clear and magnitude non-zero (the hi plane carries the activation's sign)
@@ -341,6 +349,10 @@ static PlaneTensor pt(const bf16* base, int cols, int rows, long pitch, long pla
 template <bool A_MN, bool B_MN, bool F16, class Epi>
 static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const Epi& e, cudaStream_t s, const char* what) {
     const long ctas128 = (long)cdiv(g.M, BM) * cdiv(g.N, 128) * g.batches * g.ksplit;
+    // 128 x 256 tiles for the long contractions: the 128 x 128 tile streams 64 KB of operand planes per 64-deep k-block, more than an
+    // SM ingests from L2 in the 768 tensor cycles the block's three products take; the wider tile moves 25 % fewer bytes per flop
+    static const bool bn256 = [] { const char* e = getenv("MHE_TC_BN256"); return e ? atoi(e) != 0 : true; }();
+    if (bn256 && g.N % 256 == 0 && g.K >= 256 && ctas128 >= 2 * 148) return launch_tc_gemm<256, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
     if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
     return launch_tc_gemm<64, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
 }

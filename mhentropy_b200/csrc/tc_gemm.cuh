@@ -62,6 +62,10 @@ __device__ __forceinline__ float from16(uint16_t u) {
 // bound by exactly that.
 template <class E, class = void> struct epi_tile8 : std::false_type {};
 template <class E> struct epi_tile8<E, std::void_t<decltype(E::kTile8)>> : std::bool_constant<E::kTile8> {};
+// a tile8 epilogue names the register blob of its prefetched global operand: E::Pre, filled by E::pre8(batch, row, col, Pre&)
+struct EpiNoPre {};
+template <class E, class = void> struct epi_pre_type { typedef EpiNoPre type; };
+template <class E> struct epi_pre_type<E, std::void_t<typename E::Pre>> { typedef typename E::Pre type; };
 
 #if defined(__CUDACC__)
 // 8 fp32 -> 8 hi + 8 lo 16-bit values packed as two uint4 (packed two-at-a-time conversions)
@@ -121,6 +125,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): issued a few k-blocks ahead of the loads proper, it turns the HBM
+// latency of streamed operands into an L2 hit by the time the ring slot is free
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -325,7 +335,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     float w[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) w[k] = st[rl][cl + k];
-                    if (m0 + q * 32 + rl < g.M) epi.tile8(batch, split, m0 + q * 32 + rl, n0 + c0 + cl, w, g);
+                    if (m0 + q * 32 + rl < g.M) {
+                        typename Epi::Pre pre;
+                        epi.pre8(batch, m0 + q * 32 + rl, n0 + c0 + cl, pre);
+                        epi.tile8(batch, split, m0 + q * 32 + rl, n0 + c0 + cl, w, pre, g);
+                    }
                 }
                 __syncwarp();
             } else
@@ -388,7 +402,7 @@ int stages_for(const char* what, int requested, int max_stages);
 template <int BN, bool A_MN, bool B_MN, int NPAIR, bool F16, class Epi>
 __global__ void __launch_bounds__(kThreadsP, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi,
-                          int tiles_n, int tiles_m, int tiles_total) {
+                          int tiles_n, int tiles_m, int tiles_total, int l2_prefetch_distance) {
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
     using Plan = SmemPlan<BN, NPL>;
     constexpr int NSmax = Plan::kStages;
@@ -441,9 +455,41 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (warp == 0) {
         if (lane == 0) {
             uint32_t q = 0;
+            // Optional (MHE_TC_L2_PREFETCH=<k-blocks>, default off): prefetch each k-block into L2 `pf_dist` k-blocks ahead of its ring
+            // slot, across tile boundaries.  Measured on the long-batch flow GEMMs (tensor pipe 56 % active): 3-7 % SLOWER at distance
+            // 4 and 8 - the operands are not what the MMAs wait for; kept as a diagnostic switch.
+            const int pf_dist = l2_prefetch_distance;
+            auto prefetch_kb = [&](const Tile& P, int i) {
+                const int k0 = (P.kb_begin + i % P.nkb1) * BK;
+                const int bsrc = P.batch * g.kfold + i / P.nkb1;
+#pragma unroll
+                for (int p = 0; p < NPL; ++p) {
+                    if (!A_MN) tma_prefetch_4d(&mapA, k0, P.m0, p, bsrc * g.a_batch_mul);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_prefetch_4d(&mapA, P.m0 + 64 * j, k0, p, bsrc * g.a_batch_mul);
+                    }
+                    if (!B_MN) tma_prefetch_4d(&mapB, k0, P.n0, p, bsrc * g.b_batch_mul);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_prefetch_4d(&mapB, P.n0 + 64 * j, k0, p, bsrc * g.b_batch_mul);
+                    }
+                }
+            };
+            if (pf_dist > 0 && (int)blockIdx.x < tiles_total) {      // the first tile's leading k-blocks
+                const Tile T0 = tile_of(blockIdx.x);
+                for (int i = 0; i < pf_dist && i < T0.nkb; ++i) prefetch_kb(T0, i);
+            }
             for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
                 const Tile T = tile_of(t);
+                const bool has_next = t + (int)gridDim.x < tiles_total;
+                Tile Tn = T;
+                if (pf_dist > 0 && has_next) Tn = tile_of(t + gridDim.x);
                 for (int i = 0; i < T.nkb; ++i, ++q) {
+                    if (pf_dist > 0) {
+                        if (i + pf_dist < T.nkb) prefetch_kb(T, i + pf_dist);
+                        else if (has_next && i + pf_dist - T.nkb < Tn.nkb) prefetch_kb(Tn, i + pf_dist - T.nkb);
+                    }
                     const int s = q % NS;
                     mbar_wait(smem_u32(&bar_empty[s]), ((q / NS) & 1) ^ 1);
                     const uint32_t full = smem_u32(&bar_full[s]);
@@ -511,12 +557,29 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             const Tile T = tile_of(t);
             const uint32_t buf = tl & 1;
             const int row = T.m0 + qd * 32 + lane;
+            // tile8 epilogues read a global operand per element (conditioning term, saved activation): its loads are issued one chunk
+            // ahead - the first chunk's before the accumulator is even complete - so their L2 latency hides behind the MMAs / the
+            // previous chunk instead of stalling every pass (4 passes x ~700 cycles per chunk otherwise: the epilogue, not the tensor
+            // pipe, bounded the plane-writing GEMMs)
+            [[maybe_unused]] typename epi_pre_type<Epi>::type pre_cur[4], pre_nxt[4];
+            [[maybe_unused]] auto issue_pre = [&](int c0, typename epi_pre_type<Epi>::type* pr) {
+                if constexpr (epi_tile8<Epi>::value) {
+                    if (T.n0 + c0 >= g.N) return;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = T.m0 + qd * 32 + i * 8 + (lane >> 2);
+                        if (rr < g.M) epi.pre8(T.batch, rr, T.n0 + c0 + (lane & 3) * 8, pr[i]);
+                    }
+                }
+            };
+            issue_pre(half * kCols, pre_cur);
             mbar_wait(smem_u32(&bar_acc_full[buf]), (tl >> 1) & 1);
             tcgen05_fence_after();
             const uint32_t acc = tmem_d + buf * BN + ((uint32_t)(qd * 32) << 16);
 #pragma unroll 1
             for (int c0 = half * kCols; c0 < (half + 1) * kCols; c0 += 32) {
                 float v[32];
+                if (c0 + 32 < (half + 1) * kCols) issue_pre(c0 + 32, pre_nxt);
                 tmem_ld32(acc + c0, v);
                 if (c0 + 32 >= (half + 1) * kCols) {   // last chunk read: hand the accumulator back before the (long) global stores of this chunk
                     tcgen05_fence_before();
@@ -534,9 +597,11 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                         float w[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) w[k] = st[rl][cl + k];
-                        if (T.m0 + qd * 32 + rl < g.M) epi.tile8(T.batch, T.split, T.m0 + qd * 32 + rl, T.n0 + c0 + cl, w, g);
+                        if (T.m0 + qd * 32 + rl < g.M) epi.tile8(T.batch, T.split, T.m0 + qd * 32 + rl, T.n0 + c0 + cl, w, pre_cur[i], g);
                     }
                     __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pre_cur[i] = pre_nxt[i];
                 } else
                 if constexpr (Epi::kDirect) {
                     if (row < g.M) epi(T.batch, T.split, row, T.n0 + c0, v, g);
@@ -631,7 +696,10 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
         if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
         if (per_sm < 1) per_sm = 1;
         const int nctas = tiles_total < 148 * per_sm ? tiles_total : 148 * per_sm;
-        if (launch_chain(pkern, dim3(nctas), dim3(kThreadsP), smem, stream, *ma, *mb, gs, epi, (int)grid.x, (int)grid.y, tiles_total) != cudaSuccess) {
+        static const int pf_env = [] { const char* e = getenv("MHE_TC_L2_PREFETCH"); return e ? atoi(e) : 0; }();
+        // (worth it only for contractions long enough to run ahead in; the short ones are epilogue-bound)
+        const int pf = cdiv(g.K, BK) * (g.kfold > 0 ? g.kfold : 1) >= 4 ? pf_env : 0;
+        if (launch_chain(pkern, dim3(nctas), dim3(kThreadsP), smem, stream, *ma, *mb, gs, epi, (int)grid.x, (int)grid.y, tiles_total, pf) != cudaSuccess) {
             set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
             return MHE_ERR_CUDA;
         }
