@@ -211,8 +211,8 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         for (int s = 0; s < kASlots; ++s) { mbar_init(smem_u32(&bar_fullA[s]), 1); mbar_init(smem_u32(&bar_emptyA[s]), 1); }
         for (int s = 0; s < kBSlots; ++s) { mbar_init(smem_u32(&bar_fullB[s]), 1); mbar_init(smem_u32(&bar_emptyB[s]), 1); }
         for (int s = 0; s < 3; ++s) mbar_init(smem_u32(&bar_acc[s]), 1);
-        mbar_init(smem_u32(&bar_xm), kWorkers);
-        mbar_init(smem_u32(&bar_a1), kWorkers);
+        mbar_init(smem_u32(&bar_xm), kWorkers / 32);     // one elected arrival per worker warp (256 arrivals on one barrier serialise)
+        mbar_init(smem_u32(&bar_a1), kWorkers / 32);
         mbar_init(smem_u32(&bar_own), 1);
         mbar_init(smem_u32(&bar_a0), 4);
         mbar_init(smem_u32(&bar_part), kCluster);
@@ -398,7 +398,8 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 st_shared_v4(xa + 8192 + off, lo);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(smem_u32(&bar_xm));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_xm));
         };
         auto load_cp = [&](float* c, int which, int layer) {   // cp[image of row][layer, net, which][f] for this thread's 32 rows
             const float* cpb = p.cp + (size_t)(layer * 4 + net * 2 + which) * p.H + f;
@@ -490,7 +491,8 @@ flow_fwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 for (int n = 0; n < 32; ++n) v[n] = lrelu(v[n] + c[n]);
                 store_slice(v, nullptr, nullptr);
                 tcgen05_fence_before();
-                mbar_arrive(smem_u32(&bar_a1));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_a1));
                 if (p.save) {   // saved for the backward; off the critical path (G2 only reads xa).  (Storing the planes straight from
                     // the registers instead - 32 scattered 16-byte segments per instruction - measured slower than this coalesced copy.)
                     worker_sync();
@@ -635,7 +637,7 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
         for (int s = 0; s < kBSlotsBwd; ++s) { mbar_init(smem_u32(&bar_fullB[s]), 1); mbar_init(smem_u32(&bar_emptyB[s]), 1); }
         for (int s = 0; s < 3; ++s) mbar_init(smem_u32(&bar_acc[s]), 1);
         mbar_init(smem_u32(&bar_xm), 1);
-        mbar_init(smem_u32(&bar_a1), kWorkers);
+        mbar_init(smem_u32(&bar_a1), kWorkers / 32);
         mbar_init(smem_u32(&bar_own), 1);
         mbar_init(smem_u32(&bar_a0), 4);
         mbar_init(smem_u32(&bar_part), kCluster);
@@ -969,7 +971,8 @@ flow_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapW0, const __grid_co
                 load_acc(kAcc1, v);
                 store_grad_slice(v, sg, nullptr, nullptr);
                 tcgen05_fence_before();
-                mbar_arrive(smem_u32(&bar_a1));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_a1));
                 worker_sync();      // kept for the weight gradients; off the critical path (bG0 only reads xa)
                 copy_slice_to_global(xa, p.dh0T + gbatch * p.H * p.Rp, p.H, p.Rp, j * FS, r0, t);
                 if (t == 0) BSTAMP(7);

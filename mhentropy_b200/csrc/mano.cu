@@ -7,6 +7,10 @@
 #include "tc_gemm.cuh"
 
 namespace mhe {
+namespace skin {   // mano_skin_tc.cu: linear blend skinning with the transform blend on the tensor cores
+int launch(const uint16_t* wplanes, const float* A, const float* cen, const float* vp, int ld_vp, float* verts, float* jtr, int R, int order,
+           cudaStream_t stream);
+}
 using namespace mano;
 
 constexpr int kV = MHE_MANO_VERTS;   // 778
@@ -782,7 +786,8 @@ int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
         if (c->posedirs_planes) {   // both contractions of the mesh on the tensor cores (see above)
             const uint16_t* bd = (const uint16_t*)c->posedirs_planes;
             const uint16_t* wp = bd + (size_t)2 * kPmK * kOffLd;
-            static const bool tc_skin = getenv("MHE_MANO_TC_SKIN") != nullptr;
+            static const bool tc_skin = getenv("MHE_MANO_TC_SKIN") != nullptr;     // (round 1's generic-GEMM skinning: diagnostic only)
+            static const bool simt_skin = [] { const char* e = getenv("MHE_MANO_SKIN"); return e && !strcmp(e, "simt"); }();
             const long nel = (long)R * (kPmK + (tc_skin ? kLbsN * 64 : 0));
             const int nblk = (int)((nel + 255) / 256 < 1184 ? (nel + 255) / 256 : 1184);      // grid-stride beyond 8 blocks per SM
             mano_mesh_operands_kernel<<<nblk, 256, 0, stream>>>(ws.pm, ws.A, beta, ld_beta, R, (uint16_t*)ws.pmp, tc_skin ? (uint16_t*)ws.lbsb : nullptr);
@@ -795,8 +800,10 @@ int mhe_mano_fwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
             tc::GemmShape g{R, kOffLd, kPmK, 1, 1, 1, 1};
             EpiPoseOffsets e{ws.poff};
             MHE_TRY((tc::launch_tc_gemm<128, false, true, 3, true>(A, Bp, g, e, stream, "mano blend")));
-            if (!tc_skin) {   // skinning on the CUDA cores from the GEMM's vertices: the one-tile-per-CTA GEMM kernel's fixed cost per
-                // 128 x 128 tile makes the K = 16 skinning GEMM below no faster yet (measured 0.544 vs 0.536 ms/step)
+            if (!tc_skin && !simt_skin) {   // default: the dedicated tensor-core skinning kernel (mano_skin_tc.cu)
+                MHE_TRY(skin::launch(wp, ws.A, ws.cen, ws.poff, kOffLd, verts, jtr, R, joint_order, stream));
+            } else
+            if (!tc_skin) {   // MHE_MANO_SKIN=simt: skinning on the CUDA cores from the GEMM's vertices (round 1; instruction-bound)
                 if (R >= 512) mano_skin_fwd_kernel<8><<<dim3(cdiv(kV, 128), cdiv(R, 8)), 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, ws.poff);
                 else mano_skin_fwd_kernel<2><<<dim3(cdiv(kV, 128), cdiv(R, 2)), 128, 0, stream>>>(*c, beta, ld_beta, R, joint_order, ws.pm, ws.A, ws.cen, verts, jtr, nullptr, ws.poff);
                 MHE_TRY(check_launch("mano skin fwd"));

@@ -420,7 +420,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 256); }
+        for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 8); }   // one elected arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -582,8 +582,10 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                 if (c0 + 32 < (half + 1) * kCols) issue_pre(c0 + 32, pre_nxt);
                 tmem_ld32(acc + c0, v);
                 if (c0 + 32 >= (half + 1) * kCols) {   // last chunk read: hand the accumulator back before the (long) global stores of this chunk
+                    // (one arrival per warp: hundreds of arrivals on one mbarrier serialise - ~3 ns each, measured in mano_skin_tc.cu)
                     tcgen05_fence_before();
-                    mbar_arrive_cta(smem_u32(&bar_acc_empty[buf]));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(smem_u32(&bar_acc_empty[buf]));
                 }
                 if (T.n0 + c0 >= g.N) continue;
                 if constexpr (epi_tile8<Epi>::value) {
