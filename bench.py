@@ -237,8 +237,10 @@ def run_ours(args):
     # multi-GPU: TrainStep.exchange_gradients() after the step - factored (all-gather of the conditioning factors + local weight-gradient
     # GEMM, all-reduce of the other 30 MB) while the factors are well below the dense gradient (2, 4 ranks), one dense all-reduce above
     # (8 ranks); MHE_BENCH_EXCHANGE=dense|factored forces one.  MHE_BENCH_ALLREDUCE_INSIDE=1: bucketed all-reduce inside the captured step.
-    ar_inside = world > 1 and bool(os.environ.get('MHE_BENCH_ALLREDUCE_INSIDE'))
     exchange = os.environ.get('MHE_BENCH_EXCHANGE', 'dense' if os.environ.get('MHE_BENCH_DENSE_ALLREDUCE') else 'auto')
+    ar_inside = world > 1 and (bool(os.environ.get('MHE_BENCH_ALLREDUCE_INSIDE')) or exchange == 'inside')
+    if exchange == 'inside':
+        exchange = 'dense'
 
     def allreduce(engine):
         if world > 1:

@@ -22,10 +22,11 @@ from .losses import MHEntHead
 def factored_exchange_pays(shape, B: int, world: int) -> bool:
     """Factored vs dense exchange of the conditioning weight gradient: the factors all-gathered per rank are
     world x B x (L*4*H + C) floats, the dense gradient L*4*H*C.  The gather also feeds a contraction over world x B images on every
-    rank, so it only pays while the factors are well below the dense size: 2 and 4 ranks at 64 images, not 8."""
+    rank, so it only pays while the factors are a small fraction of the dense size.  Measured at 64 images per rank (ms/step,
+    profiles/r2_exchange_modes_*): 2 ranks 0.655 factored vs 0.73 dense; 4 ranks 0.767 vs 0.752; 8 ranks 0.849 vs 0.842."""
     factors = world * B * (shape.layers * 4 * shape.hidden + shape.cond)
     dense = shape.layers * 4 * shape.hidden * shape.cond
-    return factors <= 0.6 * dense
+    return factors <= 0.3 * dense
 
 
 @contextlib.contextmanager
