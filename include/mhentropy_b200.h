@@ -299,13 +299,15 @@ int mhe_image_loss_reduce(const float* row_log_p, const float* log_q, int R, int
 /* The joints-only training path of every hypothesis in ONE launch: MANO forward (mhe_mano_fwd without the mesh; reference
  * manolayer.py:110-274), root / bone normalisation, projection, Laplace(visible) and priors (mhe_reproj_loss_fwd's row part;
  * utils.py:46-66, network.py:497-514, 233-258, 155-165), and the backward of both down to dz (mhe_reproj_loss_bwd + mhe_mano_bwd).
- * The loss is linear in the row terms, so the gradient seed of every row is the constant -dloss / R and nothing waits for a
- * reduction.  z [R][61] (theta = z[:, 0:48], beta = z[:, 48:58]) - or z == NULL and its two sources x_flow [R][45], z_det [B][16]
+ * The loss is linear in the row terms, so with the criterion's loss = -mean_b log_p (criteria.py:55,173) the gradient seed of every
+ * row is the constant -dloss / R and nothing waits for a reduction; dlog_p [B] != NULL supplies dL/dlog_p per image instead (the seed
+ * of a row of image b is then dlog_p[b] / N: what an autograd caller with an arbitrary downstream loss needs).  z [R][61] (theta = z[:, 0:48], beta = z[:, 48:58]) - or z == NULL and its two sources x_flow [R][45], z_det [B][16]
  * (mhe_combine_z_fwd's inputs: the kernel assembles the row itself) -, crop_uv [B][42], vis [B][21] ->
  *   jtr [R][21][3] (may be NULL), uv [R][42] (may be NULL), row_log_p [R], dz [R][61] (overwritten), dx_flow [R][45] (may be NULL: the
  *   flow's columns of dz, what mhe_combine_z_bwd extracts), dlog_q [R] (may be NULL).                                               */
 int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* x_flow,
                                 const float* z_det, const float* crop_uv, const float* vis, int R, int B, int joint_order, float dloss,
+                                const float* dlog_p,
                                 float* jtr, float* uv, float* row_log_p, float* dz, float* dx_flow, float* dlog_q, void* stream);
 
 /* xyz / verts normalisation and projection for MHEnt.sample (network.py:466-483, 497-514, 876-877):

@@ -84,7 +84,7 @@ _SIGNATURES = {
     'mhe_reproj_loss_bwd': (c_int, [POINTER(LossCfg), _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     'mhe_image_loss_reduce': (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     'mhe_hypothesis_rows_fwd_bwd': (c_int, [POINTER(ManoConsts), POINTER(LossCfg), _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P,
-                                            _P, _P]),
+                                            _P, _P, _P]),
     'mhe_hypothesis_metrics_workspace_bytes': (c_size_t, [c_int]),
     'mhe_hypothesis_metrics': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, c_size_t, _P]),
     'mhe_topk_hypotheses': (c_int, [_P, c_int, c_int, c_int, _P, _P]),

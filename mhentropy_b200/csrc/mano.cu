@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(kPoseWarps * 32) mano_pose_bwd_kernel(mhe_mano
 __global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_mano_consts c, mhe_loss_cfg cfg, const float* __restrict__ z,
                                      const float* __restrict__ x_flow, const float* __restrict__ z_det,
                                      const float* __restrict__ crop_uv, const float* __restrict__ vis, int R, int B, int order, float dloss,
+                                     const float* __restrict__ dlog_p,
                                      float* __restrict__ jtr, float* __restrict__ uv, float* __restrict__ row_lp, float* __restrict__ dz,
                                      float* __restrict__ dx_flow, float* __restrict__ dlog_q) {
     __shared__ WarpPose s_w[kPoseWarps];
@@ -627,7 +628,9 @@ __global__ void __launch_bounds__(kPoseWarps * 32) hypothesis_rows_kernel(mhe_ma
     // reprojection + likelihood + priors, and their gradient with the constant seed
     const loss::RowGeom g = loss::row_geom(cfg, jo, zz, lane);
     const float lp = loss::reproj_row_fwd(cfg, g, zz, crop_uv + b * 42, vis + b * kNJ, lane, uv ? uv + (long)r * 42 : nullptr);
-    const float gr = -dloss / (float)R;                                   // -dloss / B / N
+    // gradient seed of the row: dL/d row_log_p = dL/dlog_p[b] / N.  With the criterion's loss = -mean_b log_p (criteria.py:55,173) that is
+    // the constant -dloss / (B N); a caller differentiating something else passes its own dL/dlog_p per image.
+    const float gr = dlog_p ? __ldg(dlog_p + b) / (float)(R / B) : -dloss / (float)R;
     if (lane == 0) { row_lp[r] = lp; if (dlog_q) dlog_q[r] = -gr; }
     loss::reproj_row_bwd(cfg, g, zz, crop_uv + b * 42, vis + b * kNJ, gr, lane, W.dj, dzr);
     __syncwarp();
@@ -879,13 +882,13 @@ int mhe_mano_bwd(const mhe_mano_consts* c, const float* theta, int ld_theta, con
 }
 
 int mhe_hypothesis_rows_fwd_bwd(const mhe_mano_consts* c, const mhe_loss_cfg* cfg, const float* z, const float* x_flow, const float* z_det,
-                                const float* crop_uv, const float* vis, int R, int B, int joint_order, float dloss, float* jtr, float* uv,
-                                float* row_log_p, float* dz, float* dx_flow, float* dlog_q, void* stream) {
+                                const float* crop_uv, const float* vis, int R, int B, int joint_order, float dloss, const float* dlog_p,
+                                float* jtr, float* uv, float* row_log_p, float* dz, float* dx_flow, float* dlog_q, void* stream) {
     if (R == 0) return MHE_OK;
     MHE_REQUIRE(c && cfg && (z || (x_flow && z_det)) && crop_uv && vis && row_log_p && dz, "hypothesis_rows_fwd_bwd: null pointer");
     MHE_REQUIRE(R > 0 && B > 0 && R % B == 0 && joint_order >= 0 && joint_order <= 1, "hypothesis_rows_fwd_bwd: bad sizes");
     hypothesis_rows_kernel<<<cdiv(R, kPoseWarps), kPoseWarps * 32, 0, (cudaStream_t)stream>>>(*c, *cfg, z, x_flow, z_det, crop_uv, vis, R, B, joint_order,
-                                                                                               dloss, jtr, uv, row_log_p, dz, dx_flow, dlog_q);
+                                                                                               dloss, dlog_p, jtr, uv, row_log_p, dz, dx_flow, dlog_q);
     return check_launch("hypothesis rows fwd+bwd");
 }
 

@@ -139,6 +139,7 @@ class TrainStep:
             self.xws_bytes = L.mhe_flow_cond_workspace_bytes(self.shape, world * B)
             self.xws = torch.empty(self.xws_bytes, dtype=torch.uint8, device=dev)
         self.launches_per_step = None
+        self._g_fwd, self._g_bwd, self.busy = None, {}, False
 
     # ------------------------------------------------------------------
     def _enqueue(self):
@@ -215,7 +216,7 @@ class TrainStep:
         # (the kernel can also assemble its row of z from x / z_det and emit the flow's share of dz itself, which takes both combine_z
         # kernels off this chain - measured slower, 0.549 vs 0.537 ms: the backward's cluster kernel needs entirely free SMs and cannot
         # start before the mesh skinning has drained anyway, and an earlier per-row kernel collides with the pose-blend GEMM)
-        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), None, None, ptr(self.crop_uv), ptr(self.vis), R, B, 1, self.dloss,
+        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), None, None, ptr(self.crop_uv), ptr(self.vis), R, B, 1, self.dloss, None,
                                             ptr(self.jtr), ptr(self.uv), ptr(self.row_lp), ptr(self.dz), None, ptr(self.dlog_q), s),
               'hypothesis_rows')
         self.side4.wait_stream(main)
@@ -367,6 +368,96 @@ class TrainStep:
             self.comm.wait_stream(self.side4)            # the loss (reduced on a side stream)
             dist.all_reduce(self.loss, group=self.allreduce_group)
         main.wait_stream(self.comm)
+
+    # ------------------------------------------------------------------ split mode: forward and backward as two captured graphs
+    # (what the autograd drop-in path replays: MHEntHead.get_loss -> losses._FusedLossFn; the backward receives dL/dlog_p per image)
+    def _enqueue_forward_only(self):
+        L, s = lib(), _lib.stream_ptr(self.dev)
+        R, B, shape, ws, wsb = self.R, self.B, self.shape, ptr(self.ws), self.ws_bytes
+        z = self.z
+        theta, beta = z.data_ptr(), z.data_ptr() + 48 * 4
+        pk, cws, cwsb = ptr(self.packed), ptr(self.cws), self.cws_bytes
+        main = torch.cuda.current_stream(self.dev)
+        check(L.mhe_flow_cond_fwd(shape, ptr(self.flat), pk, ptr(self.feat), B, ptr(self.cp), cws, cwsb, s), 'cond_fwd')
+        check(L.mhe_flow_pass_fwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.z0), R, B, 0, ptr(self.x),
+                                  ptr(self.logdet), ptr(self.saved), ws, wsb, s), 'pass_fwd')
+        self.side4.wait_stream(main)
+        with torch.cuda.stream(self.side4):
+            check(L.mhe_std_normal_logp_fwd(ptr(self.z0), ptr(self.logdet), -1.0, R, shape.dim, ptr(self.log_q),
+                                            _lib.stream_ptr(self.dev)), 'log_q')
+        check(L.mhe_combine_z_fwd(ptr(self.x), ptr(self.z_det), R, B, ptr(z), s), 'combine_z')
+        if self.verts is not None:
+            self.side2.wait_stream(main)
+            with torch.cuda.stream(self.side2):
+                check(L.mhe_mano_fwd(self.consts, theta, 61, beta, 61, R, 1, ptr(self.verts), ptr(self.jtr_mesh), None, ptr(self.mws),
+                                     self.mws_bytes, _lib.stream_ptr(self.dev)), 'mano_fwd mesh')
+        # the per-row kernel's forward outputs (joints, uv, row log-likelihood + priors); its gradient outputs are rewritten by the backward
+        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(z), None, None, ptr(self.crop_uv), ptr(self.vis), R, B, 1, 0.0, None,
+                                            ptr(self.jtr), ptr(self.uv), ptr(self.row_lp), ptr(self.dz), None, None, s), 'hypothesis_rows fwd')
+        main.wait_stream(self.side4)
+        check(L.mhe_image_loss_reduce(ptr(self.row_lp), ptr(self.log_q), R, B, ptr(self.log_p), ptr(self.h), ptr(self.qlp), ptr(self.loss), s),
+              'image_loss_reduce')
+        self.norms[0].copy_(z[:, :48].norm(p=2, dim=1))          # th_norm / bt_norm (network.py:787-788): outputs only
+        self.norms[1].copy_(z[:, 48:58].norm(p=2, dim=1))
+        if self.verts is not None:
+            main.wait_stream(self.side2)
+
+    def _enqueue_backward_only(self, dflat):
+        """dL/dlog_p per image in self.dlog_p -> dflat (weight slots stored, bias slots zeroed first on the fused path), dfeat, dz_det."""
+        L, s = lib(), _lib.stream_ptr(self.dev)
+        R, B, shape, ws, wsb = self.R, self.B, self.shape, ptr(self.ws), self.ws_bytes
+        pk, cws, cwsb = ptr(self.packed), ptr(self.cws), self.cws_bytes
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            if self.fused:
+                check(L.mhe_flow_zero_bias_grads(shape, ptr(dflat), _lib.stream_ptr(self.dev)), 'zero_bias_grads')
+            else:
+                dflat.zero_()
+            self.dcp.zero_()
+            self.dfeat.zero_()
+        check(L.mhe_hypothesis_rows_fwd_bwd(self.consts, self.cfg, ptr(self.z), None, None, ptr(self.crop_uv), ptr(self.vis), R, B, 1, 1.0,
+                                            ptr(self.dlog_p), None, None, ptr(self.row_lp_scratch), ptr(self.dz), None, ptr(self.dlog_q), s),
+              'hypothesis_rows bwd')
+        check(L.mhe_combine_z_bwd(ptr(self.dz), R, B, ptr(self.dx), ptr(self.dz_det), s), 'combine_z_bwd')
+        main.wait_stream(self.side)
+        flags = ((7 if self.fused else 5) if self.tc else 3)
+        check(L.mhe_flow_set_async(flags), 'set_async')
+        try:
+            check(L.mhe_flow_pass_bwd(shape, ptr(self.flat), pk, ptr(self.mask), ptr(self.cp), ptr(self.saved), R, B, 0, ptr(self.dx),
+                                      ptr(self.dlog_q), -1.0, ptr(self.dz0), ptr(dflat), ptr(self.dcp), ws, wsb, s), 'pass_bwd')
+            check(L.mhe_flow_cond_bwd(shape, ptr(self.flat), pk, ptr(self.feat), ptr(self.dcp), B, ptr(dflat), ptr(self.dfeat), cws, cwsb, s),
+                  'cond_bwd')
+        finally:
+            check(L.mhe_flow_set_async(0), 'set_async')
+        check(L.mhe_flow_join(s), 'flow_join')
+
+    def _capture(self, fn):
+        side = torch.cuda.Stream(self.dev, priority=-1)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            fn()                                  # warm-up outside capture
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+        return g
+
+    def forward_graph(self):
+        if self._g_fwd is None:
+            self.norms = torch.empty(2, self.R, device=self.dev)
+            self.dlog_p = torch.zeros(self.B, device=self.dev)
+            self.row_lp_scratch = torch.empty(self.R, device=self.dev)
+            self._g_fwd = self._capture(self._enqueue_forward_only)
+        return self._g_fwd
+
+    def backward_graph(self, dflat):
+        """Graph of the backward writing its parameter gradients into `dflat` (one graph per destination buffer)."""
+        key = dflat.data_ptr()
+        if key not in self._g_bwd:
+            self._g_bwd[key] = self._capture(lambda: self._enqueue_backward_only(dflat))
+        return self._g_bwd[key]
 
     def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
         """Copy one batch (host or device tensors) into the static input buffers."""

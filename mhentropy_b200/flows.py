@@ -377,6 +377,27 @@ class RealNVP(nn.Module):
         self._grad_writes[family] += 1
         return buf, store
 
+    def _grad_destination(self):
+        """For a backward that OVERWRITES its destination (the engine's captured backward graph): ``(buffer, direct)``.
+        ``direct``: no gradient is attached yet (first step / ``zero_grad(set_to_none=True)``) - the views are attached and the graph may
+        write straight into the flow's gradient buffer.  Otherwise the caller must write to scratch and ``add_`` (gradient accumulation)."""
+        buf = self.grad_buffer()
+        if self._grads_attached():
+            return buf, False
+        carry = []
+        for (p, _, _, _), v in zip(self._slots, self._grad_views):      # one pass: attach the views, note gradients held elsewhere
+            if p.requires_grad:
+                g = p.grad
+                if g is not None and g is not v:
+                    carry.append((v, g))
+                p.grad = v
+        if carry:                                   # gradients accumulated elsewhere are carried over into the flat buffer
+            buf.zero_()
+            for v, g in carry:
+                v.copy_(g)
+        self._grad_writes = {'pass': 1, 'cond': 1}
+        return buf, not carry
+
     def _flat_for_autograd(self, device):
         flat = self.flat_parameters(device)
         if torch.is_grad_enabled() and any(p.requires_grad for p, _, _, _ in self._slots):

@@ -6,6 +6,7 @@
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 import torch.nn as nn
@@ -87,6 +88,56 @@ class _ReprojLossFn(torch.autograd.Function):
         return dj, dz, dlq, None, None, None
 
 
+def _release_engine(eng, token):
+    if getattr(eng, 'token', None) is token:          # the graph was dropped without a backward: the engine is free again
+        eng.busy, eng.token = False, None
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """``MHEnt._reverse_kld`` from the feature on (``network.py:760-831``) as ONE autograd node: forward and backward are two captured
+    CUDA graphs of the engine (``engine.TrainStep`` split mode), so a ``get_loss`` + ``backward()`` costs two graph launches on the host
+    instead of ~25 kernel launches through eight autograd functions.  Differentiable through ``log_p`` (B,) with ANY downstream loss:
+    the backward graph takes dL/dlog_p per image.  Parameter gradients land in the flow's flat gradient buffer (``p.grad`` are views)."""
+
+    @staticmethod
+    def forward(ctx, feat, z_det, anchor, head, eng, z0, crop_uv, vis):
+        flow = head.q_z_giv_i
+        flow.packed_weights(eng.dev)                  # re-packs the split planes here (eagerly, stream-ordered) if the weights changed
+        eng.load(feat.detach(), z_det.detach(), z0, crop_uv, vis)
+        eng.forward_graph().replay()
+        outs = tuple(t.clone() for t in (eng.log_p, eng.h, eng.qlp, eng.uv, eng.norms[0], eng.norms[1]))
+        ctx.head, ctx.eng = head, eng
+        if any(ctx.needs_input_grad[:3]):             # the engine's buffers hold this forward until its backward (or until the graph is dropped)
+            eng.busy = True
+            eng.token = token = object()
+            ctx.token = token
+            ctx._fin = weakref.finalize(ctx, _release_engine, eng, token)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, dlog_p, *_):
+        eng, flow = ctx.eng, ctx.head.q_z_giv_i
+        if getattr(eng, 'token', None) is not ctx.token:
+            raise RuntimeError('the fused loss node was run again before this backward (retain_graph / double backward are not supported on '
+                               'the fused path: set head.fuse_loss = False)')
+        eng.dlog_p.copy_(dlog_p)
+        if ctx.needs_input_grad[2]:                   # some flow parameter wants a gradient
+            buf, direct = flow._grad_destination()
+            if direct:                                # nothing accumulated yet: the graph writes straight into the flow's gradient buffer
+                eng.backward_graph(buf).replay()
+            else:                                     # gradient accumulation: into the engine's scratch, then add
+                eng.backward_graph(eng.dflat).replay()
+                buf.add_(eng.dflat)
+        else:
+            eng.backward_graph(eng.dflat).replay()
+        ctx._fin.detach()
+        eng.busy, eng.token = False, None
+        dfeat = eng.dfeat.clone() if ctx.needs_input_grad[0] else None
+        dzd = eng.dz_det.clone() if ctx.needs_input_grad[1] else None
+        return dfeat, dzd, None, None, None, None, None, None
+
+
 def normalize_project(cfg: LossCfg, joints, verts, z, inv_norm: bool, image_size: int = 256):
     """xyz (R,21,3), normalised verts (R,778,3) and uv (R,21,2) for ``MHEnt.sample`` (``network.py:466-514``)."""
     joints = joints.contiguous().float()
@@ -127,6 +178,8 @@ class MHEntHead(nn.Module):
         self.entropy = entropy
         self.loss_cfg = default_loss_cfg()
         self.T = 1.0
+        self.fuse_loss = True          # get_loss on CUDA tensors replays the engine's captured forward / backward graphs (_FusedLossFn)
+        self._fused_pool = {}
 
     # -- network.py:719-758
     def _sample_q_z_giv_i(self, feat, N=1, temp=1., z0=None, z_det=None, return_log_q=False):
@@ -157,6 +210,19 @@ class MHEntHead(nn.Module):
         """``fused=True`` takes log q of the samples from the sampling pass itself; ``fused=False`` runs the
         reference's second, inverse pass (``network.py:801``).  Both give the same value and gradient."""
         out = {}
+        eng = self._fused_engine(feat, N, want_verts) if (fused and self.fuse_loss and self.entropy) else None
+        if eng is not None:
+            flow = self.q_z_giv_i
+            B = feat.shape[0]
+            if z0 is None:
+                z0 = torch.randn(N * B, flow.dim, device=feat.device)        # == prior.sample * 1.0 (flows.py:339, network.py:720)
+            if z_det is None:
+                z_det = self.det_head(feat)
+            flat = flow._flat_for_autograd(feat.device)
+            anchor = flat if flat.requires_grad else feat.new_zeros(())
+            log_p, h, qlp, uv, th_norm, bt_norm = _FusedLossFn.apply(feat.float(), z_det.float(), anchor, self, eng, z0.float(),
+                                                                    y['crop_uv'].float(), y['vis'].float())
+            return {'th_norm': th_norm, 'bt_norm': bt_norm, 'q_log_p_z_giv_y': qlp, 'h_q_z_giv_i': h, 'log_p': log_p, 'uv_mu': uv}
         if fused:
             z, log_q = self._sample_q_z_giv_i(feat, N=N, z0=z0, z_det=z_det, return_log_q=True)
         else:
@@ -173,6 +239,29 @@ class MHEntHead(nn.Module):
         out['log_p'] = log_p
         out['uv_mu'] = uv
         return out
+
+    def _fused_engine(self, feat, N, want_verts):
+        """A split-mode engine for this batch shape, or None when the fused node does not apply (CPU tensors, a shape the kernels do not
+        cover, both pooled engines still waiting for their backward)."""
+        flow = self.q_z_giv_i
+        if not feat.is_cuda or not flow._kernel_ok or feat.shape[0] * N > 65536 or feat.shape[0] == 0:
+            return None
+        from .engine import TrainStep
+        key = (feat.shape[0], N, str(feat.device), bool(want_verts), flow.precision, flow._shape.max_split)
+        pool = self._fused_pool.setdefault(key, [])
+        for eng in pool:
+            if not eng.busy:
+                return eng
+        if len(pool) >= 2:
+            return None
+        eng = TrainStep(self, feat.shape[0], N, feat.device, want_verts=want_verts, use_graph=False, planes='optimizer', exchange='dense',
+                        average_over_ranks=False)
+        pool.append(eng)
+        return eng
+
+    def _apply(self, fn, *args, **kwargs):
+        self._fused_pool = {}            # engines hold device pointers of the parameters: rebuilt after .to() / .cuda()
+        return super()._apply(fn, *args, **kwargs)
 
     def log_prob(self, y: dict, feat, **kw):
         return self._reverse_kld(y, feat, **kw)

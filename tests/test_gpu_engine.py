@@ -94,17 +94,17 @@ def test_hypothesis_rows_kernel_matches_separate_kernels(R, B):
     check(L.mhe_mano_bwd(consts, theta, 61, beta, 61, R, 1, None, ptr(dj0), None, dz0.data_ptr(), 61, dz0.data_ptr() + 48 * 4, 61, 1,
                          ptr(ws), wsb, s), 'mano_bwd')
     jtr1, uv1, lp1, dz1, dlq1 = f(R, 21, 3), f(R, 42), f(R), f(R, 61), f(R)
-    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(z), None, None, ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr1), ptr(uv1), ptr(lp1),
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(z), None, None, ptr(crop_uv), ptr(vis), R, B, 1, 1.0, None, ptr(jtr1), ptr(uv1), ptr(lp1),
                                         ptr(dz1), None, ptr(dlq1), s), 'rows')
     # the same from z's two sources, with the flow's share of dz as an extra output
     x_flow, z_det = z[:, 3:48].contiguous(), torch.cat([z[:B, :3], z[:B, 48:]], 1).contiguous()
     zc = torch.empty_like(z)
     check(L.mhe_combine_z_fwd(ptr(x_flow), ptr(z_det), R, B, ptr(zc), s), 'combine')
     jtr2, uv2, lp2, dz2, dx2 = f(R, 21, 3), f(R, 42), f(R), f(R, 61), f(R, 45)
-    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, None, ptr(x_flow), ptr(z_det), ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr2), ptr(uv2),
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, None, ptr(x_flow), ptr(z_det), ptr(crop_uv), ptr(vis), R, B, 1, 1.0, None, ptr(jtr2), ptr(uv2),
                                         ptr(lp2), ptr(dz2), ptr(dx2), None, s), 'rows from sources')
     jtr3, lp3, dz3 = f(R, 21, 3), f(R), f(R, 61)
-    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(zc), None, None, ptr(crop_uv), ptr(vis), R, B, 1, 1.0, ptr(jtr3), None, ptr(lp3),
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(zc), None, None, ptr(crop_uv), ptr(vis), R, B, 1, 1.0, None, ptr(jtr3), None, ptr(lp3),
                                         ptr(dz3), None, None, s), 'rows from combined z')
     torch.cuda.synchronize()
     assert torch.equal(jtr2, jtr3) and torch.equal(lp2, lp3) and torch.equal(dz2, dz3) and torch.equal(dx2, dz2[:, 3:48])
@@ -277,3 +277,42 @@ def test_engine_long_batch_replay_matches_autograd_path():
     g_eng = eng.flow_grads()
     for k, p in head.q_z_giv_i.named_parameters():
         assert rel(g_eng[k], p.grad) < 1e-4, k
+
+
+def test_fused_loss_node_general_downstream_and_accumulation():
+    """MHEntHead.get_loss through the fused autograd node (two captured graphs) against the unfused chain of autograd functions: a
+    NON-uniform downstream loss (weights per image), gradient accumulation over two backward calls, and a dropped graph."""
+    head = MHEntHead(mano_data=synthetic_mano(0))
+    head.q_z_giv_i.load_state_dict(fo.init_state_dict(seed=0))
+    head.q_z_giv_i.precision = 'bf16x3'
+    head = head.to(DEV)
+    for p in head.parameters():
+        p.requires_grad_(True)
+    B, S = 6, 10
+    devb = {k: v.to(DEV) for k, v in synthetic_batch(B, S, seed=41).items()}
+    w = torch.linspace(0.5, 2.0, B, device=DEV)
+
+    def run(fuse, feat, zd):
+        head.fuse_loss = fuse
+        out = head.get_loss(feat, {'crop_uv': devb['crop_uv'], 'vis': devb['vis']}, z0=devb['z0'], z_det=zd, N=S)
+        return out, -(w * out['log_p']).sum()
+
+    res = {}
+    for fuse in (False, True):
+        head.zero_grad(set_to_none=True)
+        feat, zd = devb['feat'].clone().requires_grad_(True), devb['z_det'].clone().requires_grad_(True)
+        if fuse:
+            run(True, feat, zd)                     # a forward whose graph is dropped without backward must release its engine
+        out, loss = run(fuse, feat, zd)
+        loss.backward()
+        out2, loss2 = run(fuse, feat, zd)           # second backward: gradients accumulate (2x)
+        loss2.backward()
+        torch.cuda.synchronize()
+        res[fuse] = (out, feat.grad.clone(), zd.grad.clone(), {k: p.grad.clone() for k, p in head.q_z_giv_i.named_parameters()})
+    (o0, f0, z0g, g0), (o1, f1, z1g, g1) = res[False], res[True]
+    for k in ('log_p', 'h_q_z_giv_i', 'q_log_p_z_giv_y', 'uv_mu', 'th_norm', 'bt_norm'):
+        assert rel(o1[k], o0[k]) < 1e-5, k
+    assert rel(f1, f0) < 1e-4 and rel(z1g, z0g) < 1e-4
+    for k in g0:
+        assert rel(g1[k], g0[k]) < 1e-4, k
+    assert all(not e.busy for pool in head._fused_pool.values() for e in pool)

@@ -118,7 +118,7 @@ def stage_rows(B, S, seed):
     f = lambda *sh: torch.empty(*sh, device=DEV)  # noqa: E731
     jtr, uv, lp, dz, dlq = f(R, 21, 3), f(R, 42), f(R), f(R, 61), f(R)
     s = _lib.stream_ptr(torch.device(DEV))
-    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(zc), None, None, ptr(cuv), ptr(visc), R, B, 1, 1.0, ptr(jtr), ptr(uv),
+    check(L.mhe_hypothesis_rows_fwd_bwd(consts, cfg, ptr(zc), None, None, ptr(cuv), ptr(visc), R, B, 1, 1.0, None, ptr(jtr), ptr(uv),
                                         ptr(lp), ptr(dz), None, ptr(dlq), s), 'rows')
     torch.cuda.synchronize()
     out = {}
