@@ -164,6 +164,27 @@ struct EpiWgrad {   // dW[batch][row][col] += acc, col < ncols  (staged: lanes a
         return col < ncols ? dW + (long)b * batch_stride + (long)row0 * ld + col : nullptr;
     }
 };
+struct EpiWgradVec {   // the same for unsplit contractions into 16-byte aligned rows (ld % 4 == 0, ncols % 8 == 0): 8 columns of a row per
+    // lane, 128 contiguous bytes per row and instruction - the short contractions (K = 64 images / rows) are all epilogue
+    static constexpr bool kDirect = false, kStaged = false, kRmw = false, kTile8 = true;
+    float* dW; long ld; long batch_stride; int overwrite;
+    struct Pre { float4 a, b; };
+    __device__ void operator()(int, int, int, int, float*, const GemmShape&) const {}
+    __device__ void elem(int, int, int, int, float, const GemmShape&) const {}
+    __device__ void pre8(int b, int row, int col, Pre& p) const {
+        if (overwrite) return;
+        const float4* q = reinterpret_cast<const float4*>(dW + (long)b * batch_stride + (long)row * ld + col);
+        p.a = q[0]; p.b = q[1];
+    }
+    __device__ void tile8(int b, int, int row, int col, float* v, const Pre& p, const GemmShape&) const {
+        float4* q = reinterpret_cast<float4*>(dW + (long)b * batch_stride + (long)row * ld + col);
+        if (overwrite) { q[0] = make_float4(v[0], v[1], v[2], v[3]); q[1] = make_float4(v[4], v[5], v[6], v[7]); }
+        else {
+            q[0] = make_float4(p.a.x + v[0], p.a.y + v[1], p.a.z + v[2], p.a.w + v[3]);
+            q[1] = make_float4(p.b.x + v[4], p.b.y + v[5], p.b.z + v[6], p.b.w + v[7]);
+        }
+    }
+};
 struct EpiWgradT {   // element (row, col) goes to dW[batch][col][row]: lanes = rows are already contiguous in memory
     static constexpr bool kDirect = true, kStaged = false, kRmw = false;
     float* dW; long ld; long batch_stride; int ncols; int atomic; int overwrite = 0;
@@ -388,6 +409,10 @@ int wgrad_kmajor(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, float*
         EpiWgradT e{dW, ld, batch_stride, ncols, g.ksplit > 1, grads_are_zero() && g.ksplit == 1};
         return gemm<false, false, false>(A, B, g, e, stream, what);
     }
+    if (g.ksplit == 1 && ld % 4 == 0 && ncols % 8 == 0 && g.N % 8 == 0 && ((uintptr_t)dW & 15) == 0 && batch_stride % 4 == 0) {
+        EpiWgradVec e{dW, ld, batch_stride, grads_are_zero() ? 1 : 0};
+        return gemm<false, false, false>(A, B, g, e, stream, what);
+    }
     EpiWgrad e{dW, ld, batch_stride, ncols, g.ksplit > 1, grads_are_zero() && g.ksplit == 1};
     return gemm<false, false, false>(A, B, g, e, stream, what);
 }
@@ -481,8 +506,13 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
         PlaneTensor A = pt(dcpp, L.H, B, cp_ld, (long)B * cp_ld, L.L * 4, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, L.L * 4, 1, 1, 0};
-        EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
-        MHE_TRY((gemm<true, true, false>(A, Bt, g, e, wstream, "tc cond wgrad")));
+        if (L.C % 8 == 0 && L.cw_stride % 4 == 0 && L.cw_base % 4 == 0) {
+            EpiWgradVec e{dparams + L.cw_base, L.C, (long)L.cw_stride, grads_are_zero() ? 1 : 0};
+            MHE_TRY((gemm<true, true, false>(A, Bt, g, e, wstream, "tc cond wgrad")));
+        } else {
+            EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
+            MHE_TRY((gemm<true, true, false>(A, Bt, g, e, wstream, "tc cond wgrad")));
+        }
     }
     if (fork) MHE_TRY(cuda_ok(cudaEventRecord(aux.done[0][0], wstream), "join cond wgrad"));
     if (dfeat) {   // dfeat [B][C] = sum_idx dcp[:, idx, :] Cw[idx]   (A K-major over h; B MN-major: cols = c, rows = h)
@@ -516,6 +546,10 @@ int cond_wgrad(const FlowLayout& L, const float* feat, const float* dcp, int Bt,
     PlaneTensor A = pt(dcpp, L.H, Bt, cp_ld, (long)Bt * cp_ld, L.L * 4, L.H);
     PlaneTensor Bt_ = pt(featp, L.C, Bt, L.C, (long)Bt * L.C, 1, 0);
     GemmShape g{L.H, L.C, Bt, L.L * 4, 1, 1, 0};
+    if (L.C % 8 == 0 && L.cw_stride % 4 == 0 && L.cw_base % 4 == 0) {
+        EpiWgradVec e{dparams + L.cw_base, L.C, (long)L.cw_stride, grads_are_zero() ? 1 : 0};
+        return gemm<true, true, false>(A, Bt_, g, e, stream, "tc cond wgrad");
+    }
     EpiWgrad e{dparams + L.cw_base, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
     return gemm<true, true, false>(A, Bt_, g, e, stream, "tc cond wgrad");
 }
@@ -546,8 +580,13 @@ int cond_bwd_layers(const FlowLayout& L, const void* packed, const float* dcp, i
         PlaneTensor A = pt(dcpp, L.H, B, ld_c, (long)B * ld_c, nb, L.H);
         PlaneTensor Bt = pt(featp, L.C, B, L.C, (long)B * L.C, 1, 0);
         GemmShape g{L.H, L.C, B, nb, 1, 1, 0};
-        EpiWgrad e{dparams + L.cw_base + (size_t)l0 * 4 * L.cw_stride, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
-        MHE_TRY((gemm<true, true, false>(A, Bt, g, e, s_wgrad, "tc cond wgrad")));
+        if (L.C % 8 == 0 && L.cw_stride % 4 == 0 && L.cw_base % 4 == 0) {
+            EpiWgradVec e{dparams + L.cw_base + (size_t)l0 * 4 * L.cw_stride, L.C, (long)L.cw_stride, grads_are_zero() ? 1 : 0};
+            MHE_TRY((gemm<true, true, false>(A, Bt, g, e, s_wgrad, "tc cond wgrad")));
+        } else {
+            EpiWgrad e{dparams + L.cw_base + (size_t)l0 * 4 * L.cw_stride, L.C, (long)L.cw_stride, L.C, 0, grads_are_zero()};
+            MHE_TRY((gemm<true, true, false>(A, Bt, g, e, s_wgrad, "tc cond wgrad")));
+        }
     }
     if (dfeat) {   // dfeat [B][C] += sum_idx dcp[:, idx, :] Cw[idx]   (dfeat zeroed by the caller of the pass)
         PlaneTensor A = pt(dcpp, L.H, B, ld_c, (long)B * ld_c, nb, L.H);

@@ -731,8 +731,16 @@ struct EpiSkin {
 
 // epilogue of the pose-blend GEMM: row = hypothesis (TMEM lane), 32 consecutive vertex coordinates -> pose offsets [R][kOffLd]
 struct EpiPoseOffsets {
-    static constexpr bool kDirect = true, kStaged = false, kRmw = false;
+    static constexpr bool kDirect = true, kStaged = false, kRmw = false, kTile8 = true;
     float* out;
+    struct Pre {};
+    __device__ void pre8(int, int, int, Pre&) const {}
+    __device__ void tile8(int, int, int row, int col, float* v, const Pre&, const tc::GemmShape&) const {   // 128 contiguous bytes per row and 4 lanes
+        if (col >= kOffLd) return;
+        float4* o = reinterpret_cast<float4*>(out + (long)row * kOffLd + col);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
     __device__ void operator()(int, int, int row, int col0, float* v, const tc::GemmShape&) const {
         float4* o = reinterpret_cast<float4*>(out + (long)row * kOffLd + col0);
 #pragma unroll

@@ -48,6 +48,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {   // 32 columns of this lane; the caller waits (tcgen05.wait::ld)
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -152,17 +164,21 @@ __global__ void __launch_bounds__(kThreads, 1) mano_skin_tc_kernel(Args p) {
         // ===================== v_posed loader: 16 bulk copies per tile (one row of the CTA's 128 vertices each: 1536 contiguous bytes)
         // into a ring, kVpStages tiles ahead of the epilogue - the kernel is a stream of independent 24 KB tiles and only lives at HBM
         // speed with tens of KB in flight per SM (the register-prefetch version ran at 1.3 TB/s)
-        if (lane == 0) {
+        {   // (the 17 copies of a tile are issued by 17 lanes at once: one thread issuing them back to back costs ~100 ns per copy)
             const uint32_t rowbytes = vt < 6 ? (uint32_t)kVpRow : (uint32_t)((p.ld_vp - 6 * 128 * 3) * 4);   // last tile: what is left of the row
             uint32_t it = 0;
             for (int tile = slot; tile < p.tiles; tile += p.slots, ++it) {
                 const uint32_t s = it % kVpStages, use = it / kVpStages;
-                mbar_wait(smem_u32(&bar_vp_empty[s]), (use & 1) ^ 1);
                 const int r0 = tile * kRows, nr = (p.dbg & 4) ? 0 : min(kRows, p.R - r0);
-                mbar_expect_tx(smem_u32(&bar_vp_full[s]), (rowbytes + 16) * nr);      // (one arrival + the bytes of the rows that exist)
-                if (nr > 0) bulk_load(vbase + s * kVpStage + kRows * kVpRow, p.cen + (size_t)r0 * 4, 16 * nr, smem_u32(&bar_vp_full[s]));
-                for (int rr = 0; rr < nr; ++rr)
-                    bulk_load(vbase + s * kVpStage + rr * kVpRow, p.vp + (size_t)(r0 + rr) * p.ld_vp + vt * 128 * 3, rowbytes, smem_u32(&bar_vp_full[s]));
+                if (lane == 0) {
+                    mbar_wait(smem_u32(&bar_vp_empty[s]), (use & 1) ^ 1);
+                    mbar_expect_tx(smem_u32(&bar_vp_full[s]), (rowbytes + 16) * nr);      // (one arrival + the bytes of the rows that exist)
+                }
+                __syncwarp();
+                if (lane < nr)
+                    bulk_load(vbase + s * kVpStage + lane * kVpRow, p.vp + (size_t)(r0 + lane) * p.ld_vp + vt * 128 * 3, rowbytes, smem_u32(&bar_vp_full[s]));
+                else if (lane == 16 && nr > 0)
+                    bulk_load(vbase + s * kVpStage + kRows * kVpRow, p.cen + (size_t)r0 * 4, 16 * nr, smem_u32(&bar_vp_full[s]));
             }
         }
     } else if (warp == 12) {
@@ -209,30 +225,28 @@ __global__ void __launch_bounds__(kThreads, 1) mano_skin_tc_kernel(Args p) {
             mbar_wait(smem_u32(&bar_acc_full[s]), (it >> 1) & 1);
             tcgen05_fence_after();
             const uint32_t acc = tmem + s * 256 + ((uint32_t)(q * 32) << 16) + h * 96;
+            // the 8 rows' 96 blended coefficients of this vertex: three TMEM loads in flight, one wait
+            float t[96];
+            tmem_ld32_nowait(acc, t);
+            tmem_ld32_nowait(acc + 32, t + 32);
+            tmem_ld32_nowait(acc + 64, t + 64);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(smem_u32(&bar_acc_empty[s]));      // everything read: the accumulator goes back before the stores
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {          // 4 rows = 48 accumulator columns at a time
-                float t[48];
-                tmem_ld32(acc + half * 48, t);
-                tmem_ld16(acc + half * 48 + 32, t + 32);
-                if (half == 1) {   // everything read: hand the accumulator back before the stores
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cta(smem_u32(&bar_acc_empty[s]));
-                }
+            for (int rr = 0; rr < 8; ++rr) {
+                const int r = r0 + rr;
+                if (!vok || r >= p.R) continue;
+                const float* T = t + rr * 12;
+                float* pv = vs + rr * (kVpRow / 4) + (q * 32 + lane) * 3;       // stride 3 floats across the lanes: conflict-free
+                const float p0 = pv[0], p1 = pv[1], p2 = pv[2];
+                float o[3];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int rr = half * 4 + k, r = r0 + rr;
-                    if (!vok || r >= p.R) continue;
-                    const float* T = t + k * 12;
-                    float* pv = vs + rr * (kVpRow / 4) + (q * 32 + lane) * 3;       // stride 3 floats across the lanes: conflict-free
-                    const float p0 = pv[0], p1 = pv[1], p2 = pv[2];
-                    float o[3];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-                        o[i] = (T[i * 3 + 0] * p0 + T[i * 3 + 1] * p1 + T[i * 3 + 2] * p2 + T[9 + i] - cs[rr * 4 + i]) * kMM;
-                    pv[0] = o[0]; pv[1] = o[1]; pv[2] = o[2];                        // the tile becomes the output tile in place
-                    if (tip_slot >= 0 && p.jtr) { float* dj = p.jtr + ((size_t)r * kNJ + tip_slot) * 3; dj[0] = o[0]; dj[1] = o[1]; dj[2] = o[2]; }
-                }
+                for (int i = 0; i < 3; ++i)
+                    o[i] = (T[i * 3 + 0] * p0 + T[i * 3 + 1] * p1 + T[i * 3 + 2] * p2 + T[9 + i] - cs[rr * 4 + i]) * kMM;
+                pv[0] = o[0]; pv[1] = o[1]; pv[2] = o[2];                        // the tile becomes the output tile in place
+                if (tip_slot >= 0 && p.jtr) { float* dj = p.jtr + ((size_t)r * kNJ + tip_slot) * 3; dj[0] = o[0]; dj[1] = o[1]; dj[2] = o[2]; }
             }
             __syncwarp();
             // the warp's 96 floats of every row are contiguous in the output: three fully coalesced stores per row

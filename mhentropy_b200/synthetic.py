@@ -22,3 +22,17 @@ def synthetic_batch(B, S, seed=0, dtype=torch.float32, temp=1.0, cond_dim=512, d
     z_det = torch.cat([th3, beta, logs, t], dim=1)
     return {'feat': feat.to(dtype), 'z_det': z_det.to(dtype), 'z0': z0.to(dtype),
             'crop_uv': crop_uv.to(dtype), 'vis': vis.to(dtype)}
+
+
+def det_head_state_dict(seed=5, feat_dim=512):
+    """Seeded weights for ``det_head`` (reference ``network.py:376-385``: Linear(512, 512) - ReLU - Linear(512, 16)) whose outputs land in the
+    range of a trained head: th3 ~ 0.5, beta ~ 0.02, log s ~ log 0.3, t ~ 0.1.  Shared by the golden-fixture generator (which loads them into
+    the REFERENCE's det_head) and the tests (which load them into ``MHEntHead.det_head``), so the fixture need not carry a megabyte of weights."""
+    g = torch.Generator().manual_seed(seed)
+    w0 = torch.randn(feat_dim, feat_dim, generator=g) / math.sqrt(feat_dim)
+    b0 = 0.1 * torch.randn(feat_dim, generator=g)
+    scale = torch.cat([0.5 * torch.ones(3), 0.02 * torch.ones(10), 0.1 * torch.ones(1), 0.1 * torch.ones(2)])
+    w2 = torch.randn(16, feat_dim, generator=g) / math.sqrt(feat_dim) * scale[:, None]
+    b2 = torch.zeros(16)
+    b2[13] = math.log(0.3)
+    return {'0.weight': w0, '0.bias': b0, '2.weight': w2, '2.bias': b2}

@@ -16,6 +16,8 @@ Fixtures
   mano.npz         ManoLayer forward + gradients of a fixed linear functional
   mhent_small.npz  MHEnt.get_loss fwd+bwd and MHEnt.sample with the small flow
   mhent_prod.npz   MHEnt.get_loss fwd+bwd with the production flow (B=4, N=10)
+  mhent_dethead.npz  MHEnt.get_loss fwd+bwd with the production flow AND the reference's real det_head (network.py:376-385; the other
+                   MHEnt fixtures replace it by a fixed z_det): weights set from mhentropy_b200.synthetic.det_head_state_dict(5)
   metrics.npz      MHEntLoss.forward metrics (criteria.py:47-173) and torch.topk selection (network.py:866-871) on
                    seeded (N, B, .) outputs: N = 7 with occluded / all-visible / none-visible images, and N = 1
                    (``python tests/golden/make_golden.py metrics`` regenerates only this one)
@@ -169,6 +171,34 @@ def mhent_fixture(mano, cfg, B, N, seed, with_weight_grads, with_sample):
     return fx
 
 
+def mhent_dethead_fixture(mano, B, N, seed):
+    """``MHEnt.get_loss`` with the reference's own ``det_head`` (``network.py:376-385``) in the graph: feat -> det_head -> z_det."""
+    from mhentropy_b200.synthetic import det_head_state_dict
+    model = ref_shim.build_mhent(mano, seed=seed, flow_cfg=PROD)
+    model.det_head.load_state_dict(det_head_state_dict(5))
+    batch = synthetic_batch(B, N, seed=seed + 1)
+    y = {'crop_uv': batch['crop_uv'], 'vis': batch['vis'], 'st': torch.zeros(B, 3), 'image': np.zeros(1)}
+    fx = {k: npy(v) for k, v in batch.items() if k != 'z_det'}
+    with ref_shim.cpu_mode():
+        feat = batch['feat'].clone().requires_grad_(True)
+        torch.manual_seed(seed + 2)
+        z0 = torch.randn(N * B, 45)
+        torch.manual_seed(seed + 2)
+        out = model.get_loss(feat, y, mods=['uv'])
+        loss = (-out['log_p']).mean()
+        loss.backward()
+        fx.update({'z0_train': npy(z0), 'log_p': npy(out['log_p']), 'h_q_z_giv_i': npy(out['h_q_z_giv_i']), 'loss': npy(loss),
+                   'dfeat': npy(feat.grad), 'z_det': npy(model.det_head(batch['feat']))})
+        for k, p in model.det_head.named_parameters():
+            g = npy(p.grad)
+            fx['gdet/' + k] = g if g.size <= 16 * 512 else g[:16, :64].copy()
+            fx['gdetnorm/' + k] = np.array(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        for k, p in model.q_z_giv_i.named_parameters():
+            fx['gnorm/' + k] = np.array(np.sqrt((npy(p.grad).astype(np.float64) ** 2).sum()))
+    fx['seed'] = np.array(seed)
+    return fx
+
+
 def metrics_fixture(mano):
     """Reference ``MHEntLoss.forward`` (``criteria.py:47-173``) run on seeded stand-ins for the outputs of ``MHEnt.sample``."""
     ref_shim.install_stubs(mano)
@@ -205,6 +235,10 @@ def metrics_fixture(mano):
 def main():
     assert ref_shim.reference_available(), 'needs /root/reference'
     mano = synthetic_mano(0)
+    if 'dethead' in sys.argv[1:]:
+        np.savez_compressed(os.path.join(HERE, 'mhent_dethead.npz'), **mhent_dethead_fixture(mano, B=4, N=10, seed=0))
+        print('mhent_dethead.npz', os.path.getsize(os.path.join(HERE, 'mhent_dethead.npz')))
+        return
     if 'metrics' in sys.argv[1:]:
         np.savez_compressed(os.path.join(HERE, 'metrics.npz'), **metrics_fixture(mano))
         print('metrics.npz', os.path.getsize(os.path.join(HERE, 'metrics.npz')))
@@ -218,6 +252,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'mhent_prod.npz'),
                         **mhent_fixture(mano, PROD, B=4, N=10, seed=0, with_weight_grads=False, with_sample=False))
     np.savez_compressed(os.path.join(HERE, 'metrics.npz'), **metrics_fixture(mano))
+    np.savez_compressed(os.path.join(HERE, 'mhent_dethead.npz'), **mhent_dethead_fixture(mano, B=4, N=10, seed=0))
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -276,3 +276,36 @@ def test_library_is_the_path():
         flow.forward_p(torch.randn(4, 45, device=DEV), cond=torch.randn(4, 32, device=DEV))
     assert _lib.lib().mhe_kernel_launch_count() > before
     assert _lib.lib().mhe_built_for_sm() == 100
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+@pytest.mark.parametrize('fuse', [True, False])
+def test_mhent_loss_with_real_det_head_against_golden(golden_dir, precision, fuse):
+    """MHEntHead.get_loss with ITS det_head in the graph (feat -> det_head -> z_det -> ...), against the fixture the unmodified reference
+    produced with its own det_head (network.py:376-385): log_p, dfeat (flow + det_head paths summed) and the det_head gradients."""
+    from mhentropy_b200.synthetic import det_head_state_dict
+    from _gradcheck import kink_aware_ok
+    fx = np.load(os.path.join(golden_dir, 'mhent_dethead.npz'))
+    head = MHEntHead(mano_data=synthetic_mano(0))
+    head.q_z_giv_i.load_state_dict(fo.init_state_dict(seed=int(fx['seed'])))
+    head.det_head.load_state_dict(det_head_state_dict(5))
+    head.q_z_giv_i.precision = precision
+    head.fuse_loss = fuse
+    head = head.to(DEV)
+    for p in head.parameters():
+        p.requires_grad_(True)
+    feat = T(fx['feat'], grad=True)
+    out = head.get_loss(feat, {'crop_uv': T(fx['crop_uv']), 'vis': T(fx['vis'])}, z0=T(fx['z0_train']), N=10)
+    loss = (-out['log_p']).mean()
+    loss.backward()
+    assert relerr(out['log_p'], fx['log_p']) < 1e-4
+    assert relerr(loss, fx['loss']) < 1e-4
+    ok, med, n_cross = kink_aware_ok(feat.grad, T(fx['dfeat']))
+    bar = 1e-3 if (precision == 'fp32' or n_cross == 0) else 5e-3
+    assert ok and relerr(feat.grad, fx['dfeat']) < bar
+    dh = dict(head.det_head.named_parameters())
+    assert relerr(dh['2.weight'].grad, fx['gdet/2.weight']) < 1e-3
+    assert relerr(dh['0.weight'].grad[:16, :64], fx['gdet/0.weight']) < 1e-3
+    for k in ('0.weight', '0.bias', '2.weight', '2.bias'):
+        n = float(dh[k].grad.double().norm())
+        assert abs(n - float(fx['gdetnorm/' + k])) < 1e-3 * float(fx['gdetnorm/' + k]), k

@@ -193,3 +193,24 @@ def test_metrics_oracle_against_golden(golden_dir, tag):
         if name.startswith(f'{tag}/topk'):
             kk = int(name.split('topk')[1])
             assert np.array_equal(meo.topk_hypotheses(t('log_q'), kk).numpy(), fx[name])
+
+
+def test_oracle_with_real_det_head_against_golden(golden_dir):
+    """The fixture ran the reference's OWN det_head (network.py:376-385) inside MHEnt.get_loss; the oracle composes the same head
+    (plain torch Linear - ReLU - Linear on the seeded weights) with reverse_kld and must reproduce log_p and the gradients."""
+    from mhentropy_b200.synthetic import det_head_state_dict
+    fx = load(golden_dir, 'mhent_dethead.npz')
+    sd = fo.init_state_dict(seed=int(fx['seed']))
+    sdg = {k: v.clone().requires_grad_(k != 'mask') for k, v in sd.items()}
+    dh = {k: v.clone().requires_grad_(True) for k, v in det_head_state_dict(5).items()}
+    feat = T(fx['feat'], True)
+    z_det = torch.relu(feat @ dh['0.weight'].T + dh['0.bias']) @ dh['2.weight'].T + dh['2.bias']
+    assert relerr(z_det, fx['z_det']) < 1e-5
+    out = lo.reverse_kld(sdg, mo.mano_constants(synthetic_mano(0)), feat, z_det, T(fx['z0_train']), T(fx['crop_uv']), T(fx['vis']), 10)
+    lo.mhent_loss(out['log_p']).backward()
+    assert relerr(out['log_p'], fx['log_p']) < 1e-5
+    assert relerr(feat.grad, fx['dfeat']) < 1e-4
+    assert relerr(dh['2.weight'].grad, fx['gdet/2.weight']) < 1e-4
+    assert relerr(dh['0.weight'].grad[:16, :64], fx['gdet/0.weight']) < 1e-4
+    for k in ('0.weight', '0.bias', '2.weight', '2.bias'):
+        assert abs(l2(dh[k].grad) - float(fx['gdetnorm/' + k])) < 1e-4 * float(fx['gdetnorm/' + k]), k
