@@ -260,9 +260,16 @@ int split_planes(const float* src, long src_ld, long src_batch, int rows, int co
 
 struct EpiRawStore {   // C[batch][row][col] = acc  (+= when accumulate; atomic when K is split)
     static constexpr bool kDirect = true, kStaged = false, kRmw = false;
-    float* C; long ldc; long strideC; int accumulate; int atomic;
+    float* C; long ldc; long strideC; int accumulate; int atomic; int null_epi = 0;
     __device__ void operator()(int b, int, int row, int col0, float* v, const GemmShape& g) const {
         float* p = C + (long)b * strideC + (long)row * ldc + col0;
+        if (null_epi) {   // MHE_RAW_NULL_EPI=1 (tools/bench_tc_gemm.py): the main loop alone - nothing is stored unless a value is NaN
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += v[j];
+            if (s != s) p[0] = s;
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             if (col0 + j < g.N) {
@@ -304,7 +311,8 @@ int mhe_tc_gemm_raw(const void* A, const void* B, float* C, int M, int N, int K,
     ta.row_pitch = ta.cols; tb.row_pitch = tb.cols;
     MHE_REQUIRE(ta.cols % 8 == 0 && tb.cols % 8 == 0, "tc_gemm_raw: contiguous extents must be multiples of 8");
     GemmShape g{M, N, K, batches, ksplit, 1, 1};
-    EpiRawStore e{C, N, (long)M * N, 0, ksplit > 1};
+    static const int null_epi = [] { const char* e = getenv("MHE_RAW_NULL_EPI"); return e ? atoi(e) : 0; }();
+    EpiRawStore e{C, N, (long)M * N, 0, ksplit > 1, null_epi};
     if (ksplit > 1 && cudaMemsetAsync(C, 0, (size_t)batches * M * N * sizeof(float), stream) != cudaSuccess) return MHE_ERR_CUDA;
 #define MHE_RAW(BN_, AMN_, BMN_, NP_) do { if (f16) return launch_tc_gemm<BN_, AMN_, BMN_, NP_, true>(ta, tb, g, e, stream, "tc raw"); \
                                              return launch_tc_gemm<BN_, AMN_, BMN_, NP_, false>(ta, tb, g, e, stream, "tc raw"); } while (0)

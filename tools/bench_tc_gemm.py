@@ -34,6 +34,11 @@ def bench(name, M, N, K, b, a_mn, b_mn, bn, ksplit=1, reps=40):
 
 
 if __name__ == '__main__':
+    if os.environ.get('G1_ONLY'):      # the long-batch G1 shape alone (MHE_RAW_NULL_EPI=1: main loop without the epilogue's stores)
+        for R in (8192, 32768):
+            bench('fwd G1 (K,K)', R, 512, 512, 2, False, False, 128)
+            bench('dgrad G1 (K,MN)', R, 512, 512, 2, False, True, 128)
+        sys.exit(0)
     for R in (640, 8192, 65536):
         print('--- rows', R)
         for bn in (64, 128):
