@@ -472,7 +472,9 @@ def run_ours(args):
     if rank == 0:
         exch = None
         if world > 1:
-            exch = ('bucketed NCCL all-reduce inside the captured step' if ar_inside else
+            exch = ('peer-memory exchange inside the captured step: copy-engine pushes over NVLink per backward chunk (reduce-scatter, '
+                    'mhe_sum_shards, all-gather), no NCCL kernel' if eng.px is not None else
+                    'bucketed NCCL all-reduce inside the captured step' if ar_inside else
                     ('NCCL all-gather of the conditioning factors + local weight-gradient GEMM, NCCL all-reduce of the other 30 MB'
                      if factored else 'one NCCL all-reduce of the flat 80 MB gradient + loss'))
         line = {
@@ -576,12 +578,14 @@ def other_configs(args, head, dev, flush, rank, world, peaks) -> dict:
                 'rows_per_gpu': Rn, 'ms': ms, 'value': world * Rn / (ms * 1e-3), 'unit': 'poses/s', 'scaling': 'replicas (no collective)',
                 'algorithmic_gflop': flop / 1e9, 'frac_of_bf16_sustained': flop / (ms * 1e-3) / peak}
 
+    exchange_env = os.environ.get('MHE_BENCH_EXCHANGE', 'auto')
+
     def config5(images_total, tag):
         S = 64
         Bl = images_total // world
         batch = {k: v.to(dev) for k, v in synthetic_batch(Bl, S, seed=2000 + rank).items()}
         eng = TrainStep(head, Bl, S, dev, want_verts=True, use_graph=True, planes=args.planes,
-                        exchange=os.environ.get('MHE_BENCH_EXCHANGE', 'auto'))
+                        exchange={'peer': 'auto', 'inside': 'dense'}.get(exchange_env, exchange_env))
         eng.load(**batch)
 
         def step():

@@ -193,6 +193,11 @@ int mhe_flow_grad_sqnorm(mhe_flow_shape s, const float* dparams, double* sqnorm_
 int mhe_flow_adam_step(mhe_flow_shape s, float* params, const float* dparams, float* exp_avg, float* exp_avg_sq, void* packed, int step,
                        double lr, double beta1, double beta2, double eps, double grad_scale, void* stream);
 
+/* Reduction step of the peer-memory gradient exchange (mhentropy_b200/parallel.py PeerExchange; the reference has no distributed code,
+ * SURVEY.md section 8e): acc[i] += sum over s in [0, n_src), s != skip, of land[s * stride + i] for i < n.  `land` holds the copies of this
+ * rank's shard that the other ranks pushed over NVLink (slot s = source rank), `skip` is this rank's own (unused) slot.              */
+int mhe_sum_shards(float* acc, const float* land, int n_src, int skip, size_t stride, size_t n, void* stream);
+
 /* log N(z; 0, I) + logdet per row (flows.py:320) and its gradient seeds:
  *   fwd: logp[r] = -0.5|z_r|^2 - 0.5 D ln(2 pi) + logdet_sign*logdet[r]   (logdet may be NULL)
  *   bwd: dz[r][:] = -z[r][:] * dlogp[r]                                                          */

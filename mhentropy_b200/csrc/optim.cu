@@ -77,6 +77,30 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ x
     if (threadIdx.x == 0) atomicAdd(out, s[0]);
 }
 
+// the reduction step of the peer-memory gradient exchange: acc[i] += sum over the landing slots s != skip of land[s * stride + i]
+template <bool kVec>
+__global__ void __launch_bounds__(256) sum_shards_kernel(float* __restrict__ acc, const float* __restrict__ land, int n_src, int skip,
+                                                         size_t stride, size_t n) {
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    if (kVec) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += step) {
+            float4 a = reinterpret_cast<float4*>(acc)[i];
+            for (int s = 0; s < n_src; ++s) {
+                if (s == skip) continue;
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(land + (size_t)s * stride) + i);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            reinterpret_cast<float4*>(acc)[i] = a;
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+            float a = acc[i];
+            for (int s = 0; s < n_src; ++s) if (s != skip) a += land[(size_t)s * stride + i];
+            acc[i] = a;
+        }
+    }
+}
+
 }  // namespace tcflow
 }  // namespace mhe
 
@@ -119,6 +143,17 @@ int mhe_flow_adam_step(mhe_flow_shape s, float* params, const float* dparams, fl
         }
     }
     return MHE_OK;
+}
+
+int mhe_sum_shards(float* acc, const float* land, int n_src, int skip, size_t stride, size_t n, void* stream) {
+    MHE_REQUIRE(acc && land && n_src >= 1 && n_src <= 64, "sum_shards: bad args");
+    if (n == 0) return MHE_OK;
+    const bool vec = n % 4 == 0 && stride % 4 == 0 && ((uintptr_t)acc | (uintptr_t)land) % 16 == 0;
+    const size_t work = vec ? n / 4 : n;
+    const int grid = (int)(work < (size_t)148 * 8 * 256 ? (work + 255) / 256 : 148 * 8);
+    if (vec) tcflow::sum_shards_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, land, n_src, skip, stride, n);
+    else     tcflow::sum_shards_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(acc, land, n_src, skip, stride, n);
+    return check_launch("sum shards");
 }
 
 }  // extern "C"

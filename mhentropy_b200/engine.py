@@ -138,11 +138,97 @@ class TrainStep:
             self.feat_all = torch.empty(world * B, flow.cond_dim, device=dev)
             self.xws_bytes = L.mhe_flow_cond_workspace_bytes(self.shape, world * B)
             self.xws = torch.empty(self.xws_bytes, dtype=torch.uint8, device=dev)
+        # exchange == 'peer': the gradient and the loss live in symmetric memory and are exchanged INSIDE the step by copy-engine pushes
+        # over NVLink (parallel.PeerExchange), bucketed by backward chunk - unlike NCCL's kernels the pushes take no SM from the step's
+        # cluster kernels, so chunk c's exchange runs beside the remaining chunks.  Collective: every rank constructs its engine.
+        self.px = None
+        # MHE_ENGINE_TRACE=1: timestamps of the step's phases (events recorded inside the captured graph; trace_ms() reads them)
+        self.trace = [] if os.environ.get('MHE_ENGINE_TRACE') else None
+        if exchange == 'peer' and self.world > 1:
+            from .parallel import PeerExchange
+            if self.allreduce or self.factored_exchange:
+                raise ValueError("exchange='peer' excludes allreduce= / factored_exchange=")
+            total = L.mhe_flow_param_floats(self.shape)
+            self.px = PeerExchange(total, self.dev, allreduce_group)
+            self.px.buf[:total].copy_(self.dflat)
+            self.dflat = self.px.buf[:total]
+            self.loss = self.px.buf[self.px.n_pad:self.px.n_pad + 1]
+            self.pipelined_cond_bwd = self.tc
+            self.comm = torch.cuda.Stream(self.dev)
+            buckets = [self._chunk_segments(c) for c in range(self._bwd_chunks())]
+            buckets[-1].append((self.px.n_pad, self.px.n_pad + 1))       # the loss travels with the last bucket
+            self.px.plan(buckets)
+            if self.trace is not None:
+                self.px.mark = self._mark
         self.launches_per_step = None
         self._g_fwd, self._g_bwd, self.busy = None, {}, False
 
+    def _mark(self, label):
+        """Phase mark on the current stream (diagnostic timeline, MHE_ENGINE_TRACE)."""
+        if self.trace is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True, external=True)
+        ev.record(torch.cuda.current_stream(self.dev))
+        self._trace_now.append((label, ev))
+
+    def trace_ms(self):
+        """[(label, ms since the step's start)] of the last run (MHE_ENGINE_TRACE=1)."""
+        torch.cuda.synchronize(self.dev)
+        t0 = self.trace[0][1]
+        return [(label, t0.elapsed_time(ev)) for label, ev in self.trace]
+
+    def _bwd_chunks(self) -> int:
+        return lib().mhe_flow_bwd_chunk_count(self.shape, self.R) if self.tc else 1
+
+    def _chunk_segments(self, c: int):
+        """Float ranges of the flat gradient that backward chunk ``c`` completes: coupling blocks | conditioning weights | conditioning
+        biases of its layers."""
+        import ctypes
+        L, shape = lib(), self.shape
+        total, nlayers = L.mhe_flow_param_floats(shape), shape.layers
+
+        def off(layer, which):      # float offset of (layer, net 0, which); layer == L gives the end of that region
+            if layer < nlayers:
+                return L.mhe_flow_param_offset(shape, layer, 0, which)
+            return {0: L.mhe_flow_param_offset(shape, 0, 0, 6), 6: L.mhe_flow_param_offset(shape, 0, 0, 7), 7: total}[which]
+
+        if not self.tc:
+            return [(0, total)]
+        l0, nl = ctypes.c_int(), ctypes.c_int()
+        check(L.mhe_flow_bwd_chunk_layers(shape, self.R, 0, c, ctypes.byref(l0), ctypes.byref(nl)), 'bwd_chunk_layers')
+        return [(off(l0.value, which), off(l0.value + nl.value, which)) for which in (0, 6, 7)]
+
+    def _enqueue_peer_exchange(self, L):
+        """Bucketed peer-memory exchange on the communication stream: chunk c's ranges as soon as its layers are complete."""
+        main = torch.cuda.current_stream(self.dev)
+        self.comm.wait_stream(main)
+        nchunks = self._bwd_chunks()
+        after = bool(os.environ.get('MHE_ENGINE_PEER_AFTER'))       # diagnostic: the whole exchange after the step's last kernel
+        with torch.cuda.stream(self.comm):
+            sp = _lib.stream_ptr(self.dev)
+            for c in range(nchunks):
+                if self.tc and nchunks > 1 and not after:
+                    check(L.mhe_flow_join_chunk(sp, c), 'join_chunk')
+                else:
+                    check(L.mhe_flow_join(sp), 'flow_join')
+                self._mark(f'chunk{c}.gradients_ready')
+                if c == nchunks - 1:
+                    self.comm.wait_stream(self.side4)            # the loss (reduced on a side stream)
+                self.px.reduce_bucket(c)
+        main.wait_stream(self.comm)
+
     # ------------------------------------------------------------------
     def _enqueue(self):
+        self._trace_now = []
+        self._mark('step.start')
+        try:
+            self._enqueue_body()
+        finally:
+            self._mark('step.end')
+            if self.trace is not None:
+                self.trace = self._trace_now
+
+    def _enqueue_body(self):
         L, s = lib(), _lib.stream_ptr(self.dev)
         R, B, shape, ws, wsb = self.R, self.B, self.shape, ptr(self.ws), self.ws_bytes
         z = self.z
@@ -228,6 +314,7 @@ class TrainStep:
         check(L.mhe_combine_z_bwd(ptr(self.dz), R, B, ptr(self.dx), ptr(self.dz_det), s), 'combine_z_bwd')
         torch.cuda.nvtx.range_pop()
         torch.cuda.nvtx.range_push('mhe.step.flow_backward')
+        self._mark('flow_backward.start')
         # log_q = log N(z0) - logdet  ->  dL/dlogdet = -dL/dlog_q
         # the weight-gradient GEMMs of the pass keep running on the library's streams while the conditioning backward (which only
         # needs dcp) is enqueued; mhe_flow_join() brings them back before the step ends
@@ -256,7 +343,11 @@ class TrainStep:
         torch.cuda.nvtx.range_push('mhe.step.join')
         if self.allreduce:
             self._enqueue_allreduce(L, shape, R)
+        self._mark('flow_backward.enqueued')
+        if self.px is not None:
+            self._enqueue_peer_exchange(L)
         check(L.mhe_flow_join(s), 'flow_join')
+        self._mark('flow.joined')
         if self.exchange_in_graph:              # every local gradient is complete: reduce the dense remainder
             self._enqueue_dense_remainder(L, shape)
         if self.verts is not None:
@@ -315,7 +406,7 @@ class TrainStep:
         L, shape, grp = lib(), self.shape, self.allreduce_group
         with _nvtx('mhe.step.exchange_gradients'):
             if not self.factored_exchange:
-                if self.world > 1 and not self.allreduce:
+                if self.world > 1 and not self.allreduce and self.px is None:
                     if os.environ.get('MHE_ENGINE_NO_COALESCE'):
                         dist.all_reduce(self.dflat, group=grp)
                         dist.all_reduce(self.loss, group=grp)

@@ -2,6 +2,10 @@
 [g*B/G, (g+1)*B/G) with all their S hypotheses, so the per-image N-means and the hoisted conditioning stay
 local.  The only exchange per training step is one all-reduce of the flat fp32 gradient and of the scalar loss.
 The reference has no distributed code; this is the B200 addition (NCCL over NVLink; gloo in the CPU tests).
+
+:class:`PeerExchange` is the exchange that overlaps with the step: the gradient lives in symmetric (peer-mapped) memory, shards travel
+by copy-engine pushes over NVLink / NVSwitch (no SM is taken from the step's cluster kernels, unlike NCCL's), and one small kernel of
+this library (``mhe_sum_shards``) adds the landed copies.
 """
 from __future__ import annotations
 
@@ -63,3 +67,135 @@ def cond_wgrad_from_factors(dcp_all: torch.Tensor, feat_all: torch.Tensor, hidde
     """Plain-PyTorch statement of ``mhe_flow_cond_wgrad``: (L*4, H, C) conditioning weight gradients from the (gathered) factors."""
     Bt = dcp_all.shape[0]
     return torch.einsum('bih,bc->ihc', dcp_all.reshape(Bt, -1, hidden), feat_all)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# peer-memory exchange: reduce-scatter + all-gather by copy-engine pushes
+def shard_length(n: int, world: int, align: int = 32) -> int:
+    """Floats per rank of an ``n``-float segment cut into ``world`` contiguous shards (a multiple of ``align``; trailing shards may be
+    short or empty)."""
+    return -(-(-(-n // world)) // align) * align
+
+
+def plan_peer_buckets(buckets, world: int, align: int = 32):
+    """``buckets``: list of lists of (start, stop) float ranges of the flat buffer.  Returns ``(plan, landing_floats)``: per bucket a list
+    of (start, stop, shard, landing_offset); rank p owns [start + p*shard, min(stop, start + (p+1)*shard)) of every segment and receives
+    the other ranks' copies of it at ``landing_offset`` of its landing slot for the source rank."""
+    plan, off = [], 0
+    for segs in buckets:
+        out = []
+        for a, b in segs:
+            if b < a:
+                raise ValueError('empty-negative segment')
+            sh = shard_length(b - a, world, align)
+            out.append((a, b, sh, off))
+            off += sh
+        plan.append(out)
+    return plan, off
+
+
+def shard_range(seg, rank: int):
+    """[lo, hi) of ``rank``'s shard of a planned segment (possibly empty)."""
+    a, b, sh, _ = seg
+    lo = min(b, a + rank * sh)
+    return lo, min(b, lo + sh)
+
+
+class PeerExchange:
+    """Sum-all-reduce of ranges of a flat fp32 buffer over peer-mapped memory.  Collective constructor: allocates ``buf`` (``n_floats``
+    rounded up + ``extra`` floats for scalars such as the loss) in symmetric memory.  ``plan(buckets)`` (collective) fixes the ranges
+    exchanged together; ``reduce_bucket(i)`` enqueues, on the current stream and capturable in a CUDA graph:
+
+      1. per peer p, on its own stream: copy of my values of p's shard into p's landing slot for me (cudaMemcpyAsync between peer-mapped
+         allocations = a copy engine; writes are posted, so pushes beat pulls on NVLink),
+      2. a device-side barrier over the ranks, ``mhe_sum_shards`` on my shard (+= the world-1 landed copies),
+      3. per peer: copy of my reduced shard into p's buffer, and a closing barrier.
+
+    Hazards: a landing slot is rewritten only after its owner passed the closing barrier of the previous use; a peer's buffer range is
+    overwritten in (3) only after that peer pushed its copy of it (it reached the barrier of (2)).  The caller must not write the
+    exchanged ranges again before ``reduce_bucket`` has completed in stream order."""
+
+    ALIGN = 32
+
+    def __init__(self, n_floats: int, device, group=None, extra: int = 32):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm_mem = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.dev = torch.device(device)
+        self.n = int(n_floats)
+        self.n_pad = -(-self.n // self.ALIGN) * self.ALIGN
+        self.size = self.n_pad + int(extra)
+        self.buf = symm_mem.empty(self.size, dtype=torch.float32, device=self.dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
+        self.peers = [(self.rank + i) % self.world for i in range(1, self.world)]
+        self.peer_buf = {p: self.hdl.get_buffer(p, (self.size,), torch.float32) for p in self.peers}
+        self.streams = [torch.cuda.Stream(self.dev) for _ in self.peers]
+        self.buckets, self.land = None, None
+        self.mark = None            # optional callable(label): phase marks for a timeline (engine.TrainStep.trace)
+
+    def _mark(self, label):
+        if self.mark is not None:
+            self.mark(label)
+
+    def plan(self, buckets):
+        self.buckets, self.land_floats = plan_peer_buckets(buckets, self.world, self.ALIGN)
+        self.land_floats = max(self.land_floats, self.ALIGN)
+        self.land = self._symm_mem.empty(self.world * self.land_floats, dtype=torch.float32, device=self.dev)
+        self.hland = self._symm_mem.rendezvous(self.land, self.group.group_name)
+        self.peer_land = {p: self.hland.get_buffer(p, (self.world, self.land_floats), torch.float32) for p in self.peers}
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(self.group)
+        return self
+
+    def _fan_out(self, copies_for):
+        main = torch.cuda.current_stream(self.dev)
+        used = []
+        for st, p in zip(self.streams, self.peers):
+            pairs = copies_for(p)
+            if not pairs:
+                continue
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                for dst, src in pairs:
+                    dst.copy_(src, non_blocking=True)
+            used.append(st)
+        for st in used:
+            main.wait_stream(st)
+
+    def reduce_bucket(self, i: int):
+        from . import _lib
+        segs, r = self.buckets[i], self.rank
+
+        def scatter(p):
+            out = []
+            for seg in segs:
+                lo, hi = shard_range(seg, p)
+                if hi > lo:
+                    out.append((self.peer_land[p][r, seg[3]:seg[3] + hi - lo], self.buf[lo:hi]))
+            return out
+
+        self._mark(f'bucket{i}.start')
+        self._fan_out(scatter)
+        self._mark(f'bucket{i}.scattered')
+        self.hdl.barrier(channel=0)
+        self._mark(f'bucket{i}.barrier0')
+        L, sp = _lib.lib(), _lib.stream_ptr(self.dev)
+        mine = []
+        for seg in segs:
+            lo, hi = shard_range(seg, r)
+            if hi > lo:
+                _lib.check(L.mhe_sum_shards(self.buf.data_ptr() + 4 * lo, self.land.data_ptr() + 4 * seg[3], self.world, r,
+                                            self.land_floats, hi - lo, sp), 'sum_shards')
+                mine.append((lo, hi))
+        self._mark(f'bucket{i}.summed')
+        self._fan_out(lambda p: [(self.peer_buf[p][lo:hi], self.buf[lo:hi]) for lo, hi in mine])
+        self._mark(f'bucket{i}.gathered')
+        self.hdl.barrier(channel=1)
+        self._mark(f'bucket{i}.barrier1')
+
+    def all_reduce(self):
+        """Every planned bucket, in order."""
+        for i in range(len(self.buckets)):
+            self.reduce_bucket(i)

@@ -119,3 +119,54 @@ def test_factored_cond_exchange_equals_dense_allreduce():
         assert p.exitcode == 0
     assert shape == (6, 8 * 16)
     np.testing.assert_allclose(fact, dense, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_peer_exchange_plan_reduces_every_range_once(world):
+    """The shard plan of the peer-memory exchange (parallel.PeerExchange), replayed on the host with one array per rank: pushes into the
+    landing slots, the owner's sum, pushes back.  Exchanged ranges end up as the sum over the ranks on every rank, everything else is
+    untouched, no landing slot is used twice (ragged ranges: unaligned starts, a 1-float range, an empty one)."""
+    import numpy as np
+    from mhentropy_b200.parallel import plan_peer_buckets, shard_length, shard_range
+    n = 5000
+    buckets = [[(0, 1000), (1003, 2001)], [(2001, 2002), (2500, 2500)], [(2600, n)]]
+    plan, land_floats = plan_peer_buckets(buckets, world, align=32)
+    assert shard_length(1, world) == 32 and shard_length(0, world) == 0
+    rng = np.random.default_rng(0)
+    src = [rng.standard_normal(n) for _ in range(world)]
+    buf = [s.copy() for s in src]
+    land = [np.full((world, land_floats), np.nan) for _ in range(world)]
+    used = np.zeros(land_floats, dtype=int)
+    for segs in plan:
+        for seg in segs:
+            los = [shard_range(seg, p) for p in range(world)]
+            assert los[0][0] == seg[0] and los[-1][1] == seg[1] and all(los[i][1] == los[i + 1][0] for i in range(world - 1))
+            assert all(hi - lo <= seg[2] for lo, hi in los)
+            used[seg[3]:seg[3] + seg[2]] += 1
+        for r in range(world):                      # 1. pushes
+            for p in range(world):
+                if p != r:
+                    for seg in segs:
+                        lo, hi = shard_range(seg, p)
+                        land[p][r, seg[3]:seg[3] + hi - lo] = buf[r][lo:hi]
+        for r in range(world):                      # 2. the owner's sum
+            for seg in segs:
+                lo, hi = shard_range(seg, r)
+                for s in range(world):
+                    if s != r:
+                        buf[r][lo:hi] += land[r][s, seg[3]:seg[3] + hi - lo]
+        for r in range(world):                      # 3. pushes back
+            for p in range(world):
+                if p != r:
+                    for seg in segs:
+                        lo, hi = shard_range(seg, r)
+                        buf[p][lo:hi] = buf[r][lo:hi]
+    assert used.max() == 1
+    total = np.sum(src, axis=0)
+    exchanged = np.zeros(n, dtype=bool)
+    for segs in buckets:
+        for a, b in segs:
+            exchanged[a:b] = True
+    for r in range(world):
+        np.testing.assert_allclose(buf[r][exchanged], total[exchanged], rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(buf[r][~exchanged], src[r][~exchanged])

@@ -30,11 +30,39 @@ full = synthetic_batch(B * world, S, seed=321)
 mine = {k: v.to(dev) for k, v in shard_batch(full, S, rank, world).items()}
 fro = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))  # noqa: E731
 ok = True
+# the peer-memory exchange by itself against NCCL on ragged ranges (unaligned starts, a 1-float range, an untouched gap), eager and captured
+from mhentropy_b200.parallel import PeerExchange
+n = 1_000_003
+px = PeerExchange(n, dev).plan([[(0, 1000), (1003, 50_001)], [(50_001, 50_002), (60_000, n)], [(px_tail := 1_000_032, px_tail + 1)]])
+for use_graph in (False, True):
+    g = torch.cuda.CUDAGraph() if use_graph else None
+    if g is not None:
+        with torch.cuda.graph(g):
+            px.all_reduce()
+    for it in range(3):
+        src = torch.randn(px.size, device=dev, generator=torch.Generator(device=dev).manual_seed(100 * it + rank))
+        px.buf.copy_(src)
+        want = src.clone()
+        dist.all_reduce(want)
+        want[50_002:60_000] = src[50_002:60_000]        # not exchanged
+        want[1000:1003] = src[1000:1003]
+        want[n:px_tail] = src[n:px_tail]
+        want[px_tail + 1:] = src[px_tail + 1:]
+        torch.cuda.synchronize()
+        dist.barrier()
+        g.replay() if g is not None else px.all_reduce()
+        torch.cuda.synchronize()
+        err = float((px.buf - want).abs().max())
+        if err > 1e-5:
+            ok = False
+        if rank == 0:
+            print(f'PeerExchange vs NCCL (graph={use_graph}, round {it}): max abs error {err:.2e}')
+del px, g
 results = {}
-for mode in ('dense', 'factored', 'auto'):
+for mode in ('dense', 'factored', 'auto', 'peer'):
     eng = TrainStep(head, B, S, dev, want_verts=False, use_graph=True, exchange=mode)
     eng.load(**mine)
-    for _ in range(2):
+    for _ in range(4 if mode == 'peer' else 2):
         eng.run()
         eng.exchange_gradients()
     torch.cuda.synchronize()
