@@ -201,9 +201,10 @@ class TrainStep:
     def _enqueue_peer_exchange(self, L):
         """Bucketed peer-memory exchange on the communication stream: chunk c's ranges as soon as its layers are complete."""
         main = torch.cuda.current_stream(self.dev)
-        self.comm.wait_stream(main)
         nchunks = self._bwd_chunks()
         after = bool(os.environ.get('MHE_ENGINE_PEER_AFTER'))       # diagnostic: the whole exchange after the step's last kernel
+        if after or not (self.tc and nchunks > 1):
+            self.comm.wait_stream(main)             # no per-chunk events to wait for: everything the main stream enqueued
         with torch.cuda.stream(self.comm):
             sp = _lib.stream_ptr(self.dev)
             for c in range(nchunks):
@@ -214,7 +215,7 @@ class TrainStep:
                 self._mark(f'chunk{c}.gradients_ready')
                 if c == nchunks - 1:
                     self.comm.wait_stream(self.side4)            # the loss (reduced on a side stream)
-                self.px.reduce_bucket(c)
+                self.px.reduce_bucket(c, closing=c == nchunks - 1)
         main.wait_stream(self.comm)
 
     # ------------------------------------------------------------------
@@ -324,6 +325,10 @@ class TrainStep:
             torch.cuda.current_stream(self.dev).wait_stream(self.side5)
         flags = ((7 if self.fused else 5) if self.tc else 3) | (8 if self.prepared else 0) | (16 if self.factored_exchange else 0)
         check(L.mhe_flow_set_async(flags), 'set_async')
+        if self.px is not None or self.allreduce:
+            # the communication stream forks HERE, before the pass is enqueued: it must wait for the chunks' gradient events only
+            # (mhe_flow_join_chunk), not for the main stream's position after the whole pass
+            self.comm.wait_stream(torch.cuda.current_stream(self.dev))
         try:
             if self.tc and self.pipelined_cond_bwd:
                 # ONE call: the conditioning backward is pipelined into the chunked pass
@@ -428,7 +433,6 @@ class TrainStep:
         import ctypes
         import torch.distributed as dist
         main = torch.cuda.current_stream(self.dev)
-        self.comm.wait_stream(main)
         total = L.mhe_flow_param_floats(shape)
         nlayers = shape.layers
 
@@ -438,6 +442,8 @@ class TrainStep:
             return {0: L.mhe_flow_param_offset(shape, 0, 0, 6), 6: L.mhe_flow_param_offset(shape, 0, 0, 7), 7: total}[which]
 
         nchunks = L.mhe_flow_bwd_chunk_count(shape, R) if self.tc else 1
+        if not (self.tc and nchunks > 1):
+            self.comm.wait_stream(main)
         with torch.cuda.stream(self.comm):
             sp = _lib.stream_ptr(self.dev)
             for c in range(nchunks):

@@ -118,6 +118,7 @@ class PeerExchange:
     ALIGN = 32
 
     def __init__(self, n_floats: int, device, group=None, extra: int = 32):
+        import os
         import torch.distributed._symmetric_memory as symm_mem
         self._symm_mem = symm_mem
         self.group = group if group is not None else dist.group.WORLD
@@ -131,7 +132,8 @@ class PeerExchange:
         self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
         self.peers = [(self.rank + i) % self.world for i in range(1, self.world)]
         self.peer_buf = {p: self.hdl.get_buffer(p, (self.size,), torch.float32) for p in self.peers}
-        self.streams = [torch.cuda.Stream(self.dev) for _ in self.peers]
+        k = int(os.environ.get("MHE_PEER_COPIES", 1))      # >1: measured slower (parallel copies to ONE peer contend)
+        self.streams = [[torch.cuda.Stream(self.dev) for _ in range(k)] for _ in self.peers]
         self.buckets, self.land = None, None
         self.mark = None            # optional callable(label): phase marks for a timeline (engine.TrainStep.trace)
 
@@ -150,21 +152,29 @@ class PeerExchange:
         return self
 
     def _fan_out(self, copies_for):
+        """Enqueue the (dst, src) copies of every peer on that peer's streams, forked from and joined back into the current stream.  One
+        copy engine moves ~450 GB/s over NVLink; with few peers a large copy is cut over ``copies_per_peer`` streams to fill the link."""
         main = torch.cuda.current_stream(self.dev)
         used = []
-        for st, p in zip(self.streams, self.peers):
-            pairs = copies_for(p)
-            if not pairs:
-                continue
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                for dst, src in pairs:
+        for sts, p in zip(self.streams, self.peers):
+            jobs = []
+            for dst, src in copies_for(p):
+                k = len(sts) if src.numel() >= (1 << 20) else 1
+                step = -(-src.numel() // k)
+                jobs += [(dst[j:j + step], src[j:j + step]) for j in range(0, src.numel(), step)]
+            for j, (dst, src) in enumerate(jobs):
+                st = sts[j % len(sts)]
+                if st not in used:
+                    st.wait_stream(main)
+                    used.append(st)
+                with torch.cuda.stream(st):
                     dst.copy_(src, non_blocking=True)
-            used.append(st)
         for st in used:
             main.wait_stream(st)
 
-    def reduce_bucket(self, i: int):
+    def reduce_bucket(self, i: int, closing: bool = True):
+        """``closing=False`` leaves out the closing barrier: allowed when another ``reduce_bucket`` follows in stream order before anything
+        reads the exchanged ranges or rewrites them (its barriers order this bucket's pushes as well)."""
         from . import _lib
         segs, r = self.buckets[i], self.rank
 
@@ -192,10 +202,11 @@ class PeerExchange:
         self._mark(f'bucket{i}.summed')
         self._fan_out(lambda p: [(self.peer_buf[p][lo:hi], self.buf[lo:hi]) for lo, hi in mine])
         self._mark(f'bucket{i}.gathered')
-        self.hdl.barrier(channel=1)
-        self._mark(f'bucket{i}.barrier1')
+        if closing:
+            self.hdl.barrier(channel=1)
+            self._mark(f'bucket{i}.barrier1')
 
     def all_reduce(self):
         """Every planned bucket, in order."""
         for i in range(len(self.buckets)):
-            self.reduce_bucket(i)
+            self.reduce_bucket(i, closing=i == len(self.buckets) - 1)
