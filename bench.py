@@ -281,6 +281,7 @@ def run_ours(args):
     launches_per_step = eng.launches_per_step
     value = world * R * args.steps / (total_ms * 1e-3)
     factored = eng.factored_exchange
+    peer_on = eng.px is not None
     del launches0
 
     if args.profile:
@@ -473,7 +474,7 @@ def run_ours(args):
         exch = None
         if world > 1:
             exch = ('peer-memory exchange inside the captured step: copy-engine pushes over NVLink per backward chunk (reduce-scatter, '
-                    'mhe_sum_shards, all-gather), no NCCL kernel' if eng.px is not None else
+                    'mhe_sum_shards, all-gather), no NCCL kernel' if peer_on else
                     'bucketed NCCL all-reduce inside the captured step' if ar_inside else
                     ('NCCL all-gather of the conditioning factors + local weight-gradient GEMM, NCCL all-reduce of the other 30 MB'
                      if factored else 'one NCCL all-reduce of the flat 80 MB gradient + loss'))
