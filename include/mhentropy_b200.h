@@ -118,6 +118,18 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed,
                       const float* in, int R, int B, int direction,
                       float* out, float* logdet, float* saved,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same pass when EVERY row has its own conditioning vector - feat [R][C], no hoisting possible: RealNVP.log_prob(x, logvar=feat) of the
+ * reference's scoring / p_nf use (flows.py:271-331 with cond (R, C); hand/CrossModalHand.py:278-279, 293-295) - and nothing is saved for
+ * a backward.  The projections c.j(feat) of flows.py:107-109 are not materialised (R x L*4*H fp32, 1.6 GB at 16,384 rows, written and read
+ * back) but contracted inside the coupling GEMMs: h_j = lrelu([a | feat] [W_j | Cw_j]^T + b_j + Cb_j).  Tensor-core path only (`packed`
+ * from mhe_flow_pack_weights); mhe_flow_rowcond_supported() says whether this entry applies (long batches: R above the cluster-fused
+ * limit, C a multiple of 64) - otherwise use mhe_flow_cond_fwd(B = R) + mhe_flow_pass_fwd.                                          */
+int mhe_flow_rowcond_supported(mhe_flow_shape s, int R);
+size_t mhe_flow_rowcond_workspace_bytes(mhe_flow_shape s, int R);
+int mhe_flow_pass_fwd_rowcond(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* feat,
+                              const float* in, int R, int direction, float* out, float* logdet,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* dout [R][D], dlogdet [R] (NULL = 0; multiplied by dlogdet_scale, so -1 turns dL/dlog_q of the fused
  * sampler into dL/dlogdet) -> din [R][D]; dparams (accumulate; W0,W1,W2,b2 slots), dcp [B][L*4][H] (accumulate). */
 int mhe_flow_pass_bwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,

@@ -56,6 +56,9 @@ _SIGNATURES = {
     'mhe_flow_pass_cond_bwd': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_size_t, _P, c_size_t, _P]),
     'mhe_flow_cond_wgrad': (c_int, [FlowShape, _P, _P, c_int, _P, _P, c_size_t, _P]),
     'mhe_flow_grad_sqnorm': (c_int, [FlowShape, _P, _P, _P]),
+    'mhe_flow_rowcond_supported': (c_int, [FlowShape, c_int]),
+    'mhe_flow_rowcond_workspace_bytes': (c_size_t, [FlowShape, c_int]),
+    'mhe_flow_pass_fwd_rowcond': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     'mhe_sum_shards': (c_int, [_P, _P, c_int, c_int, c_size_t, c_size_t, _P]),
     'mhe_flow_adam_step': (c_int, [FlowShape, _P, _P, _P, _P, _P, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                    ctypes.c_double, _P]),

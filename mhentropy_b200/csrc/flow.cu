@@ -359,6 +359,29 @@ int mhe_flow_cond_bwd(mhe_flow_shape s, const float* params, const void* packed,
     return MHE_OK;
 }
 
+int mhe_flow_rowcond_supported(mhe_flow_shape s, int R) {
+    if (!valid_shape(s) || R <= 0) return 0;
+    FlowLayout L(s);
+    return tcflow::rowcond_supported(L) && !fused::supported(L, R) ? 1 : 0;
+}
+size_t mhe_flow_rowcond_workspace_bytes(mhe_flow_shape s, int R) {
+    if (!valid_shape(s) || R <= 0) return 0;
+    FlowLayout L(s);
+    return tcflow::rowcond_ws_bytes(L, R);
+}
+int mhe_flow_pass_fwd_rowcond(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* feat,
+                              const float* in, int R, int direction, float* out, float* logdet,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+    MHE_REQUIRE(valid_shape(s), "pass_fwd_rowcond: bad shape");
+    MHE_REQUIRE(R >= 0 && direction >= 0 && direction <= 1, "pass_fwd_rowcond: bad R/direction");
+    if (R == 0) return MHE_OK;
+    MHE_REQUIRE(params && packed && mask && feat && in && out && workspace, "pass_fwd_rowcond: null pointer");
+    FlowLayout L(s);
+    if (!tcflow::rowcond_supported(L)) { set_error("pass_fwd_rowcond: shape outside the tensor-core path"); return MHE_ERR_UNSUPPORTED; }
+    if (workspace_bytes < tcflow::rowcond_ws_bytes(L, R)) { set_error("pass_fwd_rowcond: workspace too small"); return MHE_ERR_WORKSPACE; }
+    return tcflow::pass_fwd_rowcond(L, params, packed, mask, feat, in, R, direction, out, logdet, workspace, (cudaStream_t)stream_);
+}
+
 int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* cp,
                       const float* in, int R, int B, int direction,
                       float* out, float* logdet, float* saved,

@@ -366,13 +366,22 @@ static PlaneTensor pt(const bf16* base, int cols, int rows, long pitch, long pla
     return t;
 }
 
+static bool bn256_enabled() {
+    static const bool on = [] { const char* e = getenv("MHE_TC_BN256"); return e ? atoi(e) != 0 : true; }();
+    return on;
+}
 // BN = 64 while the grid would not fill the chip with 128-wide tiles.  F16: both operands are half planes (forward GEMMs) or both bfloat16 planes (backward GEMMs).
 template <bool A_MN, bool B_MN, bool F16, class Epi>
-static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const Epi& e, cudaStream_t s, const char* what) {
+static int gemm(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, const Epi& e, cudaStream_t s, const char* what,
+                const PlaneTensor* A2 = nullptr, const PlaneTensor* B2 = nullptr) {
     const long ctas128 = (long)cdiv(g.M, BM) * cdiv(g.N, 128) * g.batches * g.ksplit;
+    if (A2) {   // K-concatenated second operand pair (GemmShape::kb2): persistent kernel, wide tiles
+        if (bn256_enabled() && g.N % 256 == 0 && ctas128 >= 2 * 148) return launch_tc_gemm<256, A_MN, B_MN, 3, F16>(A, B, g, e, s, what, A2, B2);
+        return launch_tc_gemm<128, A_MN, B_MN, 3, F16>(A, B, g, e, s, what, A2, B2);
+    }
     // 128 x 256 tiles for the long contractions: the 128 x 128 tile streams 64 KB of operand planes per 64-deep k-block, more than an
     // SM ingests from L2 in the 768 tensor cycles the block's three products take; the wider tile moves 25 % fewer bytes per flop
-    static const bool bn256 = [] { const char* e = getenv("MHE_TC_BN256"); return e ? atoi(e) != 0 : true; }();
+    const bool bn256 = bn256_enabled();
     if (bn256 && g.N % 256 == 0 && g.K >= 256 && ctas128 >= 2 * 148) return launch_tc_gemm<256, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
     if (g.N > 64 && ctas128 >= 148) return launch_tc_gemm<128, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
     return launch_tc_gemm<64, A_MN, B_MN, 3, F16>(A, B, g, e, s, what);
@@ -606,23 +615,35 @@ struct LayerBufs {   // where one layer's activations live (workspace, or the sa
     float* st;
 };
 
+// One conditioning row per flow row (log_prob / sample with per-row features, reference flows.py:107-109 with cond (R, C)): the
+// projections c.j(cond) are NOT materialised - an R x L*4*H fp32 tensor written and read back, 1.6 GB at 16,384 rows - but contracted
+// inside the coupling GEMMs: h_j = lrelu([a | cond] [W_j | Cw_j]^T + (b_j + Cb_j)), the second operand pair of the GEMM (GemmShape::kb2).
+struct RowCond {
+    const bf16* featp;     // half planes of the conditioning rows [2][R][C]
+    const float* bias;     // [L*4][H]: Cb[idx] + b_j of the owning net, idx = layer*4 + net*2 + j
+};
+
 static int layer_nets_fwd(const FlowLayout& L, const float* params, const Packed& P, const float* cp, int R, int B, int layer,
-                          const LayerBufs& bf, cudaStream_t stream) {
+                          const LayerBufs& bf, cudaStream_t stream, const RowCond* rc = nullptr) {
     const long cp_ld = (long)L.L * 4 * L.H;
     const long RH = (long)R * L.H, RD = (long)R * kDp;
-    {   // G0: xm [R][64] x W0^T -> a0
-        PlaneTensor A = pt(bf.xm, kDp, R, kDp, RD, 1, 0);
-        PlaneTensor Bt = pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp);
-        GemmShape g{R, L.H, kDp, 2, 1, 0, 1};
-        EpiHiddenPlanes e{bf.a0, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 0) * L.H, (long)2 * L.H, B};
-        MHE_TRY((gemm<false, false, true>(A, Bt, g, e, stream, "tc flow G0")));
-    }
-    {   // G1: a0 x W1^T -> a1
-        PlaneTensor A = pt(bf.a0, L.H, R, L.H, RH, 2, 2 * RH);
-        PlaneTensor Bt = pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
-        GemmShape g{R, L.H, L.H, 2, 1, 1, 1};
-        EpiHiddenPlanes e{bf.a1, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + 1) * L.H, (long)2 * L.H, B};
-        MHE_TRY((gemm<false, false, true>(A, Bt, g, e, stream, "tc flow G1")));
+    const long HC = (long)L.H * L.C;
+    for (int j = 0; j < 2; ++j) {   // G0: xm [R][64] x W0^T -> a0;  G1: a0 x W1^T -> a1
+        PlaneTensor A = j == 0 ? pt(bf.xm, kDp, R, kDp, RD, 1, 0) : pt(bf.a0, L.H, R, L.H, RH, 2, 2 * RH);
+        PlaneTensor Bt = j == 0 ? pt(P.w0 + (size_t)layer * 2 * 2 * L.H * kDp, kDp, L.H, kDp, (long)L.H * kDp, 2, (long)2 * L.H * kDp)
+                                : pt(P.w1 + (size_t)layer * 2 * 2 * L.H * L.H, L.H, L.H, L.H, (long)L.H * L.H, 2, (long)2 * L.H * L.H);
+        GemmShape g{R, L.H, j == 0 ? kDp : L.H, 2, 1, j, 1};
+        bf16* out = j == 0 ? bf.a0 : bf.a1;
+        if (rc) {
+            PlaneTensor A2 = pt(rc->featp, L.C, R, L.C, (long)R * L.C, 1, 0);                                   // shared by both nets
+            PlaneTensor B2 = pt(P.cw + (size_t)(layer * 4 + j) * 2 * HC, L.C, L.H, L.C, HC, 2, 4 * HC);       // nets are 2 idx apart
+            g.kb2 = L.C / 64; g.a2_batch_mul = 0; g.b2_batch_mul = 1;
+            EpiHiddenPlanes e{out, L.H, RH, 2 * RH, rc->bias, 0, (long)(layer * 4 + j) * L.H, (long)2 * L.H, 1};
+            MHE_TRY((gemm<false, false, true>(A, Bt, g, e, stream, j == 0 ? "tc flow G0 rowcond" : "tc flow G1 rowcond", &A2, &B2)));
+        } else {
+            EpiHiddenPlanes e{out, L.H, RH, 2 * RH, cp, cp_ld, (long)(layer * 4 + j) * L.H, (long)2 * L.H, B};
+            MHE_TRY((gemm<false, false, true>(A, Bt, g, e, stream, j == 0 ? "tc flow G0" : "tc flow G1")));
+        }
     }
     {   // G2: a1 x W2^T + b2 -> st
         PlaneTensor A = pt(bf.a1, L.H, R, L.H, RH, 2, 2 * RH);
@@ -634,8 +655,8 @@ static int layer_nets_fwd(const FlowLayout& L, const float* params, const Packed
     return MHE_OK;
 }
 
-int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,
-             int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream) {
+static int pass_fwd_impl(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R,
+                         int B, int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream, const RowCond* rc) {
     Packed P(L, (bf16*)packed);
     Ws ws(workspace, L, R);
     Saved S(saved, L, R);
@@ -649,7 +670,7 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
         const int layer = direction == 0 ? step : L.L - 1 - step;
         const bool last = step == L.L - 1;
         LayerBufs bf = saved ? LayerBufs{S.xm(step), S.a0(step), S.a1(step), S.st(step)} : LayerBufs{ws.xm, ws.a0, ws.a1, ws.st};
-        MHE_TRY(layer_nets_fwd(L, params, P, cp, R, B, layer, bf, stream));
+        MHE_TRY(layer_nets_fwd(L, params, P, cp, R, B, layer, bf, stream, rc));
         float* y;
         if (saved) y = S.x(step + 1);
         else y = last ? out : ((x == ws.gx) ? ws.dpre : ws.gx);
@@ -662,6 +683,37 @@ int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const
     }
     if (saved) MHE_TRY(cuda_ok(cudaMemcpyAsync(out, S.x(L.L), row_bytes, cudaMemcpyDeviceToDevice, stream), "copy out"));
     return MHE_OK;
+}
+int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,
+             int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream) {
+    return pass_fwd_impl(L, params, packed, mask, cp, in, R, B, direction, out, logdet, saved, workspace, stream, nullptr);
+}
+
+// ---- per-row conditioning folded into the coupling GEMMs (no saved state: inference / scoring) ----------------
+__global__ void cond_bias_kernel(const float* __restrict__ params, float* __restrict__ bias, int H, int n, size_t cb_base, size_t cb_stride,
+                                 size_t blk, size_t ob0, size_t ob1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int idx = i / H, col = i - idx * H;
+    bias[i] = params[cb_base + (size_t)idx * cb_stride + col] + params[(size_t)(idx >> 1) * blk + ((idx & 1) ? ob1 : ob0) + col];
+}
+bool rowcond_supported(const FlowLayout& L) { return supported(L) && L.C % 64 == 0 && L.C >= 64; }
+static size_t up1k(size_t n) { return (n + 1023) / 1024 * 1024; }
+size_t rowcond_ws_bytes(const FlowLayout& L, int R) {
+    return up1k(Ws::bytes(L, R)) + up1k((size_t)2 * R * L.C * 2) + up1k((size_t)L.L * 4 * L.H * 4) + 1024;
+}
+int pass_fwd_rowcond(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* feat, const float* in, int R,
+                     int direction, float* out, float* logdet, void* workspace, cudaStream_t stream) {
+    if (R <= 0) return MHE_OK;
+    uint8_t* extra = (uint8_t*)workspace + up1k(Ws::bytes(L, R));
+    bf16* featp = (bf16*)extra;
+    float* bias = (float*)(extra + up1k((size_t)2 * R * L.C * 2));
+    MHE_TRY(split_planes(feat, L.C, 0, R, L.C, nullptr, featp, R, L.C, 2, 1, true, stream));
+    const int n = L.L * 4 * L.H;
+    cond_bias_kernel<<<cdiv(n, 256), 256, 0, stream>>>(params, bias, L.H, n, L.cb_base, L.cb_stride, L.blk, L.ob0, L.ob1);
+    MHE_TRY(check_launch("cond bias"));
+    RowCond rc{featp, bias};
+    return pass_fwd_impl(L, params, packed, mask, nullptr, in, R, 1, direction, out, logdet, nullptr, workspace, stream, &rc);
 }
 
 // The backward reads the hidden activations the forward saved (no recomputation on this path).

@@ -110,6 +110,11 @@ int cond_bwd(const FlowLayout& L, const float* params, const void* packed, const
              float* dfeat, void* ws, cudaStream_t stream);
 int pass_fwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* in, int R, int B,
              int direction, float* out, float* logdet, float* saved, void* workspace, cudaStream_t stream);
+// forward pass with ONE conditioning row per flow row, the projections contracted inside the coupling GEMMs (flow_tc.cu RowCond)
+bool rowcond_supported(const FlowLayout& L);
+size_t rowcond_ws_bytes(const FlowLayout& L, int R);
+int pass_fwd_rowcond(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* feat, const float* in, int R,
+                     int direction, float* out, float* logdet, void* workspace, cudaStream_t stream);
 int pass_bwd(const FlowLayout& L, const float* params, const void* packed, const float* mask, const float* cp, const float* saved, int R, int B,
              int direction, const float* dout, const float* dlogdet, float dlogdet_scale, float* din, float* dparams, float* dcp,
              void* workspace, cudaStream_t stream);

@@ -195,6 +195,12 @@ struct GemmShape {
     int kfold = 1;     // consecutive batches contracted into ONE accumulator per CTA (batches % kfold == 0; the epilogue sees batch / kfold)
     int stages = 0;    // operand ring depth (0 = as deep as shared memory allows).  Short contractions with large outputs run better with a
                        // shallow ring: several CTAs share an SM and one's epilogue overlaps the others' loads and MMAs
+    // K-concatenation (persistent kernel, ksplit == kfold == 1): after the K / 64 k-blocks of (A, B), `kb2` more k-blocks are read from a
+    // SECOND operand pair (A2, B2: same majorness, planes and element type) into the same accumulator: C = A B^T + A2 B2^T without
+    // materialising either product (the conditioning projection folded into the coupling GEMM, flow_tc.cu pass_fwd_rowcond)
+    int kb2 = 0;
+    int a2_batch_mul = 0;
+    int b2_batch_mul = 0;
 };
 
 template <int BN, int NPL>
@@ -400,7 +406,8 @@ int stages_for(const char* what, int requested, int max_stages);
 // dominated by the per-CTA fixed cost (barrier init, TMEM allocation, first TMA round trip, epilogue drain) in the one-tile kernel.
 template <int BN, bool A_MN, bool B_MN, int NPAIR, bool F16, class Epi>
 __global__ void __launch_bounds__(kThreadsP, 1)
-tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, GemmShape g, Epi epi,
+tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                          const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, GemmShape g, Epi epi,
                           int tiles_n, int tiles_m, int tiles_total, int l2_prefetch_distance) {
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
     using Plan = SmemPlan<BN, NPL>;
@@ -423,6 +430,10 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        if (g.kb2 > 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB2) : "memory");
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(2 * BN) : "memory");
@@ -447,7 +458,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         T.kb_begin = T.split * kb_per;
         const int kb_end = min(kb_total, T.kb_begin + kb_per);
         T.nkb1 = max(kb_end - T.kb_begin, 0);
-        T.nkb = T.nkb1 * g.kfold;
+        T.nkb = T.nkb1 * g.kfold + g.kb2;
         return T;
     };
 
@@ -493,19 +504,24 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                     mbar_wait(smem_u32(&bar_empty[s]), ((q / NS) & 1) ^ 1);
                     const uint32_t full = smem_u32(&bar_full[s]);
                     mbar_expect_tx(full, Plan::kStageBytes);
-                    const int k0 = (T.kb_begin + i % T.nkb1) * BK;
-                    const int bsrc = T.batch * g.kfold + i / T.nkb1;
+                    const int nmain = T.nkb1 * g.kfold;
+                    const bool tail = i >= nmain;                         // k-blocks of the second operand pair (GemmShape::kb2)
+                    const int k0 = tail ? (i - nmain) * BK : (T.kb_begin + i % T.nkb1) * BK;
+                    const int bsrc = tail ? T.batch : T.batch * g.kfold + i / T.nkb1;
+                    const CUtensorMap* mA = tail ? &mapA2 : &mapA;
+                    const CUtensorMap* mB = tail ? &mapB2 : &mapB;
+                    const int ba = bsrc * (tail ? g.a2_batch_mul : g.a_batch_mul), bb = bsrc * (tail ? g.b2_batch_mul : g.b_batch_mul);
 #pragma unroll
                     for (int p = 0; p < NPL; ++p) {
-                        if (!A_MN) tma_load_4d(stage_a(s, p), &mapA, full, k0, T.m0, p, bsrc * g.a_batch_mul);
+                        if (!A_MN) tma_load_4d(stage_a(s, p), mA, full, k0, T.m0, p, ba);
                         else {
 #pragma unroll
-                            for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, &mapA, full, T.m0 + 64 * j, k0, p, bsrc * g.a_batch_mul);
+                            for (int j = 0; j < BM / 64; ++j) tma_load_4d(stage_a(s, p) + j * 8192, mA, full, T.m0 + 64 * j, k0, p, ba);
                         }
-                        if (!B_MN) tma_load_4d(stage_b(s, p), &mapB, full, k0, T.n0, p, bsrc * g.b_batch_mul);
+                        if (!B_MN) tma_load_4d(stage_b(s, p), mB, full, k0, T.n0, p, bb);
                         else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, &mapB, full, T.n0 + 64 * j, k0, p, bsrc * g.b_batch_mul);
+                            for (int j = 0; j < BN / 64; ++j) tma_load_4d(stage_b(s, p) + j * 8192, mB, full, T.n0 + 64 * j, k0, p, bb);
                         }
                     }
                 }
@@ -655,8 +671,13 @@ bool tc_persistent_enabled(const char* what);
 const CUtensorMap* cached_map(const PlaneTensor& t, int box_rows, int* status);
 
 template <int BN, bool A_MN, bool B_MN, int NPAIR, bool F16, class Epi>
-inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const GemmShape& g, const Epi& epi, cudaStream_t stream, const char* what) {
+inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const GemmShape& g, const Epi& epi, cudaStream_t stream, const char* what,
+                          const PlaneTensor* A2 = nullptr, const PlaneTensor* B2 = nullptr) {
     if (g.M <= 0 || g.N <= 0 || g.batches <= 0) return MHE_OK;
+    if ((g.kb2 > 0) != (A2 != nullptr && B2 != nullptr) || (g.kb2 > 0 && (g.ksplit != 1 || g.kfold != 1))) {
+        set_error("%s: a second operand pair needs kb2 > 0, both tensors, ksplit == kfold == 1", what);
+        return MHE_ERR_INVALID_ARG;
+    }
     constexpr int NPL = NPAIR == 1 ? 1 : 2;
     using Plan = SmemPlan<BN, NPL>;
     int st = MHE_OK;
@@ -664,6 +685,13 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
     if (st != MHE_OK) return st;
     const CUtensorMap* mb = cached_map(B, B_MN ? 64 : BN, &st);
     if (st != MHE_OK) return st;
+    const CUtensorMap *ma2 = ma, *mb2 = mb;
+    if (g.kb2 > 0) {
+        ma2 = cached_map(*A2, A_MN ? 64 : BM, &st);
+        if (st != MHE_OK) return st;
+        mb2 = cached_map(*B2, B_MN ? 64 : BN, &st);
+        if (st != MHE_OK) return st;
+    }
     auto kern = tc_gemm_kernel<BN, A_MN, B_MN, NPAIR, F16, Epi>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -678,7 +706,7 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
     GemmShape gs = g;
     gs.stages = stages_for(what, g.stages, Plan::kStages);
     {   // a ring deeper than the contraction is wasted shared memory: short contractions leave room for several CTAs per SM
-        const int kb_total = cdiv(g.K, BK), kb_per = cdiv(kb_total, g.ksplit > 0 ? g.ksplit : 1) * (g.kfold > 0 ? g.kfold : 1);
+        const int kb_total = cdiv(g.K, BK), kb_per = cdiv(kb_total, g.ksplit > 0 ? g.ksplit : 1) * (g.kfold > 0 ? g.kfold : 1) + g.kb2;
         if (gs.stages > kb_per) gs.stages = kb_per > 0 ? kb_per : 1;
     }
     const size_t smem = (size_t)gs.stages * Plan::kStageBytes + 1024;
@@ -701,12 +729,16 @@ inline int launch_tc_gemm(const PlaneTensor& A, const PlaneTensor& B, const Gemm
         const int nctas = tiles_total < 148 * per_sm ? tiles_total : 148 * per_sm;
         static const int pf_env = [] { const char* e = getenv("MHE_TC_L2_PREFETCH"); return e ? atoi(e) : 0; }();
         // (worth it only for contractions long enough to run ahead in; the short ones are epilogue-bound)
-        const int pf = cdiv(g.K, BK) * (g.kfold > 0 ? g.kfold : 1) >= 4 ? pf_env : 0;
-        if (launch_chain(pkern, dim3(nctas), dim3(kThreadsP), smem, stream, *ma, *mb, gs, epi, (int)grid.x, (int)grid.y, tiles_total, pf) != cudaSuccess) {
+        const int pf = (cdiv(g.K, BK) * (g.kfold > 0 ? g.kfold : 1) >= 4 && g.kb2 == 0) ? pf_env : 0;
+        if (launch_chain(pkern, dim3(nctas), dim3(kThreadsP), smem, stream, *ma, *mb, *ma2, *mb2, gs, epi, (int)grid.x, (int)grid.y, tiles_total, pf) != cudaSuccess) {
             set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));
             return MHE_ERR_CUDA;
         }
         return check_launch(what);
+    }
+    if (g.kb2 > 0) {
+        set_error("%s: the second operand pair needs the persistent kernel", what);
+        return MHE_ERR_UNSUPPORTED;
     }
     if (launch_chain(kern, grid, dim3(kThreads), smem, stream, *ma, *mb, gs, epi) != cudaSuccess) {
         set_error("%s: launch failed: %s", what, cudaGetErrorString(cudaGetLastError()));

@@ -70,8 +70,15 @@ class TrainStep:
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         cpf = L.mhe_flow_cp_floats_per_image(self.shape)
         # static inputs
-        self.feat, self.z_det, self.z0 = f(B, flow.cond_dim), f(B, 16), f(R, D)
-        self.crop_uv, self.vis = f(B, 42), f(B, 21)
+        # (one contiguous block, every input a 128-byte aligned view of it: a batch collated into staging() travels in ONE host-to-device copy)
+        self._input_shapes = {'feat': (B, flow.cond_dim), 'z_det': (B, 16), 'z0': (R, D), 'crop_uv': (B, 42), 'vis': (B, 21)}
+        self._input_offsets, n_in = {}, 0
+        for k, shp in self._input_shapes.items():
+            self._input_offsets[k] = n_in
+            n_in += -(-(shp[0] * shp[1]) // 32) * 32
+        self.inputs = torch.zeros(n_in, device=dev, dtype=torch.float32)
+        self._stage = None
+        self.feat, self.z_det, self.z0, self.crop_uv, self.vis = (self._input_view(self.inputs, k) for k in self._input_shapes)
         # forward state
         self.cp, self.x, self.logdet, self.log_q = f(B, cpf), f(R, D), f(R), f(R)
         self.z, self.jtr = f(R, 61), f(R, 21, 3)
@@ -555,6 +562,23 @@ class TrainStep:
         if key not in self._g_bwd:
             self._g_bwd[key] = self._capture(lambda: self._enqueue_backward_only(dflat))
         return self._g_bwd[key]
+
+    def _input_view(self, block, k):
+        shp, o = self._input_shapes[k], self._input_offsets[k]
+        return block[o:o + shp[0] * shp[1]].view(shp)
+
+    def staging(self) -> dict:
+        """Pinned host views (feat, z_det, z0, crop_uv, vis) of ONE staging block laid out like the device inputs: a data loader collates
+        the batch straight into them and :meth:`load_staged` moves it with a single host-to-device copy."""
+        if self._stage is None:
+            self._stage_block = torch.zeros(self.inputs.numel(), dtype=torch.float32).pin_memory()
+            self._stage = {k: self._input_view(self._stage_block, k) for k in self._input_shapes}
+        return self._stage
+
+    def load_staged(self, non_blocking=True):
+        """One copy of the whole staging block (see :meth:`staging`) into the static input buffers."""
+        self.staging()
+        self.inputs.copy_(self._stage_block, non_blocking=non_blocking)
 
     def load(self, feat, z_det, z0, crop_uv, vis, non_blocking=True):
         """Copy one batch (host or device tensors) into the static input buffers."""

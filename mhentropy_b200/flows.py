@@ -14,6 +14,7 @@ path).  CUDA tensors always take the kernel path and fail loudly if the library 
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -420,7 +421,32 @@ class RealNVP(nn.Module):
         flat = self._flat_for_autograd(cond.device)
         return _CondFn.apply(cond.float(), flat, self._shape, self.packed_weights(cond.device), self)
 
+    def _rowcond_applies(self, inp, cond) -> bool:
+        """One conditioning row per flow row, nothing to differentiate, long batch on the tensor-core path: the pass that contracts the
+        conditioning projections inside the coupling GEMMs (``mhe_flow_pass_fwd_rowcond``; ``MHE_FLOW_ROWCOND=0`` disables it)."""
+        if cond is None or cond.shape[0] != inp.shape[0] or inp.shape[0] == 0 or os.environ.get('MHE_FLOW_ROWCOND') == '0':
+            return False
+        if torch.is_grad_enabled() and (inp.requires_grad or cond.requires_grad or any(p.requires_grad for p, _, _, _ in self._slots)):
+            return False
+        return self.packed_weights(inp.device) is not None and bool(lib().mhe_flow_rowcond_supported(self._shape, inp.shape[0]))
+
+    def _pass_rowcond(self, inp, cond, direction):
+        dev = inp.device
+        flat, packed = self.flat_parameters(dev), self.packed_weights(dev)
+        inp, feat = inp.float().contiguous(), cond.float().contiguous()
+        _lib.require_cuda_f32(inp, feat, flat, self.mask)
+        R = inp.shape[0]
+        out = torch.empty_like(inp)
+        logdet = torch.empty(R, device=dev, dtype=torch.float32)
+        wsb = lib().mhe_flow_rowcond_workspace_bytes(self._shape, R)
+        ws = _lib.WORKSPACE.get(wsb, dev)
+        check(lib().mhe_flow_pass_fwd_rowcond(self._shape, ptr(flat), ptr(packed), ptr(self.mask), ptr(feat), ptr(inp), R, direction, ptr(out),
+                                              ptr(logdet), ptr(ws), wsb, stream_ptr(dev)), 'mhe_flow_pass_fwd_rowcond')
+        return out, logdet
+
     def _pass(self, inp, cond, direction, cp=None, images=None):
+        if cp is None and self._rowcond_applies(inp, cond):
+            return self._pass_rowcond(inp, cond, direction)
         flat = self._flat_for_autograd(inp.device)
         packed = self.packed_weights(inp.device)
         if cp is None:

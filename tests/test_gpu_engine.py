@@ -316,3 +316,27 @@ def test_fused_loss_node_general_downstream_and_accumulation():
     for k in g0:
         assert rel(g1[k], g0[k]) < 1e-4, k
     assert all(not e.busy for pool in head._fused_pool.values() for e in pool)
+
+
+def test_staged_single_copy_load_equals_per_tensor_load():
+    """TrainStep.staging() + load_staged() (one host-to-device copy of the pinned block) gives the same step as load() of five tensors; an
+    odd shape exercises the padded segment offsets."""
+    head = MHEntHead(mano_data=synthetic_mano(0))
+    head.q_z_giv_i.load_state_dict(fo.init_state_dict(seed=0))
+    head.q_z_giv_i.precision = 'bf16x3'
+    head = head.to(DEV)
+    B, S = 7, 9
+    batch = synthetic_batch(B, S, seed=23)
+    eng = TrainStep(head, B, S, DEV, want_verts=False, use_graph=True)
+    eng.load(**{k: v.to(DEV) for k, v in batch.items()})
+    l0 = eng.run().clone()
+    g0, f0 = eng.dflat.clone(), eng.dfeat.clone()
+    for v in eng.staging().values():
+        assert v.is_pinned()
+    eng.inputs.zero_()
+    for k, v in batch.items():
+        eng.staging()[k].copy_(v)
+    eng.load_staged()
+    l1 = eng.run().clone()
+    torch.cuda.synchronize()
+    assert rel(l1, l0) < 1e-6 and rel(eng.dflat, g0) < 1e-5 and rel(eng.dfeat, f0) < 1e-5      # (atomic bias sums: not bit-stable)

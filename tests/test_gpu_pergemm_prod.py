@@ -127,6 +127,43 @@ def test_pergemm_log_prob_16384_rows(flow_and_sd):
     print(f'per-GEMM log_prob 16384 rows: round trip {float((xr.cpu() - x).abs().max()):.2e}')
 
 
+def test_rowcond_pass_matches_materialised_conditioning_and_oracle(flow_and_sd, monkeypatch):
+    """Per-row conditioning without a backward runs `mhe_flow_pass_fwd_rowcond` (the projections contracted inside the coupling GEMMs as
+    a second operand pair).  At a ragged 4,290 rows, both directions: equal to the pass on materialised projections within fp32 rounding
+    of a different summation order, and to the fp64 oracle within the north-star tolerances."""
+    flow, sd = flow_and_sd
+    R = 4290
+    L = _lib.lib()
+    assert L.mhe_flow_rowcond_supported(flow._shape, R) == 1 and L.mhe_flow_rowcond_supported(flow._shape, 640) == 0
+    g = torch.Generator().manual_seed(21)
+    feat, x = torch.randn(R, 512, generator=g), 0.5 * torch.randn(R, 45, generator=g)
+    sd64 = fo.cast_state_dict(sd, torch.float64)
+    with torch.no_grad():
+        fc, xc = feat.to(DEV), x.to(DEV)
+        assert flow._rowcond_applies(xc, fc)
+        n0 = L.mhe_kernel_launch_count()
+        got = {d: flow._pass(xc, fc, d) for d in (0, 1)}
+        n_row = L.mhe_kernel_launch_count() - n0
+        monkeypatch.setenv('MHE_FLOW_ROWCOND', '0')
+        assert not flow._rowcond_applies(xc, fc)
+        n0 = L.mhe_kernel_launch_count()
+        mat = {d: flow._pass(xc, fc, d) for d in (0, 1)}
+        n_mat = L.mhe_kernel_launch_count() - n0
+        monkeypatch.delenv('MHE_FLOW_ROWCOND')
+        torch.cuda.synchronize()
+        assert n_row > 0 and n_mat > 0
+        for d in (0, 1):
+            assert float((got[d][0] - mat[d][0]).abs().max()) < 2e-4 and float((got[d][1] - mat[d][1]).abs().max()) < 2e-3
+        z_ref, lp_ref = fo.log_prob(sd64, x.double(), feat.double(), return_z=True)
+        z, ld = got[1]
+        lp = -0.5 * (z.double() ** 2).sum(1) - 0.5 * 45 * np.log(2 * np.pi) + ld.double()
+        assert float((z.cpu().double() - z_ref).abs().max()) < 5e-4 and relmax(lp, lp_ref) < 1e-4
+        x_ref = fo.forward_p(sd64, x.double(), feat.double())
+        assert float((got[0][0].cpu().double() - x_ref).abs().max()) < 5e-4
+    # a tensor that needs gradients keeps the differentiable path
+    assert not flow._rowcond_applies(xc.clone().requires_grad_(True), fc)
+
+
 def test_wide_mask_takes_the_per_gemm_path_and_matches_the_oracle():
     """A 30/15 coupling split is wider than the cluster-fused kernels' 24-dim exchange: it must run (on the per-GEMM path) and agree with
     the oracle evaluated with the same mask - not silently drop dims."""
