@@ -1219,9 +1219,14 @@ struct BwdAux {
     int last_chunks = 0, last_L = 0, last_direction = 0;   // geometry of the last pass (join_chunk / chunk_layers)
     bool ok = false;
 };
-static BwdAux& bwd_aux() {
-    static BwdAux a;
-    static bool tried = false;
+static BwdAux& bwd_aux() {   // one context per device: streams and events belong to the device that was current when they were created
+    constexpr int kMaxDevices = 16;
+    static BwdAux ctx[kMaxDevices];
+    static bool tried_dev[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    BwdAux& a = ctx[dev];
+    bool& tried = tried_dev[dev];
     if (!tried) {
         tried = true;
         bool ok = true;

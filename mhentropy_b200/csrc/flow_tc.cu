@@ -430,14 +430,19 @@ int wgrad_kmajor(const PlaneTensor& A, const PlaneTensor& B, GemmShape g, float*
 // dW GEMMs are off the critical path of the backward (nothing downstream in the pass reads them), so they are
 // forked onto an internal stream, layer by layer, and joined at the end of the pass.  Fork/join uses events, which
 // also makes the branches parallel nodes when the caller captures the pass into a CUDA graph.
+constexpr int kMaxDevices = 16;
 struct Aux {
     cudaStream_t stream[2] = {nullptr, nullptr};   // [0]: the HxH gradient, [1]: the two thin ones
     cudaEvent_t ready[64] = {}, done[2][64] = {};
     bool ok = false;
 };
-static Aux& aux_ctx() {
-    static Aux a;
-    static bool tried = false;
+static Aux& aux_ctx() {   // one context per device: streams and events belong to the device that was current when they were created
+    static Aux ctx[kMaxDevices];
+    static bool tried_dev[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    Aux& a = ctx[dev];
+    bool& tried = tried_dev[dev];
     if (!tried) {
         tried = true;
         bool ok = cudaStreamCreateWithFlags(&a.stream[0], cudaStreamNonBlocking) == cudaSuccess &&
