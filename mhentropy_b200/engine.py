@@ -19,6 +19,11 @@ from ._lib import check, lib, ptr
 from .losses import MHEntHead
 
 
+def _env_on(name: str) -> bool:
+    """An environment switch: set and neither empty nor '0'."""
+    return os.environ.get(name, '') not in ('', '0')
+
+
 def factored_exchange_pays(shape, B: int, world: int) -> bool:
     """Factored vs dense exchange of the conditioning weight gradient: the factors all-gathered per rank are
     world x B x (L*4*H + C) floats, the dense gradient L*4*H*C.  The gather also feeds a contraction over world x B images on every
@@ -115,10 +120,10 @@ class TrainStep:
         self.graph = None
         self.use_graph = use_graph
         # re-plane the weight-gradient operands right after the forward pass (see _enqueue); measured slower, off by default
-        self.prepare_ahead = prepare_ahead or bool(os.environ.get('MHE_ENGINE_PREPARE_AHEAD'))
+        self.prepare_ahead = prepare_ahead or _env_on('MHE_ENGINE_PREPARE_AHEAD')
         # mhe_flow_pass_cond_bwd (conditioning backward pipelined into the chunked pass) instead of the two calls: measured equal
         # within 1 % on one GPU (0.557 vs 0.551 ms); it is what a bucketed gradient all-reduce needs (chunk gradients complete early)
-        self.pipelined_cond_bwd = pipelined_cond_bwd or bool(os.environ.get('MHE_ENGINE_PIPELINED_COND_BWD'))
+        self.pipelined_cond_bwd = pipelined_cond_bwd or _env_on('MHE_ENGINE_PIPELINED_COND_BWD')
         # data parallelism: sum-all-reduce of the flat gradient and the loss INSIDE the step, bucketed by backward
         # chunk - the gradients of a chunk's layers are exchanged while the remaining chunks still run (mhe_flow_join_chunk)
         self.allreduce = bool(allreduce) and torch.distributed.is_available() and torch.distributed.is_initialized() \
@@ -136,7 +141,7 @@ class TrainStep:
         # exchange_in_graph (EXPERIMENTAL, off): the factored exchange is enqueued inside the (captured) step, so the gather and the global
         # conditioning GEMM run beside the last weight gradients instead of after the step - 0.638 vs 0.670 ms/step on 2 GPUs in bench.py, but
         # tools/check_factored_exchange.py hung with it (two engines in one process); not the default until that is understood
-        self.exchange_in_graph = bool(exchange_in_graph or os.environ.get('MHE_ENGINE_EXCHANGE_IN_GRAPH')) and self.factored_exchange
+        self.exchange_in_graph = bool(exchange_in_graph or _env_on('MHE_ENGINE_EXCHANGE_IN_GRAPH')) and self.factored_exchange
         if self.factored_exchange:
             world = self.world
             self.comm = torch.cuda.Stream(self.dev)
@@ -150,7 +155,7 @@ class TrainStep:
         # cluster kernels, so chunk c's exchange runs beside the remaining chunks.  Collective: every rank constructs its engine.
         self.px = None
         # MHE_ENGINE_TRACE=1: timestamps of the step's phases (events recorded inside the captured graph; trace_ms() reads them)
-        self.trace = [] if os.environ.get('MHE_ENGINE_TRACE') else None
+        self.trace = [] if _env_on('MHE_ENGINE_TRACE') else None
         if exchange == 'peer' and self.world > 1:
             from .parallel import PeerExchange
             if self.allreduce or self.factored_exchange:
@@ -209,7 +214,7 @@ class TrainStep:
         """Bucketed peer-memory exchange on the communication stream: chunk c's ranges as soon as its layers are complete."""
         main = torch.cuda.current_stream(self.dev)
         nchunks = self._bwd_chunks()
-        after = bool(os.environ.get('MHE_ENGINE_PEER_AFTER'))       # diagnostic: the whole exchange after the step's last kernel
+        after = _env_on('MHE_ENGINE_PEER_AFTER')       # diagnostic: the whole exchange after the step's last kernel
         if after or not (self.tc and nchunks > 1):
             self.comm.wait_stream(main)             # no per-chunk events to wait for: everything the main stream enqueued
         with torch.cuda.stream(self.comm):
@@ -374,7 +379,7 @@ class TrainStep:
         self.comm.wait_stream(main)
         with torch.cuda.stream(self.comm):
             # (grouped NCCL launch: each separate call costs ~15-20 us)
-            if not os.environ.get('MHE_ENGINE_NO_COALESCE'):
+            if not _env_on('MHE_ENGINE_NO_COALESCE'):
                 with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
                     dist.all_gather_into_tensor(self.dcp_all, self.dcp, group=grp)
                     dist.all_gather_into_tensor(self.feat_all, self.feat, group=grp)
@@ -398,7 +403,7 @@ class TrainStep:
         self.comm.wait_stream(main)
         self.comm.wait_stream(self.side4)           # the loss (reduced on a side stream)
         with torch.cuda.stream(self.comm):
-            if not os.environ.get('MHE_ENGINE_NO_COALESCE'):
+            if not _env_on('MHE_ENGINE_NO_COALESCE'):
                 with dist._coalescing_manager(group=grp, device=self.dev, async_ops=False):
                     dist.all_reduce(self.dflat[:cw0], group=grp)
                     dist.all_reduce(self.dflat[cw1:], group=grp)
@@ -419,7 +424,7 @@ class TrainStep:
         with _nvtx('mhe.step.exchange_gradients'):
             if not self.factored_exchange:
                 if self.world > 1 and not self.allreduce and self.px is None:
-                    if os.environ.get('MHE_ENGINE_NO_COALESCE'):
+                    if _env_on('MHE_ENGINE_NO_COALESCE'):
                         dist.all_reduce(self.dflat, group=grp)
                         dist.all_reduce(self.loss, group=grp)
                     else:       # one grouped NCCL launch for the 80 MB and the scalar
@@ -462,7 +467,7 @@ class TrainStep:
                     check(L.mhe_flow_join(sp), 'flow_join')
                 # coupling blocks | conditioning weights | conditioning biases of layers [l0, l0 + nl): one grouped NCCL launch
                 segs = [self.dflat[off(l0.value, which):off(l0.value + nl.value, which)] for which in (0, 6, 7)]
-                if os.environ.get('MHE_ENGINE_NO_COALESCE'):
+                if _env_on('MHE_ENGINE_NO_COALESCE'):
                     for seg in segs:
                         dist.all_reduce(seg, group=self.allreduce_group)
                 else:
