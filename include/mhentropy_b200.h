@@ -123,8 +123,8 @@ int mhe_flow_pass_fwd(mhe_flow_shape s, const float* params, const void* packed,
  * reference's scoring / p_nf use (flows.py:271-331 with cond (R, C); hand/CrossModalHand.py:278-279, 293-295) - and nothing is saved for
  * a backward.  The projections c.j(feat) of flows.py:107-109 are not materialised (R x L*4*H fp32, 1.6 GB at 16,384 rows, written and read
  * back) but contracted inside the coupling GEMMs: h_j = lrelu([a | feat] [W_j | Cw_j]^T + b_j + Cb_j).  Tensor-core path only (`packed`
- * from mhe_flow_pack_weights); mhe_flow_rowcond_supported() says whether this entry applies (long batches: R above the cluster-fused
- * limit, C a multiple of 64) - otherwise use mhe_flow_cond_fwd(B = R) + mhe_flow_pass_fwd.                                          */
+ * from mhe_flow_pack_weights); mhe_flow_rowcond_supported() says whether this entry applies and pays (C a multiple of 64; R >= 1536 by
+ * measurement, MHE_ROWCOND_MIN_ROWS) - otherwise use mhe_flow_cond_fwd(B = R) + mhe_flow_pass_fwd.                                   */
 int mhe_flow_rowcond_supported(mhe_flow_shape s, int R);
 size_t mhe_flow_rowcond_workspace_bytes(mhe_flow_shape s, int R);
 int mhe_flow_pass_fwd_rowcond(mhe_flow_shape s, const float* params, const void* packed, const float* mask, const float* feat,

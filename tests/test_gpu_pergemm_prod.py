@@ -135,6 +135,7 @@ def test_rowcond_pass_matches_materialised_conditioning_and_oracle(flow_and_sd, 
     R = 4290
     L = _lib.lib()
     assert L.mhe_flow_rowcond_supported(flow._shape, R) == 1 and L.mhe_flow_rowcond_supported(flow._shape, 640) == 0
+    assert L.mhe_flow_rowcond_supported(flow._shape, 2048) == 1      # (MHE_ROWCOND_MIN_ROWS: 1536 by default)
     g = torch.Generator().manual_seed(21)
     feat, x = torch.randn(R, 512, generator=g), 0.5 * torch.randn(R, 45, generator=g)
     sd64 = fo.cast_state_dict(sd, torch.float64)

@@ -16,7 +16,7 @@ flow.load_state_dict(fo.init_state_dict(seed=0), strict=True)
 flow = flow.to(DEV)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
 g = torch.Generator().manual_seed(3)
-for R in (8192, 16384, 65536):
+for R in [int(r) for r in os.environ.get('ROWS', '8192,16384,65536').split(',')]:
     x, feat = (0.5 * torch.randn(R, 45, generator=g)).to(DEV), torch.randn(R, 512, generator=g).to(DEV)
     res = {}
     for mode in ('0', '1', '0', '1'):
