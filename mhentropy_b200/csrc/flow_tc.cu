@@ -40,6 +40,12 @@ struct EpiHiddenPlanes {   // a = lrelu(acc + cp[row % B][...]) -> planes out[ba
         const float4* c = reinterpret_cast<const float4*>(cp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride + col);
         p.a = __ldg(c); p.b = __ldg(c + 1);
     }
+    typedef const float* RowRef;                         // the row's conditioning terms (the modulo once per tile, not once per chunk)
+    __device__ RowRef pre_row(int b, int row) const { return cp + (long)(row % B) * cp_ld + cp_off + (long)b * cp_bstride; }
+    __device__ void pre8r(RowRef r, int col, Pre& p) const {
+        const float4* c = reinterpret_cast<const float4*>(r + col);
+        p.a = __ldg(c); p.b = __ldg(c + 1);
+    }
     __device__ void tile8(int b, int, int row, int col, float* v, const Pre& pr, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
         const float4 t0 = pr.a, t1 = pr.b;
         v[0] = lrelu(v[0] + t0.x); v[1] = lrelu(v[1] + t0.y); v[2] = lrelu(v[2] + t0.z); v[3] = lrelu(v[3] + t0.w);
@@ -86,6 +92,9 @@ struct EpiActGradPlanes {   // dh = acc * lrelu'(act) -> planes.  (dcp = sum ove
     __device__ void pre8(int b, int row, int col, Pre& p) const {
         p.a = __ldg(reinterpret_cast<const uint4*>(act_hi + (long)b * act_batch_stride + (long)row * ld + col));
     }
+    typedef const bf16* RowRef;
+    __device__ RowRef pre_row(int b, int row) const { return act_hi + (long)b * act_batch_stride + (long)row * ld; }
+    __device__ void pre8r(RowRef r, int col, Pre& p) const { p.a = __ldg(reinterpret_cast<const uint4*>(r + col)); }
     __device__ void tile8(int b, int, int row, int col, float* v, const Pre& pr, const GemmShape&) const {   // 8 columns of one row (see tc_gemm.cuh)
         const uint4 t = pr.a;
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
