@@ -609,6 +609,27 @@ def other_configs(args, head, dev, flush, rank, world, peaks) -> dict:
         torch.cuda.empty_cache()
         return r
 
+    def config1_gpu():
+        Bs, Ss = 8, 10
+        batch = {k: v.to(dev) for k, v in synthetic_batch(Bs, Ss, seed=3000 + rank).items()}
+        eng = TrainStep(head, Bs, Ss, dev, want_verts=True, use_graph=True, planes=args.planes, exchange='dense')
+        eng.load(**batch)
+
+        def step():
+            eng.run()
+            if world > 1:
+                eng.exchange_gradients()
+
+        ms = timeit(step, 10, warm=3)
+        assert torch.isfinite(eng.loss).all()
+        r = {'workload': "BASELINE configs[0] shape on the GPU (the reference's CPU-runnable case; its CPU number is config1_cpu): training step "
+                         'B=8 x S=10 per GPU', 'rows_per_gpu': Bs * Ss, 'ms': ms, 'value': world * Bs * Ss / (ms * 1e-3), 'unit': UNIT,
+             'launches_per_step': int(eng.launches_per_step)}
+        del eng
+        torch.cuda.empty_cache()
+        return r
+
+    guarded('config1_gpu', config1_gpu)
     guarded('config3', config3)
     guarded('config4', config4)
     if world == 1:
